@@ -1,0 +1,231 @@
+"""ctypes binding of ``libdaliid_b200.so`` (C-ABI declared in ``include/daliid_b200.h``).
+
+There is no CPU fallback and no alternative backend: if the shared library has not been
+built (``python -c 'import __graft_entry__ as g; g.build()'`` or ``make -C
+daliid_b200/csrc``) or no sm_100 GPU is visible, every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libdaliid_b200.so")
+
+# ---- constants mirrored from include/daliid_b200.h -------------------------------
+ABI_VERSION = 1
+OK, ERR_INVALID, ERR_CUDA, ERR_NO_VALID_QUERY, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3, -4, -5
+METRICS = {"cosine": 0, "sqeuclidean": 1, "euclidean": 2, "dot": 3}
+PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2}
+ACCUMS = {"cy_f32": 0, "py_f64": 1}
+K_NORMALIZE, K_DISTMAT, K_RANK_COUNT, K_RANK_FINALIZE, K_TOPK, K_FUSE, K_RANK_GATHER = range(7)
+KERNEL_SLOTS = {"normalize": 0, "distmat": 1, "rank_count": 2, "rank_finalize": 3, "topk": 4,
+                "fuse": 5, "rank_gather": 6}
+CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy handle
+
+NO_VALID_MSG = "Error: all query identities do not appear in gallery"
+
+
+class DaliError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"daliid_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+_lock = threading.Lock()
+
+c_f32p = ctypes.POINTER(ctypes.c_float)
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+c_u32p = ctypes.POINTER(ctypes.c_uint32)
+c_i64p = ctypes.POINTER(ctypes.c_int64)
+c_f64p = ctypes.POINTER(ctypes.c_double)
+c_vp = ctypes.c_void_p
+i64 = ctypes.c_int64
+ci = ctypes.c_int
+
+# name -> (restype, argtypes); data pointers are passed as void* (host or device address)
+_SIGNATURES = {
+    "dali_abi_version": (ci, []),
+    "dali_ctx_create": (ci, [ctypes.POINTER(c_vp), ci]),
+    "dali_ctx_destroy": (None, [c_vp]),
+    "dali_ctx_set_stream": (ci, [c_vp, c_vp]),
+    "dali_ctx_get_stream": (c_vp, [c_vp]),
+    "dali_last_error": (ctypes.c_char_p, [c_vp]),
+    "dali_strerror": (ctypes.c_char_p, [ci]),
+    "dali_ctx_timing_enable": (ci, [c_vp, ci]),
+    "dali_ctx_timing_reset": (ci, [c_vp]),
+    "dali_ctx_timing_read": (ci, [c_vp, ci, ctypes.POINTER(ci), c_f32p]),
+    "dali_ctx_launch_count": (i64, [c_vp]),
+    "dali_normalize_f32": (ci, [c_vp, c_vp, i64, i64, i64, c_vp, i64, c_vp]),
+    "dali_distmat_f32": (ci, [c_vp, c_vp, i64, c_vp, i64, i64, ci, ci, ci, c_vp, i64]),
+    "dali_fuse_f32": (ci, [c_vp, ctypes.POINTER(c_vp), ci, ctypes.POINTER(c_vp),
+                           ctypes.POINTER(c_vp), c_vp, i64, i64, i64]),
+    "dali_eval_rank_f32": (ci, [c_vp, c_vp, i64, i64, i64, c_i32p, c_i32p, c_i32p, c_i32p, ci, ci,
+                                c_f32p, c_f64p, c_f64p, c_i32p, c_i64p]),
+    "dali_eval_features_f32": (ci, [c_vp, c_vp, i64, c_vp, i64, i64, c_i32p, c_i32p, c_i32p,
+                                    c_i32p, ci, ci, ci, ci, ci, c_f32p, c_f64p, c_f64p, c_i32p,
+                                    c_i64p, c_vp, i64]),
+    "dali_topk_f32": (ci, [c_vp, c_vp, i64, i64, i64, ci, ci, c_vp, c_vp, c_vp]),
+    "dali_topk_features_f32": (ci, [c_vp, c_vp, i64, c_vp, i64, i64, ci, ci, ci, ci, ci,
+                                    ctypes.c_int32, c_vp, c_vp]),
+    "dali_rank_plan_create": (ci, [c_vp, c_i32p, c_i32p, c_i32p, c_i32p, i64, i64,
+                                   ctypes.POINTER(c_vp)]),
+    "dali_rank_plan_destroy": (None, [c_vp]),
+    "dali_rank_plan_num_matches": (i64, [c_vp]),
+    "dali_rank_gather_keys": (ci, [c_vp, c_vp, c_vp, i64, i64, i64, c_vp]),
+    "dali_rank_count": (ci, [c_vp, c_vp, c_vp, i64, i64, i64, c_vp, c_vp]),
+    "dali_rank_finalize": (ci, [c_vp, c_vp, c_vp, c_vp, ci, ci, c_f32p, c_f64p, c_f64p, c_i32p,
+                                c_i64p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def load():
+    """Load the shared library; raise loudly if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise ImportError(
+                    f"{LIB_PATH} is missing: build it with `python -c \"import __graft_entry__ as g; "
+                    "g.build()\"` or `make -C daliid_b200/csrc`. daliid_b200 has no CPU fallback.")
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in _SIGNATURES.items():
+                fn = getattr(lib, name)  # AttributeError if the .so does not export it
+                fn.restype = res
+                fn.argtypes = args
+            if lib.dali_abi_version() != ABI_VERSION:
+                raise ImportError("libdaliid_b200.so ABI version mismatch; rebuild it")
+            _lib = lib
+    return _lib
+
+
+class Context:
+    """Owns one ``dali_ctx`` (one per device per host thread)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = c_vp()
+        rc = self.lib.dali_ctx_create(ctypes.byref(h), int(device))
+        if rc != OK:
+            msg = self.lib.dali_last_error(None)
+            raise DaliError(rc, (msg or b"").decode() or self.lib.dali_strerror(rc).decode())
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dali_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover - interpreter shutdown order
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc == OK:
+            return
+        msg = (self.lib.dali_last_error(self.h) or b"").decode()
+        if rc == ERR_NO_VALID_QUERY:
+            raise AssertionError(NO_VALID_MSG)
+        if rc == ERR_INVALID:
+            raise ValueError(f"daliid_b200: {msg}")
+        raise DaliError(rc, msg or self.lib.dali_strerror(rc).decode())
+
+    def attach_torch_stream(self):
+        """Issue this context's work on torch's current stream of the device."""
+        import torch
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        self.lib.dali_ctx_set_stream(self.h, c_vp(s if s else CUDA_STREAM_LEGACY))
+
+    # ---- timing -----------------------------------------------------------------
+    def timing_enable(self, on=True):
+        self.check(self.lib.dali_ctx_timing_enable(self.h, 1 if on else 0))
+
+    def timing_reset(self):
+        self.check(self.lib.dali_ctx_timing_reset(self.h))
+
+    def timing_read(self):
+        out = {}
+        for name, slot in KERNEL_SLOTS.items():
+            n, ms = ci(0), ctypes.c_float(0)
+            self.check(self.lib.dali_ctx_timing_read(self.h, slot, ctypes.byref(n), ctypes.byref(ms)))
+            out[name] = (n.value, ms.value)
+        return out
+
+    def launch_count(self):
+        return int(self.lib.dali_ctx_launch_count(self.h))
+
+
+_tls = threading.local()
+
+
+def get_ctx(device=None) -> Context:
+    """Per-thread, per-device cached context.  ``device=None`` -> torch's current device."""
+    if device is None:
+        import torch
+        if not torch.cuda.is_available():
+            load()  # surfaces a missing library first
+            raise DaliError(ERR_CUDA, "no CUDA device visible (daliid_b200 has no CPU fallback)")
+        device = torch.cuda.current_device()
+    cache = getattr(_tls, "ctx", None)
+    if cache is None:
+        cache = _tls.ctx = {}
+    if device not in cache:
+        cache[device] = Context(device)
+    return cache[device]
+
+
+# ---- argument marshalling ---------------------------------------------------------
+class Buf:
+    """A host or device fp32/int32 buffer together with the object keeping it alive."""
+
+    __slots__ = ("ptr", "keep", "device", "shape", "ld")
+
+    def __init__(self, ptr, keep, device, shape, ld):
+        self.ptr, self.keep, self.device, self.shape, self.ld = ptr, keep, device, shape, ld
+
+
+def as_matrix(x, dtype=np.float32, name="array") -> Buf:
+    """numpy / torch (cpu or cuda) 2-D array -> pointer + leading dimension (row-major)."""
+    try:
+        import torch
+    except ImportError:  # pragma: no cover
+        torch = None
+    tdtype = None
+    if torch is not None:
+        tdtype = {np.float32: torch.float32, np.int32: torch.int32}[dtype]
+    if torch is not None and isinstance(x, torch.Tensor):
+        t = x.detach()
+        if t.dim() != 2:
+            raise ValueError(f"{name} must be 2-D")
+        if t.dtype != tdtype:
+            t = t.to(tdtype)
+        if t.numel() and t.stride(1) != 1:
+            t = t.contiguous()
+        if t.numel() and t.stride(0) < t.shape[1]:
+            t = t.contiguous()
+        ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
+        ld = max(ld, t.shape[1], 1)
+        dev = t.device.index if t.is_cuda else None
+        return Buf(t.data_ptr(), t, dev, tuple(t.shape), ld)
+    a = np.asarray(x)
+    if a.ndim != 2:
+        raise ValueError(f"{name} must be 2-D")
+    if a.dtype != dtype or not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a, dtype=dtype)
+    return Buf(a.ctypes.data, a, None, a.shape, max(a.shape[1], 1))
+
+
+def as_i32(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a), dtype=np.int32)
+
+
+def p_i32(a):
+    return a.ctypes.data_as(c_i32p)

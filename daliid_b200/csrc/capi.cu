@@ -1,0 +1,905 @@
+// extern "C" surface of libdaliid_b200 (include/daliid_b200.h): context, staging of host
+// operands, the rank plan (gallery CSR by identity), orchestration of the kernels and the
+// host-side tail of the CMC/mAP reduction in both upstream accumulation modes.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+
+#include "common.cuh"
+
+namespace dali {
+
+int launch_prep(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx, float *plane0,
+                float *plane1, int64_t ldo, int64_t d_pad, int64_t rows_pad, int do_normalize,
+                int round_mode, float *norms, float *sq);
+
+int set_err(dali_ctx *ctx, int code, const std::string &msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+int ws_ensure(dali_ctx *ctx, int slot, size_t bytes, void **out) {
+  DevBuf &b = ctx->ws[slot];
+  if (bytes > b.cap) {
+    if (b.p) {
+      cudaStreamSynchronize(ctx->stream);
+      cudaFree(b.p);
+      b.p = nullptr;
+      b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+      want = bytes;
+      e = cudaMalloc(&b.p, want);
+    }
+    if (e != cudaSuccess) {
+      b.p = nullptr;
+      return set_err(ctx, DALI_ERR_NOMEM,
+                     std::string("cudaMalloc of ") + std::to_string(bytes) + " bytes: " +
+                         cudaGetErrorString(e));
+    }
+    b.cap = want;
+  }
+  *out = b.p;
+  return DALI_OK;
+}
+
+KTimer::KTimer(dali_ctx *c, int s) : ctx(c), slot(s) {
+  ctx->launches++;
+  if (!ctx->timing) return;
+  auto get = [&]() {
+    cudaEvent_t e;
+    if (!ctx->t_pool.empty()) {
+      e = ctx->t_pool.back();
+      ctx->t_pool.pop_back();
+    } else {
+      cudaEventCreate(&e);
+    }
+    return e;
+  };
+  e0 = get();
+  e1 = get();
+  cudaEventRecord(e0, ctx->stream);
+}
+
+KTimer::~KTimer() {
+  if (!e0) return;
+  cudaEventRecord(e1, ctx->stream);
+  ctx->t_pending.push_back({slot, {e0, e1}});
+}
+
+static void timing_drain(dali_ctx *ctx) {
+  if (ctx->t_pending.empty()) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &pe : ctx->t_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pe.second.first, pe.second.second) == cudaSuccess) {
+      ctx->t_ms[pe.first] += ms;
+      ctx->t_launches[pe.first] += 1;
+    }
+    ctx->t_pool.push_back(pe.second.first);
+    ctx->t_pool.push_back(pe.second.second);
+  }
+  ctx->t_pending.clear();
+}
+
+static bool is_device_ptr(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Returns a device pointer holding rows x cols fp32 with leading dimension *ld_out.
+static int stage_in(dali_ctx *ctx, int slot, const float *p, int64_t rows, int64_t cols, int64_t ld,
+                    const float **out, int64_t *ld_out) {
+  if (rows == 0 || cols == 0 || is_device_ptr(p)) {
+    *out = p;
+    *ld_out = ld;
+    return DALI_OK;
+  }
+  void *d = nullptr;
+  int rc = ws_ensure(ctx, slot, sizeof(float) * rows * cols, &d);
+  if (rc) return rc;
+  if (ld == cols) {
+    DALI_CUDA_OK(ctx, cudaMemcpyAsync(d, p, sizeof(float) * rows * cols, cudaMemcpyHostToDevice,
+                                      ctx->stream));
+  } else {
+    DALI_CUDA_OK(ctx, cudaMemcpy2DAsync(d, sizeof(float) * cols, p, sizeof(float) * ld,
+                                        sizeof(float) * cols, rows, cudaMemcpyHostToDevice,
+                                        ctx->stream));
+  }
+  *out = static_cast<const float *>(d);
+  *ld_out = cols;
+  return DALI_OK;
+}
+
+static int pinned_ensure(dali_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->pinned_cap) return DALI_OK;
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  ctx->pinned = nullptr;
+  ctx->pinned_cap = 0;
+  DALI_CUDA_OK(ctx, cudaMallocHost(&ctx->pinned, bytes + 4096));
+  ctx->pinned_cap = bytes + 4096;
+  return DALI_OK;
+}
+
+static inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------
+// numpy's pairwise summation (ndarray.sum / np.mean on a contiguous float64 vector),
+// evaluated over a vector of length n whose only non-zero entries are (pos[i], val[i]),
+// pos ascending.  Zero terms leave a non-negative partial sum unchanged, so they are
+// skipped; the association of the remaining additions is numpy's
+// (8 interleaved lanes per <=128 block, recursive halving above, n<8 sequential).
+// ---------------------------------------------------------------------------
+static double np_pairwise_sparse(const int64_t *pos, const double *val, int64_t cnt, int64_t lo,
+                                 int64_t n) {
+  if (cnt == 0) return 0.0;
+  if (n < 8) {
+    double r = -0.0;
+    for (int64_t i = 0; i < cnt; ++i) r += val[i];
+    return r;
+  }
+  if (n <= 128) {
+    double r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int64_t body = n - (n % 8);
+    int64_t i = 0;
+    for (; i < cnt && pos[i] - lo < body; ++i) r[(pos[i] - lo) & 7] += val[i];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < cnt; ++i) res += val[i];
+    return res;
+  }
+  int64_t n2 = n / 2;
+  n2 -= n2 % 8;
+  const int64_t *mid = std::lower_bound(pos, pos + cnt, lo + n2);
+  const int64_t c1 = mid - pos;
+  return np_pairwise_sparse(pos, val, c1, lo, n2) +
+         np_pairwise_sparse(mid, val + c1, cnt - c1, lo + n2, n - n2);
+}
+
+static double np_pairwise_dense(const double *a, int64_t n) {
+  if (n < 8) {
+    double r = -0.0;
+    for (int64_t i = 0; i < n; ++i) r += a[i];
+    return r;
+  }
+  if (n <= 128) {
+    double r[8];
+    for (int k = 0; k < 8; ++k) r[k] = a[k];
+    int64_t i = 8;
+    for (; i < n - (n % 8); i += 8)
+      for (int k = 0; k < 8; ++k) r[k] += a[i + k];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += a[i];
+    return res;
+  }
+  int64_t n2 = n / 2;
+  n2 -= n2 % 8;
+  return np_pairwise_dense(a, n2) + np_pairwise_dense(a + n2, n - n2);
+}
+
+// ---------------------------------------------------------------------------
+// Host tail of the reduction: device results -> cmc / mAP in the chosen semantics.
+// ---------------------------------------------------------------------------
+static int finish_on_host(dali_ctx *ctx, const dali_rank_plan *plan, const int32_t *d_ranks,
+                          const float *d_ap, const int32_t *d_first, const int32_t *d_cmc,
+                          int max_rank, int accum_mode, float *cmc, double *mAP, double *ap_opt,
+                          int32_t *first_rank_opt, int64_t *num_valid_opt) {
+  const int64_t Q = plan->Q;
+  const bool need_ranks = accum_mode == DALI_ACCUM_PY_F64;
+  const size_t b_ap = sizeof(float) * Q, b_first = sizeof(int32_t) * Q,
+               b_cmc = sizeof(int32_t) * (max_rank + 1),
+               b_ranks = need_ranks ? sizeof(int32_t) * plan->M : 0;
+  int rc = pinned_ensure(ctx, b_ap + b_first + b_cmc + b_ranks + 64);
+  if (rc) return rc;
+  char *h = static_cast<char *>(ctx->pinned);
+  float *h_ap = reinterpret_cast<float *>(h);
+  int32_t *h_first = reinterpret_cast<int32_t *>(h + b_ap);
+  int32_t *h_cmc = reinterpret_cast<int32_t *>(h + b_ap + b_first);
+  int32_t *h_ranks = reinterpret_cast<int32_t *>(h + b_ap + b_first + b_cmc);
+  if (Q) {
+    DALI_CUDA_OK(ctx, cudaMemcpyAsync(h_ap, d_ap, b_ap, cudaMemcpyDeviceToHost, ctx->stream));
+    DALI_CUDA_OK(ctx, cudaMemcpyAsync(h_first, d_first, b_first, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  DALI_CUDA_OK(ctx, cudaMemcpyAsync(h_cmc, d_cmc, b_cmc, cudaMemcpyDeviceToHost, ctx->stream));
+  if (b_ranks)
+    DALI_CUDA_OK(ctx, cudaMemcpyAsync(h_ranks, d_ranks, b_ranks, cudaMemcpyDeviceToHost, ctx->stream));
+  DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+
+  const int64_t nvalid = h_cmc[max_rank];
+  if (num_valid_opt) *num_valid_opt = nvalid;
+  if (first_rank_opt)
+    for (int64_t q = 0; q < Q; ++q) first_rank_opt[q] = h_first[q];
+  if (nvalid == 0) {
+    if (ap_opt)
+      for (int64_t q = 0; q < Q; ++q) ap_opt[q] = std::numeric_limits<double>::quiet_NaN();
+    return set_err(ctx, DALI_ERR_NO_VALID_QUERY,
+                   "Error: all query identities do not appear in gallery");
+  }
+  // CMC: cumulative histogram of first-match ranks; both upstream variants end with a
+  // float32 count divided by num_valid_q in float32.
+  const float nvf = static_cast<float>(nvalid);
+  int64_t run = 0;
+  for (int r = 0; r < max_rank; ++r) {
+    run += h_cmc[r];
+    cmc[r] = static_cast<float>(run) / nvf;
+  }
+  if (accum_mode == DALI_ACCUM_CY_F32) {
+    float s = 0.f;  // sequential float sum in query order (invalid queries add 0)
+    for (int64_t q = 0; q < Q; ++q) s += h_ap[q];
+    *mAP = static_cast<double>(s / nvf);
+    if (ap_opt)
+      for (int64_t q = 0; q < Q; ++q)
+        ap_opt[q] = h_first[q] < 0 ? std::numeric_limits<double>::quiet_NaN()
+                                   : static_cast<double>(h_ap[q]);
+  } else {
+    std::vector<double> aps;
+    aps.reserve(nvalid);
+    std::vector<int64_t> pos;
+    std::vector<double> val;
+    for (int64_t q = 0; q < Q; ++q) {
+      const int nv = plan->h_nv[q];
+      if (nv == 0) {
+        if (ap_opt) ap_opt[q] = std::numeric_limits<double>::quiet_NaN();
+        continue;
+      }
+      const int64_t o = plan->h_off[q];
+      pos.resize(nv);
+      val.resize(nv);
+      for (int k = 0; k < nv; ++k) {
+        const int64_t r = h_ranks[o + k];
+        pos[k] = r - 1;
+        val[k] = static_cast<double>(k + 1) / static_cast<double>(r);
+      }
+      const int64_t kept = plan->G - plan->h_njunk[q];
+      const double sum = 0.0 + np_pairwise_sparse(pos.data(), val.data(), nv, 0, kept);
+      const double ap = sum / static_cast<double>(nv);
+      aps.push_back(ap);
+      if (ap_opt) ap_opt[q] = ap;
+    }
+    *mAP = (0.0 + np_pairwise_dense(aps.data(), static_cast<int64_t>(aps.size()))) /
+           static_cast<double>(aps.size());
+  }
+  return DALI_OK;
+}
+
+static int check_ctx(dali_ctx *ctx) {
+  if (!ctx) return DALI_ERR_INVALID;
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) return set_err(ctx, DALI_ERR_CUDA, cudaGetErrorString(e));
+  return DALI_OK;
+}
+
+// Prepared operand planes for the contraction kernels.
+struct Prepared {
+  float *planes = nullptr;  // [npl][rows_pad][Dp]
+  float *sq = nullptr;      // [rows] sum of squares (euclidean metrics)
+  int64_t rows_pad = 0, Dp = 0;
+  int npl = 1;
+};
+
+static int prepare_operand(dali_ctx *ctx, int ws_in, int ws_planes, int ws_sq, const float *x,
+                           int64_t n, int64_t D, int metric, int precision, int normalize,
+                           Prepared *out) {
+  const float *xd = nullptr;
+  int64_t ldx = D;
+  int rc = stage_in(ctx, ws_in, x, n, D, D, &xd, &ldx);
+  if (rc) return rc;
+  out->Dp = round_up(D, 32);
+  out->rows_pad = round_up(std::max<int64_t>(n, 1), 256);
+  out->npl = precision == DALI_PREC_TF32X3 ? 2 : 1;
+  void *pl = nullptr;
+  rc = ws_ensure(ctx, ws_planes, sizeof(float) * out->npl * out->rows_pad * out->Dp, &pl);
+  if (rc) return rc;
+  out->planes = static_cast<float *>(pl);
+  const bool need_sq = metric == DALI_METRIC_SQEUCLIDEAN || metric == DALI_METRIC_EUCLIDEAN;
+  if (need_sq) {
+    void *s = nullptr;
+    rc = ws_ensure(ctx, ws_sq, sizeof(float) * std::max<int64_t>(n, 1), &s);
+    if (rc) return rc;
+    out->sq = static_cast<float *>(s);
+  }
+  return launch_prep(ctx, xd, n, D, ldx, out->planes,
+                     out->npl == 2 ? out->planes + out->rows_pad * out->Dp : nullptr, out->Dp,
+                     out->Dp, out->rows_pad, normalize, precision == DALI_PREC_FP32 ? 0 : 1, nullptr,
+                     out->sq);
+}
+
+static int contract(dali_ctx *ctx, const Prepared &a, const Prepared &b, int64_t Q, int64_t G,
+                    int metric, int precision, float *out, int64_t ld) {
+  if (precision == DALI_PREC_FP32)
+    return launch_distmat_simt(ctx, a.planes, b.planes, Q, G, a.Dp, a.Dp, b.Dp, metric, a.sq, b.sq,
+                               out, ld);
+  return launch_distmat_umma(ctx, a.planes, b.planes, Q, G, a.Dp, a.rows_pad, b.rows_pad,
+                             precision == DALI_PREC_TF32X3, metric, a.sq, b.sq, out, ld);
+}
+
+static int check_metric_prec(dali_ctx *ctx, int metric, int precision) {
+  if (metric < DALI_METRIC_COSINE || metric > DALI_METRIC_DOT)
+    return set_err(ctx, DALI_ERR_INVALID, "unknown metric");
+  if (precision < DALI_PREC_FP32 || precision > DALI_PREC_TF32)
+    return set_err(ctx, DALI_ERR_INVALID, "unknown precision");
+  return DALI_OK;
+}
+
+// rank stage on a device-resident matrix, given a plan
+static int rank_from_device(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist, int64_t ld,
+                            int max_rank, int accum_mode, float *cmc, double *mAP, double *ap_opt,
+                            int32_t *first_rank_opt, int64_t *num_valid_opt) {
+  void *keys = nullptr, *counts = nullptr;
+  int rc = ws_ensure(ctx, WS_KEYS, sizeof(uint32_t) * std::max<int64_t>(plan->M, 1), &keys);
+  if (rc) return rc;
+  rc = ws_ensure(ctx, WS_COUNTS, sizeof(int32_t) * std::max<int64_t>(plan->M, 1), &counts);
+  if (rc) return rc;
+  rc = launch_rank_gather(ctx, plan, dist, ld, 0, plan->G, static_cast<uint32_t *>(keys));
+  if (rc) return rc;
+  rc = launch_rank_count(ctx, plan, dist, ld, 0, plan->G, static_cast<const uint32_t *>(keys),
+                         static_cast<int32_t *>(counts));
+  if (rc) return rc;
+  return dali_rank_finalize(ctx, plan, static_cast<const uint32_t *>(keys),
+                            static_cast<const int32_t *>(counts), max_rank, accum_mode, cmc, mAP,
+                            ap_opt, first_rank_opt, num_valid_opt);
+}
+
+}  // namespace dali
+
+using namespace dali;
+
+extern "C" {
+
+int dali_abi_version(void) { return DALI_ABI_VERSION; }
+
+const char *dali_strerror(int code) {
+  switch (code) {
+    case DALI_OK: return "ok";
+    case DALI_ERR_INVALID: return "invalid argument";
+    case DALI_ERR_CUDA: return "CUDA failure or no sm_100 device";
+    case DALI_ERR_NO_VALID_QUERY: return "Error: all query identities do not appear in gallery";
+    case DALI_ERR_UNSUPPORTED: return "unsupported";
+    case DALI_ERR_NOMEM: return "out of device memory";
+    default: return "unknown error";
+  }
+}
+
+static thread_local std::string g_create_err;
+
+int dali_ctx_create(dali_ctx **out, int device) {
+  if (!out) return DALI_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    g_create_err = "no CUDA device visible (there is no CPU fallback)";
+    return DALI_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) {
+    g_create_err = "device ordinal out of range";
+    return DALI_ERR_INVALID;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return DALI_ERR_CUDA;
+  if (prop.major != 10) {
+    g_create_err = "device is not compute capability 10.x (kernels are built for sm_100a only)";
+    return DALI_ERR_CUDA;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return DALI_ERR_CUDA;
+  dali_ctx *c = new dali_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  c->cc_major = prop.major;
+  c->cc_minor = prop.minor;
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return DALI_ERR_CUDA;
+  }
+  c->stream = c->own_stream;
+  *out = c;
+  return DALI_OK;
+}
+
+void dali_ctx_destroy(dali_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &pe : ctx->t_pending) {
+    cudaEventDestroy(pe.second.first);
+    cudaEventDestroy(pe.second.second);
+  }
+  for (auto e : ctx->t_pool) cudaEventDestroy(e);
+  for (auto &b : ctx->ws)
+    if (b.p) cudaFree(b.p);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+int dali_ctx_set_stream(dali_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return DALI_ERR_INVALID;
+  timing_drain(ctx);
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return DALI_OK;
+}
+
+void *dali_ctx_get_stream(dali_ctx *ctx) { return ctx ? static_cast<void *>(ctx->stream) : nullptr; }
+
+const char *dali_last_error(dali_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int dali_ctx_timing_enable(dali_ctx *ctx, int on) {
+  if (!ctx) return DALI_ERR_INVALID;
+  timing_drain(ctx);
+  ctx->timing = on != 0;
+  return DALI_OK;
+}
+
+int dali_ctx_timing_reset(dali_ctx *ctx) {
+  if (!ctx) return DALI_ERR_INVALID;
+  timing_drain(ctx);
+  for (int i = 0; i < DALI_K_COUNT_; ++i) {
+    ctx->t_ms[i] = 0.f;
+    ctx->t_launches[i] = 0;
+  }
+  return DALI_OK;
+}
+
+int dali_ctx_timing_read(dali_ctx *ctx, int which, int *launches, float *total_ms) {
+  if (!ctx || which < 0 || which >= DALI_K_COUNT_) return DALI_ERR_INVALID;
+  timing_drain(ctx);
+  if (launches) *launches = ctx->t_launches[which];
+  if (total_ms) *total_ms = ctx->t_ms[which];
+  return DALI_OK;
+}
+
+int64_t dali_ctx_launch_count(dali_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------
+int dali_normalize_f32(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx, float *out,
+                       int64_t ldo, float *norms_opt) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (n < 0 || d <= 0 || ldx < d || ldo < d || !x || !out)
+    return set_err(ctx, DALI_ERR_INVALID, "normalize: bad shape or null pointer");
+  if (n == 0) return DALI_OK;
+  const float *xd;
+  int64_t ldxd;
+  rc = stage_in(ctx, WS_STAGE_A, x, n, d, ldx, &xd, &ldxd);
+  if (rc) return rc;
+  const bool out_dev = is_device_ptr(out);
+  float *od = out;
+  int64_t ldod = ldo;
+  if (!out_dev) {
+    void *t;
+    rc = ws_ensure(ctx, WS_STAGE_B, sizeof(float) * n * d, &t);
+    if (rc) return rc;
+    od = static_cast<float *>(t);
+    ldod = d;
+  }
+  float *nd = nullptr;
+  const bool norms_dev = norms_opt && is_device_ptr(norms_opt);
+  if (norms_opt) {
+    if (norms_dev) {
+      nd = norms_opt;
+    } else {
+      void *t;
+      rc = ws_ensure(ctx, WS_QNORM, sizeof(float) * n, &t);
+      if (rc) return rc;
+      nd = static_cast<float *>(t);
+    }
+  }
+  rc = launch_prep(ctx, xd, n, d, ldxd, od, nullptr, ldod, d, n, 1, 0, nd, nullptr);
+  if (rc) return rc;
+  if (!out_dev)
+    DALI_CUDA_OK(ctx, cudaMemcpy2DAsync(out, sizeof(float) * ldo, od, sizeof(float) * ldod,
+                                        sizeof(float) * d, n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (norms_opt && !norms_dev)
+    DALI_CUDA_OK(ctx, cudaMemcpyAsync(norms_opt, nd, sizeof(float) * n, cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+  DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return DALI_OK;
+}
+
+// ---------------------------------------------------------------------------
+static int distmat_to(dali_ctx *ctx, const float *q, int64_t Q, const float *g, int64_t G, int64_t D,
+                      int metric, int precision, int normalize, float *out_dev, int64_t ld) {
+  Prepared a, b;
+  int rc = prepare_operand(ctx, WS_QIN, WS_QN, WS_QNORM, q, Q, D, metric, precision, normalize, &a);
+  if (rc) return rc;
+  rc = prepare_operand(ctx, WS_GIN, WS_GN, WS_GNORM, g, G, D, metric, precision, normalize, &b);
+  if (rc) return rc;
+  return contract(ctx, a, b, Q, G, metric, precision, out_dev, ld);
+}
+
+int dali_distmat_f32(dali_ctx *ctx, const float *q, int64_t Q, const float *g, int64_t G, int64_t D,
+                     int metric, int precision, int normalize, float *out, int64_t ld) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (Q < 0 || G < 0 || D <= 0 || ld < G || !out || (!q && Q) || (!g && G))
+    return set_err(ctx, DALI_ERR_INVALID, "distmat: bad shape or null pointer");
+  rc = check_metric_prec(ctx, metric, precision);
+  if (rc) return rc;
+  if (Q == 0 || G == 0) return DALI_OK;
+  const bool out_dev = is_device_ptr(out);
+  float *od = out;
+  int64_t ldd = ld;
+  if (!out_dev) {
+    ldd = round_up(G, 4);
+    void *t;
+    rc = ws_ensure(ctx, WS_DIST, sizeof(float) * Q * ldd, &t);
+    if (rc) return rc;
+    od = static_cast<float *>(t);
+  }
+  rc = distmat_to(ctx, q, Q, g, G, D, metric, precision, normalize, od, ldd);
+  if (rc) return rc;
+  if (!out_dev)
+    DALI_CUDA_OK(ctx, cudaMemcpy2DAsync(out, sizeof(float) * ld, od, sizeof(float) * ldd,
+                                        sizeof(float) * G, Q, cudaMemcpyDeviceToHost, ctx->stream));
+  DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return DALI_OK;
+}
+
+// ---------------------------------------------------------------------------
+int dali_fuse_f32(dali_ctx *ctx, const float *const *d, int n, const float *const *wq,
+                  const float *const *wg, float *out, int64_t Q, int64_t G, int64_t ld) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (!d || !out || n < 1 || n > 8 || Q < 0 || G < 0 || ld < G || ((wq == nullptr) != (wg == nullptr)))
+    return set_err(ctx, DALI_ERR_INVALID, "fuse: bad arguments (1..8 matrices, wq and wg together)");
+  if (Q == 0 || G == 0) return DALI_OK;
+  const bool dev = is_device_ptr(out);
+  for (int m = 0; m < n; ++m)
+    if (!d[m] || is_device_ptr(d[m]) != dev)
+      return set_err(ctx, DALI_ERR_INVALID, "fuse: matrices and output must all be host or all device");
+  const float *dd[8];
+  const float *wqd[8];
+  const float *wgd[8];
+  float *od = out;
+  int64_t ldd = ld;
+  if (!dev) {
+    ldd = round_up(G, 4);
+    void *t;
+    rc = ws_ensure(ctx, WS_STAGE_A, sizeof(float) * Q * ldd * (n + 1), &t);
+    if (rc) return rc;
+    float *base = static_cast<float *>(t);
+    for (int m = 0; m < n; ++m) {
+      float *dst = base + static_cast<int64_t>(m) * Q * ldd;
+      DALI_CUDA_OK(ctx, cudaMemcpy2DAsync(dst, sizeof(float) * ldd, d[m], sizeof(float) * ld,
+                                          sizeof(float) * G, Q, cudaMemcpyHostToDevice, ctx->stream));
+      dd[m] = dst;
+    }
+    od = base + static_cast<int64_t>(n) * Q * ldd;
+  } else {
+    for (int m = 0; m < n; ++m) dd[m] = d[m];
+  }
+  if (wq) {
+    void *t;
+    rc = ws_ensure(ctx, WS_STAGE_B, sizeof(float) * (Q + G) * n, &t);
+    if (rc) return rc;
+    float *base = static_cast<float *>(t);
+    for (int m = 0; m < n; ++m) {
+      if (!wq[m] || !wg[m]) return set_err(ctx, DALI_ERR_INVALID, "fuse: null weight vector");
+      float *a = base + static_cast<int64_t>(m) * (Q + G), *b = a + Q;
+      DALI_CUDA_OK(ctx, cudaMemcpyAsync(a, wq[m], sizeof(float) * Q, cudaMemcpyDefault, ctx->stream));
+      DALI_CUDA_OK(ctx, cudaMemcpyAsync(b, wg[m], sizeof(float) * G, cudaMemcpyDefault, ctx->stream));
+      wqd[m] = a;
+      wgd[m] = b;
+    }
+  }
+  // rows in bands of 65535 (grid.y limit)
+  for (int64_t r0 = 0; r0 < Q; r0 += 65535) {
+    const int64_t rows = std::min<int64_t>(65535, Q - r0);
+    const float *dband[8];
+    const float *wqband[8];
+    for (int m = 0; m < n; ++m) {
+      dband[m] = dd[m] + r0 * ldd;
+      if (wq) wqband[m] = wqd[m] + r0;
+    }
+    rc = launch_fuse(ctx, dband, n, wq ? wqband : nullptr, wq ? wgd : nullptr, od + r0 * ldd, rows,
+                     G, ldd);
+    if (rc) return rc;
+  }
+  if (!dev)
+    DALI_CUDA_OK(ctx, cudaMemcpy2DAsync(out, sizeof(float) * ld, od, sizeof(float) * ldd,
+                                        sizeof(float) * G, Q, cudaMemcpyDeviceToHost, ctx->stream));
+  DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return DALI_OK;
+}
+
+// ---------------------------------------------------------------------------
+int dali_rank_plan_create(dali_ctx *ctx, const int32_t *q_pid, const int32_t *g_pid,
+                          const int32_t *q_cam, const int32_t *g_cam, int64_t Q, int64_t G,
+                          dali_rank_plan **out) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (!out || Q < 0 || G < 0 || (Q && (!q_pid || !q_cam)) || (G && (!g_pid || !g_cam)))
+    return set_err(ctx, DALI_ERR_INVALID, "rank plan: bad arguments");
+  if (G > INT32_MAX || Q > INT32_MAX) return set_err(ctx, DALI_ERR_UNSUPPORTED, "Q or G exceeds 2^31");
+  *out = nullptr;
+  dali_rank_plan *p = new dali_rank_plan();
+  p->ctx = ctx;
+  p->Q = Q;
+  p->G = G;
+  // gallery CSR by identity: indices sorted by (pid, index)
+  std::vector<int32_t> order(G);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(),
+                   [&](int32_t a, int32_t b) { return g_pid[a] < g_pid[b]; });
+  std::vector<int32_t> sorted_pid(G);
+  for (int64_t i = 0; i < G; ++i) sorted_pid[i] = g_pid[order[i]];
+  p->h_off.assign(Q + 1, 0);
+  p->h_nv.assign(Q, 0);
+  p->h_njunk.assign(Q, 0);
+  std::vector<std::pair<int64_t, int64_t>> range(Q);
+  int64_t M = 0;
+  for (int64_t q = 0; q < Q; ++q) {
+    auto lo = std::lower_bound(sorted_pid.begin(), sorted_pid.end(), q_pid[q]);
+    auto hi = std::upper_bound(lo, sorted_pid.end(), q_pid[q]);
+    range[q] = {lo - sorted_pid.begin(), hi - sorted_pid.begin()};
+    p->h_off[q] = M;
+    M += hi - lo;
+  }
+  p->h_off[Q] = M;
+  if (M > INT32_MAX) {
+    delete p;
+    return set_err(ctx, DALI_ERR_UNSUPPORTED, "more than 2^31 same-identity (query, gallery) pairs");
+  }
+  p->M = M;
+  std::vector<int32_t> gid(std::max<int64_t>(M, 1));
+  for (int64_t q = 0; q < Q; ++q) {
+    int64_t w = p->h_off[q];
+    int nv = 0, nj = 0;
+    for (int64_t i = range[q].first; i < range[q].second; ++i)  // valid positives first
+      if (g_cam[order[i]] != q_cam[q]) { gid[w++] = order[i]; ++nv; }
+    for (int64_t i = range[q].first; i < range[q].second; ++i)  // then junk (same id, same camera)
+      if (g_cam[order[i]] == q_cam[q]) { gid[w++] = order[i]; ++nj; }
+    p->h_nv[q] = nv;
+    p->h_njunk[q] = nj;
+    p->max_nv = std::max(p->max_nv, nv);
+    p->max_m = std::max(p->max_m, nv + nj);
+  }
+  auto fail = [&](cudaError_t e) {
+    std::string m = cudaGetErrorString(e);
+    dali_rank_plan_destroy(p);
+    return set_err(ctx, DALI_ERR_CUDA, "rank plan upload: " + m);
+  };
+  cudaError_t e;
+  if ((e = cudaMalloc(&p->d_off, sizeof(int64_t) * (Q + 1))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&p->d_nv, sizeof(int32_t) * std::max<int64_t>(Q, 1))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&p->d_gid, sizeof(int32_t) * std::max<int64_t>(M, 1))) != cudaSuccess) return fail(e);
+  if ((e = cudaMemcpyAsync(p->d_off, p->h_off.data(), sizeof(int64_t) * (Q + 1), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return fail(e);
+  if (Q && (e = cudaMemcpyAsync(p->d_nv, p->h_nv.data(), sizeof(int32_t) * Q, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return fail(e);
+  if (M && (e = cudaMemcpyAsync(p->d_gid, gid.data(), sizeof(int32_t) * M, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return fail(e);
+  if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail(e);  // gid is a local
+  *out = p;
+  return DALI_OK;
+}
+
+void dali_rank_plan_destroy(dali_rank_plan *plan) {
+  if (!plan) return;
+  if (plan->d_off) cudaFree(plan->d_off);
+  if (plan->d_nv) cudaFree(plan->d_nv);
+  if (plan->d_gid) cudaFree(plan->d_gid);
+  delete plan;
+}
+
+int64_t dali_rank_plan_num_matches(const dali_rank_plan *plan) { return plan ? plan->M : -1; }
+
+int dali_rank_gather_keys(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist_slab,
+                          int64_t ld, int64_t g0, int64_t Gs, uint32_t *keys_out) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (!plan || !keys_out || (!dist_slab && Gs) || ld < Gs || g0 < 0 || g0 + Gs > plan->G)
+    return set_err(ctx, DALI_ERR_INVALID, "gather_keys: bad arguments");
+  if (Gs && !is_device_ptr(dist_slab)) return set_err(ctx, DALI_ERR_INVALID, "gather_keys: slab must be device memory");
+  if (Gs == 0) {
+    DALI_CUDA_OK(ctx, cudaMemsetAsync(keys_out, 0, sizeof(uint32_t) * plan->M, ctx->stream));
+    return DALI_OK;
+  }
+  return launch_rank_gather(ctx, plan, dist_slab, ld, g0, Gs, keys_out);
+}
+
+int dali_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist_slab, int64_t ld,
+                    int64_t g0, int64_t Gs, const uint32_t *keys, int32_t *counts_out) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (!plan || !keys || !counts_out || (!dist_slab && Gs) || ld < Gs || g0 < 0 || g0 + Gs > plan->G)
+    return set_err(ctx, DALI_ERR_INVALID, "rank_count: bad arguments");
+  if (Gs && !is_device_ptr(dist_slab)) return set_err(ctx, DALI_ERR_INVALID, "rank_count: slab must be device memory");
+  return launch_rank_count(ctx, plan, dist_slab, ld, g0, Gs, keys, counts_out);
+}
+
+int dali_rank_finalize(dali_ctx *ctx, const dali_rank_plan *plan, const uint32_t *keys,
+                       const int32_t *counts, int max_rank, int accum_mode, float *cmc, double *mAP,
+                       double *ap_opt, int32_t *first_rank_opt, int64_t *num_valid_opt) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (!plan || !cmc || !mAP || max_rank < 1 || (plan->M && (!keys || !counts)))
+    return set_err(ctx, DALI_ERR_INVALID, "rank_finalize: bad arguments");
+  if (accum_mode != DALI_ACCUM_CY_F32 && accum_mode != DALI_ACCUM_PY_F64)
+    return set_err(ctx, DALI_ERR_INVALID, "unknown accumulation mode");
+  if (max_rank > plan->G) max_rank = static_cast<int>(std::max<int64_t>(plan->G, 1));
+  void *ranks, *ap, *first, *cmcd;
+  rc = ws_ensure(ctx, WS_RANKS, sizeof(int32_t) * std::max<int64_t>(plan->M, 1), &ranks);
+  if (rc) return rc;
+  rc = ws_ensure(ctx, WS_AP, sizeof(float) * std::max<int64_t>(plan->Q, 1), &ap);
+  if (rc) return rc;
+  rc = ws_ensure(ctx, WS_FIRST, sizeof(int32_t) * std::max<int64_t>(plan->Q, 1), &first);
+  if (rc) return rc;
+  rc = ws_ensure(ctx, WS_CMC, sizeof(int32_t) * (max_rank + 1), &cmcd);
+  if (rc) return rc;
+  rc = launch_rank_finalize(ctx, plan, keys, counts, max_rank, static_cast<int32_t *>(ranks),
+                            static_cast<float *>(ap), static_cast<int32_t *>(first),
+                            static_cast<int32_t *>(cmcd));
+  if (rc) return rc;
+  return finish_on_host(ctx, plan, static_cast<int32_t *>(ranks), static_cast<float *>(ap),
+                        static_cast<int32_t *>(first), static_cast<int32_t *>(cmcd), max_rank,
+                        accum_mode, cmc, mAP, ap_opt, first_rank_opt, num_valid_opt);
+}
+
+// ---------------------------------------------------------------------------
+int dali_eval_rank_f32(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t ld,
+                       const int32_t *q_pid, const int32_t *g_pid, const int32_t *q_cam,
+                       const int32_t *g_cam, int max_rank, int accum_mode, float *cmc, double *mAP,
+                       double *ap_opt, int32_t *first_rank_opt, int64_t *num_valid_opt) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (Q < 0 || G < 0 || ld < G || (!dist && Q && G) || !cmc || !mAP || max_rank < 1)
+    return set_err(ctx, DALI_ERR_INVALID, "eval_rank: bad shape or null pointer");
+  dali_rank_plan *plan = nullptr;
+  rc = dali_rank_plan_create(ctx, q_pid, g_pid, q_cam, g_cam, Q, G, &plan);
+  if (rc) return rc;
+  const float *dd = dist;
+  int64_t ldd = ld;
+  if (Q && G) rc = stage_in(ctx, WS_DIST, dist, Q, G, ld, &dd, &ldd);
+  if (!rc)
+    rc = rank_from_device(ctx, plan, dd, ldd, max_rank, accum_mode, cmc, mAP, ap_opt,
+                          first_rank_opt, num_valid_opt);
+  dali_rank_plan_destroy(plan);
+  return rc;
+}
+
+int dali_eval_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float *g, int64_t G,
+                           int64_t D, const int32_t *q_pid, const int32_t *g_pid,
+                           const int32_t *q_cam, const int32_t *g_cam, int metric, int precision,
+                           int normalize, int max_rank, int accum_mode, float *cmc, double *mAP,
+                           double *ap_opt, int32_t *first_rank_opt, int64_t *num_valid_opt,
+                           float *distmat_opt, int64_t ld_opt) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (Q < 0 || G < 0 || D <= 0 || (!q && Q) || (!g && G) || !cmc || !mAP || max_rank < 1 ||
+      (distmat_opt && ld_opt < G))
+    return set_err(ctx, DALI_ERR_INVALID, "eval_features: bad shape or null pointer");
+  rc = check_metric_prec(ctx, metric, precision);
+  if (rc) return rc;
+  if (metric == DALI_METRIC_DOT)
+    return set_err(ctx, DALI_ERR_INVALID, "eval_features ranks distances; DOT is a similarity");
+  dali_rank_plan *plan = nullptr;
+  rc = dali_rank_plan_create(ctx, q_pid, g_pid, q_cam, g_cam, Q, G, &plan);
+  if (rc) return rc;
+  const bool user_dev = distmat_opt && is_device_ptr(distmat_opt);
+  float *dd = distmat_opt;
+  int64_t ldd = ld_opt;
+  if (!user_dev) {
+    ldd = round_up(std::max<int64_t>(G, 1), 4);
+    void *t;
+    rc = ws_ensure(ctx, WS_DIST, sizeof(float) * std::max<int64_t>(Q, 1) * ldd, &t);
+    dd = static_cast<float *>(t);
+  }
+  if (!rc && Q && G) rc = distmat_to(ctx, q, Q, g, G, D, metric, precision, normalize, dd, ldd);
+  if (!rc && distmat_opt && !user_dev && Q && G) {
+    cudaError_t e = cudaMemcpy2DAsync(distmat_opt, sizeof(float) * ld_opt, dd, sizeof(float) * ldd,
+                                      sizeof(float) * G, Q, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e != cudaSuccess) rc = set_err(ctx, DALI_ERR_CUDA, cudaGetErrorString(e));
+  }
+  if (!rc)
+    rc = rank_from_device(ctx, plan, dd, ldd, max_rank, accum_mode, cmc, mAP, ap_opt,
+                          first_rank_opt, num_valid_opt);
+  dali_rank_plan_destroy(plan);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------
+static int topk_out(dali_ctx *ctx, const float *dist_dev, int64_t Q, int64_t G, int64_t ld, int k,
+                    int largest, const int32_t *ids_dev, int32_t id_base, float *d_out,
+                    int32_t *i_out) {
+  const bool od = is_device_ptr(d_out), oi = is_device_ptr(i_out);
+  float *dd = d_out;
+  int32_t *ii = i_out;
+  int rc;
+  if (!od) {
+    void *t;
+    rc = ws_ensure(ctx, WS_TOPK_D, sizeof(float) * Q * k, &t);
+    if (rc) return rc;
+    dd = static_cast<float *>(t);
+  }
+  if (!oi) {
+    void *t;
+    rc = ws_ensure(ctx, WS_TOPK_I, sizeof(int32_t) * Q * k, &t);
+    if (rc) return rc;
+    ii = static_cast<int32_t *>(t);
+  }
+  rc = launch_topk(ctx, dist_dev, Q, G, ld, k, largest, ids_dev, id_base, dd, ii);
+  if (rc) return rc;
+  if (!od)
+    DALI_CUDA_OK(ctx, cudaMemcpyAsync(d_out, dd, sizeof(float) * Q * k, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!oi)
+    DALI_CUDA_OK(ctx, cudaMemcpyAsync(i_out, ii, sizeof(int32_t) * Q * k, cudaMemcpyDeviceToHost, ctx->stream));
+  DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return DALI_OK;
+}
+
+int dali_topk_f32(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t ld, int k,
+                  int largest, const int32_t *col_ids_opt, float *d_out, int32_t *i_out) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (Q < 0 || G < 0 || ld < G || (!dist && Q && G) || !d_out || !i_out || k < 1 || k > 128)
+    return set_err(ctx, DALI_ERR_INVALID, "topk: bad arguments (1 <= k <= 128)");
+  if (Q == 0) return DALI_OK;
+  const float *dd = dist;
+  int64_t ldd = ld;
+  const int32_t *ids = col_ids_opt;
+  if (G) {
+    rc = stage_in(ctx, WS_DIST, dist, Q, G, ld, &dd, &ldd);
+    if (rc) return rc;
+    if (col_ids_opt && !is_device_ptr(col_ids_opt)) {
+      void *t;
+      rc = ws_ensure(ctx, WS_STAGE_C, sizeof(int32_t) * Q * ldd, &t);
+      if (rc) return rc;
+      DALI_CUDA_OK(ctx, cudaMemcpy2DAsync(t, sizeof(int32_t) * ldd, col_ids_opt, sizeof(int32_t) * ld,
+                                          sizeof(int32_t) * G, Q, cudaMemcpyHostToDevice, ctx->stream));
+      ids = static_cast<const int32_t *>(t);
+    } else if (col_ids_opt && ldd != ld) {
+      return set_err(ctx, DALI_ERR_INVALID, "topk: host matrix with device col_ids is not supported");
+    }
+  }
+  return topk_out(ctx, dd, Q, G, ldd, k, largest, ids, 0, d_out, i_out);
+}
+
+int dali_topk_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float *g, int64_t G,
+                           int64_t D, int metric, int precision, int normalize, int k, int largest,
+                           int32_t g_base, float *d_out, int32_t *i_out) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (Q < 0 || G < 0 || D <= 0 || (!q && Q) || (!g && G) || !d_out || !i_out || k < 1 || k > 128)
+    return set_err(ctx, DALI_ERR_INVALID, "topk_features: bad arguments");
+  rc = check_metric_prec(ctx, metric, precision);
+  if (rc) return rc;
+  if (Q == 0) return DALI_OK;
+  // Round 1: the gallery is processed in one slab through an internal [Qc, G] matrix per
+  // query band (bounded workspace); the band results are final because each band owns its rows.
+  Prepared a, b;
+  rc = prepare_operand(ctx, WS_GIN, WS_GN, WS_GNORM, g, G, D, metric, precision, normalize, &b);
+  if (rc) return rc;
+  const int64_t ldd = round_up(std::max<int64_t>(G, 1), 4);
+  const int64_t budget = 8ll << 30;  // bytes of internal distance matrix per band
+  int64_t band = std::max<int64_t>(128, (budget / (sizeof(float) * ldd)) / 128 * 128);
+  band = std::min(band, round_up(Q, 128));
+  void *t;
+  rc = ws_ensure(ctx, WS_DIST, sizeof(float) * band * ldd, &t);
+  if (rc) return rc;
+  float *dist = static_cast<float *>(t);
+  const bool od = is_device_ptr(d_out), oi = is_device_ptr(i_out);
+  const bool qdev = is_device_ptr(q);
+  for (int64_t q0 = 0; q0 < Q; q0 += band) {
+    const int64_t qc = std::min(band, Q - q0);
+    rc = prepare_operand(ctx, WS_QIN, WS_QN, WS_QNORM, q + q0 * D, qc, D, metric, precision,
+                         normalize, &a);
+    if (rc) return rc;
+    if (G) {
+      rc = contract(ctx, a, b, qc, G, metric, precision, dist, ldd);
+      if (rc) return rc;
+    }
+    rc = topk_out(ctx, dist, qc, G, ldd, k, largest, nullptr, g_base, d_out + q0 * k, i_out + q0 * k);
+    if (rc) return rc;
+    (void)od; (void)oi; (void)qdev;
+  }
+  return DALI_OK;
+}
+
+}  // extern "C"

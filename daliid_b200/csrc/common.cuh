@@ -1,0 +1,165 @@
+// Internal definitions shared by the kernels and the C-ABI glue of libdaliid_b200.
+// Nothing here is exported; the public surface is include/daliid_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/daliid_b200.h"
+
+namespace dali {
+
+// ---------------------------------------------------------------------------
+// Order-preserving key of an fp32 distance (the canonical order of SURVEY 8c):
+// ascending value, -0.0 == +0.0, every NaN after +inf.  Largest real key is
+// key(+inf) = 0xFF800000, NaN maps to 0xFFFFFFFE so key+1 never wraps.
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t dist_key(float d) {
+  d = d + 0.0f;  // -0.0 -> +0.0 (IEEE; kept because fast-math is never enabled)
+#ifdef __CUDA_ARCH__
+  uint32_t b = __float_as_uint(d);
+#else
+  union { float f; uint32_t u; } cv; cv.f = d; uint32_t b = cv.u;
+#endif
+  uint32_t k = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return (d != d) ? 0xFFFFFFFEu : k;
+}
+
+__host__ __device__ __forceinline__ float key_to_dist(uint32_t k) {
+  uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(b);
+#else
+  union { float f; uint32_t u; } cv; cv.u = b; return cv.f;
+#endif
+}
+
+__host__ __device__ __forceinline__ uint64_t composite(uint32_t key, uint32_t gid) {
+  return (static_cast<uint64_t>(key) << 32) | gid;
+}
+
+// ---------------------------------------------------------------------------
+// Context
+// ---------------------------------------------------------------------------
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+enum WsSlot {
+  WS_QN = 0,   // normalised queries (fp32, padded rows) / hi+lo planes
+  WS_GN,       // normalised gallery
+  WS_QIN,      // staged host queries
+  WS_GIN,      // staged host gallery
+  WS_QNORM,    // row norms
+  WS_GNORM,
+  WS_DIST,     // internal distance matrix
+  WS_KEYS,     // match keys
+  WS_COUNTS,   // match counts
+  WS_RANKS,    // sorted kept ranks
+  WS_AP,       // per-query AP (fp32)
+  WS_FIRST,    // per-query first rank
+  WS_CMC,      // cmc histogram + num_valid
+  WS_STAGE_A,  // generic staging (host matrices etc.)
+  WS_STAGE_B,
+  WS_STAGE_C,
+  WS_TOPK_D,
+  WS_TOPK_I,
+  WS_PTRS,     // device arrays of pointers (fusion)
+  WS_MISC,
+  WS_COUNT_
+};
+
+}  // namespace dali
+
+struct dali_ctx {
+  int device = 0;
+  int num_sms = 0;
+  int cc_major = 0, cc_minor = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  dali::DevBuf ws[dali::WS_COUNT_];
+  void *pinned = nullptr;  // small pinned scratch for results
+  size_t pinned_cap = 0;
+  // timing
+  bool timing = false;
+  int t_launches[DALI_K_COUNT_] = {0};
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> t_pending;
+  std::vector<cudaEvent_t> t_pool;
+  float t_ms[DALI_K_COUNT_] = {0};
+  int64_t launches = 0;
+  // tensor-map encoder (driver entry point, resolved lazily)
+  void *encode_tiled = nullptr;
+};
+
+struct dali_rank_plan {
+  dali_ctx *ctx = nullptr;
+  int64_t Q = 0, G = 0, M = 0;
+  int max_m = 0;   // largest number of matches of one query
+  int max_nv = 0;  // largest number of valid positives of one query
+  // host copies
+  std::vector<int64_t> h_off;    // [Q+1] offsets into the match arrays
+  std::vector<int32_t> h_nv;     // [Q]   number of valid positives (they come first)
+  std::vector<int32_t> h_njunk;  // [Q]
+  // device copies
+  int64_t *d_off = nullptr;
+  int32_t *d_nv = nullptr;
+  int32_t *d_gid = nullptr;  // [M] gallery id of each match (valid ascending, then junk ascending)
+};
+
+namespace dali {
+
+int set_err(dali_ctx *ctx, int code, const std::string &msg);
+int ws_ensure(dali_ctx *ctx, int slot, size_t bytes, void **out);
+
+// RAII-less timing helpers: call before/after a kernel launch on ctx->stream.
+struct KTimer {
+  dali_ctx *ctx;
+  int slot;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  KTimer(dali_ctx *c, int s);
+  ~KTimer();
+};
+
+#define DALI_CUDA_OK(ctx, expr)                                                         \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      return dali::set_err((ctx), DALI_ERR_CUDA,                                        \
+                           std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+  } while (0)
+
+// ---- kernel launchers (defined in the .cu files) ---------------------------
+// normalize.cu
+int launch_prep(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx, float *plane0,
+                float *plane1, int64_t ldo, int64_t d_pad, int64_t rows_pad, int do_normalize,
+                int round_mode, float *norms, float *sq);
+// distmat_simt.cu
+int launch_distmat_simt(dali_ctx *ctx, const float *qn, const float *gn, int64_t Q, int64_t G,
+                        int64_t D, int64_t ldq, int64_t ldg, int metric, const float *qsq,
+                        const float *gsq, float *out, int64_t ld);
+// distmat_umma.cu
+int launch_distmat_umma(dali_ctx *ctx, const float *q_planes, const float *g_planes, int64_t Q,
+                        int64_t G, int64_t Dp, int64_t q_rows_pad, int64_t g_rows_pad, int split3,
+                        int metric, const float *qsq, const float *gsq, float *out, int64_t ld);
+// rank.cu
+int launch_rank_gather(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist, int64_t ld,
+                       int64_t g0, int64_t Gs, uint32_t *keys);
+int launch_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist, int64_t ld,
+                      int64_t g0, int64_t Gs, const uint32_t *keys, int32_t *counts);
+int launch_rank_finalize(dali_ctx *ctx, const dali_rank_plan *plan, const uint32_t *keys,
+                         const int32_t *counts, int max_rank, int32_t *ranks_sorted, float *ap,
+                         int32_t *first_rank, int32_t *cmc_cnt /* [max_rank+1], last = num_valid */);
+// topk.cu
+int launch_topk(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t ld, int k,
+                int largest, const int32_t *col_ids, int32_t id_base, float *d_out,
+                int32_t *i_out);
+// fuse.cu
+int launch_fuse(dali_ctx *ctx, const float *const *d_ptrs_dev, int n, const float *const *wq_dev,
+                const float *const *wg_dev, float *out, int64_t Q, int64_t G, int64_t ld);
+
+}  // namespace dali

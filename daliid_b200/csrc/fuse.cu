@@ -1,0 +1,128 @@
+// Multi-model distance fusion: element-wise, HBM bound, with the
+// reference's exact operation order so the fused matrix is bit-identical to numpy/torch.
+//
+// mean      ((d0+d1)+d2)/n             evaluate.py:278, evaluate_ensembled_models.py:313,
+//                                      evaluateCleanATModels.py:127
+// weighted  w_m[i,j] = max(wq_m[i], wg_m[j]);  (w0*d0 + w1*d1 + ..)/(w0 + w1 + ..)
+//                                      evaluateCleanATModels.py:154-157,193-196,230-233
+#include "common.cuh"
+
+namespace dali {
+
+namespace {
+
+constexpr int kMaxFuse = 8;
+
+struct FuseParams {
+  const float *d[kMaxFuse];
+  const float *wq[kMaxFuse];
+  const float *wg[kMaxFuse];
+  float *out;
+  int n;
+  int weighted;
+  int64_t Q, G, ld;
+};
+
+__device__ __forceinline__ float fuse_one(const FuseParams &p, const float (&v)[kMaxFuse],
+                                          const float (&wqv)[kMaxFuse], int64_t col) {
+  if (!p.weighted) {
+    float acc = v[0];
+#pragma unroll
+    for (int m = 1; m < kMaxFuse; ++m)
+      if (m < p.n) acc = __fadd_rn(acc, v[m]);
+    return __fdiv_rn(acc, static_cast<float>(p.n));
+  }
+  float w = fmaxf(wqv[0], __ldg(p.wg[0] + col));
+  // torch.maximum propagates NaN; fmaxf does not
+  if (wqv[0] != wqv[0] || __ldg(p.wg[0] + col) != __ldg(p.wg[0] + col)) w = NAN;
+  float num = __fmul_rn(w, v[0]);
+  float den = w;
+#pragma unroll
+  for (int m = 1; m < kMaxFuse; ++m) {
+    if (m < p.n) {
+      const float g = __ldg(p.wg[m] + col);
+      float wm = fmaxf(wqv[m], g);
+      if (wqv[m] != wqv[m] || g != g) wm = NAN;
+      num = __fadd_rn(num, __fmul_rn(wm, v[m]));
+      den = __fadd_rn(den, wm);
+    }
+  }
+  return __fdiv_rn(num, den);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) fuse_kernel(FuseParams p) {
+  const int64_t q = blockIdx.y;
+  float wqv[kMaxFuse];
+#pragma unroll
+  for (int m = 0; m < kMaxFuse; ++m) wqv[m] = (p.weighted && m < p.n) ? __ldg(p.wq[m] + q) : 0.f;
+  const int64_t nvec = (p.G + VEC - 1) / VEC;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t c = i * VEC;
+    if (VEC == 4 && c + 3 < p.G) {
+      float4 x[kMaxFuse];
+#pragma unroll
+      for (int m = 0; m < kMaxFuse; ++m)
+        if (m < p.n) x[m] = __ldcs(reinterpret_cast<const float4 *>(p.d[m] + q * p.ld + c));
+      float4 o;
+      float v[kMaxFuse];
+#pragma unroll
+      for (int m = 0; m < kMaxFuse; ++m) v[m] = (m < p.n) ? x[m].x : 0.f;
+      o.x = fuse_one(p, v, wqv, c);
+#pragma unroll
+      for (int m = 0; m < kMaxFuse; ++m) v[m] = (m < p.n) ? x[m].y : 0.f;
+      o.y = fuse_one(p, v, wqv, c + 1);
+#pragma unroll
+      for (int m = 0; m < kMaxFuse; ++m) v[m] = (m < p.n) ? x[m].z : 0.f;
+      o.z = fuse_one(p, v, wqv, c + 2);
+#pragma unroll
+      for (int m = 0; m < kMaxFuse; ++m) v[m] = (m < p.n) ? x[m].w : 0.f;
+      o.w = fuse_one(p, v, wqv, c + 3);
+      *reinterpret_cast<float4 *>(p.out + q * p.ld + c) = o;
+    } else {
+      for (int64_t e = c; e < c + VEC && e < p.G; ++e) {
+        float v[kMaxFuse];
+#pragma unroll
+        for (int m = 0; m < kMaxFuse; ++m) v[m] = (m < p.n) ? __ldg(p.d[m] + q * p.ld + e) : 0.f;
+        p.out[q * p.ld + e] = fuse_one(p, v, wqv, e);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// All pointers are DEVICE pointers here (capi.cu stages host operands first).
+int launch_fuse(dali_ctx *ctx, const float *const *d, int n, const float *const *wq,
+                const float *const *wg, float *out, int64_t Q, int64_t G, int64_t ld) {
+  if (n < 1 || n > kMaxFuse) return set_err(ctx, DALI_ERR_INVALID, "fusion supports 1..8 matrices");
+  if (Q == 0 || G == 0) return DALI_OK;
+  FuseParams p;
+  bool aligned = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  for (int m = 0; m < kMaxFuse; ++m) {
+    p.d[m] = m < n ? d[m] : nullptr;
+    p.wq[m] = (wq && m < n) ? wq[m] : nullptr;
+    p.wg[m] = (wg && m < n) ? wg[m] : nullptr;
+    if (m < n && (reinterpret_cast<uintptr_t>(d[m]) & 15)) aligned = false;
+  }
+  p.out = out; p.n = n; p.weighted = (wq && wg) ? 1 : 0; p.Q = Q; p.G = G; p.ld = ld;
+  if (Q > 65535 * 1ll) {
+    // grid.y limit: process in row bands
+    return set_err(ctx, DALI_ERR_UNSUPPORTED, "fusion of more than 65535 rows: call per band");
+  }
+  const int vec = aligned ? 4 : 1;
+  const int64_t nvec = (G + vec - 1) / vec;
+  int bx = static_cast<int>((nvec + 255) / 256);
+  if (bx > 64) bx = 64;
+  dim3 grid(bx, static_cast<unsigned>(Q));
+  KTimer t(ctx, DALI_K_FUSE);
+  if (aligned)
+    fuse_kernel<4><<<grid, 256, 0, ctx->stream>>>(p);
+  else
+    fuse_kernel<1><<<grid, 256, 0, ctx->stream>>>(p);
+  DALI_CUDA_OK(ctx, cudaGetLastError());
+  return DALI_OK;
+}
+
+}  // namespace dali

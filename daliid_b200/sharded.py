@@ -1,0 +1,184 @@
+"""Gallery-sharded evaluation: one process per GPU (``torch.distributed``, NCCL over NVLink).
+
+The reference has no multi-GPU evaluation (its hot path is single-process CPU code); this
+is the scaling axis the build adds.  Rank ``r`` holds ALL queries and a
+contiguous gallery slab ``[g0, g0+Gs)``; slabs are contiguous in gallery index so the global
+tie-break ``(distance, gallery index)`` is preserved and the result is bit-identical to the
+single-GPU one.  The only exchange steps are two tiny all-reduces:
+
+    slab distmat -> gather match keys -> all_reduce(SUM) -> count below -> all_reduce(SUM)
+                 -> CMC/mAP epilogue (every rank, identical result)
+
+and, for top-k identification, an all_gather of the per-slab top-k followed by a k-way merge.
+Everything heavy (contraction, counting, selection) is a local kernel of the C-ABI library.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib, metrics
+from ._lib import ACCUMS, c_vp, get_ctx, p_i32
+
+
+def slab_bounds(G: int, world: int, rank: int):
+    """Contiguous, balanced partition of the gallery: returns (g0, Gs)."""
+    base, rem = divmod(G, world)
+    g0 = rank * base + min(rank, rem)
+    return g0, base + (1 if rank < rem else 0)
+
+
+class CudaOps:
+    """Local building blocks backed by the C-ABI (``dali_rank_*``, ``dali_distmat_f32`` ...)."""
+
+    def __init__(self, device=None):
+        self.ctx = get_ctx(device)
+        self.device = torch.device(f"cuda:{self.ctx.device}")
+
+    def distmat(self, qf, gf_slab, metric, precision, normalize):
+        return metrics.compute_distance_matrix(qf, gf_slab, metric, precision, normalize)
+
+    def plan(self, q_pid, g_pid, q_cam, g_cam):
+        self.ctx.attach_torch_stream()
+        h = c_vp()
+        self._labels = (q_pid, g_pid, q_cam, g_cam)
+        self.ctx.check(self.ctx.lib.dali_rank_plan_create(
+            self.ctx.h, p_i32(q_pid), p_i32(g_pid), p_i32(q_cam), p_i32(g_cam),
+            len(q_pid), len(g_pid), ctypes.byref(h)))
+        return h
+
+    def plan_destroy(self, plan):
+        self.ctx.lib.dali_rank_plan_destroy(plan)
+
+    def num_matches(self, plan):
+        return int(self.ctx.lib.dali_rank_plan_num_matches(plan))
+
+    def gather_keys(self, plan, dist_slab, g0):
+        self.ctx.attach_torch_stream()
+        M = self.num_matches(plan)
+        keys = torch.zeros(max(M, 1), dtype=torch.int32, device=self.device)
+        Q, Gs = dist_slab.shape
+        self.ctx.check(self.ctx.lib.dali_rank_gather_keys(
+            self.ctx.h, plan, c_vp(dist_slab.data_ptr()), max(dist_slab.stride(0), Gs, 1) if Q else max(Gs, 1),
+            g0, Gs, c_vp(keys.data_ptr())))
+        return keys
+
+    def count(self, plan, dist_slab, g0, keys):
+        self.ctx.attach_torch_stream()
+        counts = torch.zeros_like(keys)
+        Q, Gs = dist_slab.shape
+        self.ctx.check(self.ctx.lib.dali_rank_count(
+            self.ctx.h, plan, c_vp(dist_slab.data_ptr()), max(dist_slab.stride(0), Gs, 1) if Q else max(Gs, 1),
+            g0, Gs, c_vp(keys.data_ptr()), c_vp(counts.data_ptr())))
+        return counts
+
+    def finalize(self, plan, keys, counts, Q, G, max_rank, accum):
+        self.ctx.attach_torch_stream()
+        max_rank = min(max_rank, G)
+        cmc = np.zeros(max_rank, dtype=np.float32)
+        mAP = ctypes.c_double(0.0)
+        ap = np.zeros(Q, dtype=np.float64)
+        first = np.zeros(Q, dtype=np.int32)
+        nvalid = ctypes.c_int64(0)
+        self.ctx.check(self.ctx.lib.dali_rank_finalize(
+            self.ctx.h, plan, c_vp(keys.data_ptr()), c_vp(counts.data_ptr()), max_rank,
+            ACCUMS[accum], cmc.ctypes.data_as(_lib.c_f32p), ctypes.byref(mAP),
+            ap.ctypes.data_as(_lib.c_f64p), first.ctypes.data_as(_lib.c_i32p), ctypes.byref(nvalid)))
+        return cmc, float(mAP.value), {"ap": ap, "first_rank": first, "num_valid": int(nvalid.value)}
+
+    def topk(self, distmat, k, largest, col_ids=None):
+        return metrics.topk_identify(distmat, k, largest, col_ids)
+
+    def topk_features(self, qf, gf_slab, k, metric, precision, normalize, largest, g_base):
+        return metrics.topk_features(qf, gf_slab, k, metric, precision, normalize, largest, g_base)
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def _all_reduce_sum(t, group):
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def gather_gallery_labels(g_pid_slab, g_cam_slab, group=None):
+    """All ranks learn the labels of the whole gallery (two int32 vectors; tiny) and the
+    slab offsets.  Returns (g_pid_all, g_cam_all, g0_of_this_rank, sizes)."""
+    world, rank = _world(group)
+    pid = np.ascontiguousarray(g_pid_slab, dtype=np.int32)
+    cam = np.ascontiguousarray(g_cam_slab, dtype=np.int32)
+    if world == 1:
+        return pid, cam, 0, [len(pid)]
+    objs = [None] * world
+    dist.all_gather_object(objs, (pid, cam), group=group)
+    sizes = [len(o[0]) for o in objs]
+    return (np.concatenate([o[0] for o in objs]), np.concatenate([o[1] for o in objs]),
+            int(sum(sizes[:rank])), sizes)
+
+
+def evaluate_rank_sharded(dist_slab, g0, q_pids, g_pids_all, q_camids, g_camids_all, max_rank=50,
+                          accum="cy_f32", group=None, ops=None, return_details=False):
+    """CMC/mAP from a per-rank distance slab ``[Q, Gs]`` (columns = gallery ``g0 .. g0+Gs``).
+    Labels are those of the whole gallery.  Every rank returns the same ``(cmc, mAP)``."""
+    ops = ops or CudaOps(dist_slab.device.index if dist_slab.is_cuda else None)
+    qp, gp = metrics.canonicalize_labels(q_pids, g_pids_all)
+    qc, gc = metrics.canonicalize_labels(q_camids, g_camids_all)
+    Q, G = len(qp), len(gp)
+    if dist_slab.shape[0] != Q or g0 < 0 or g0 + dist_slab.shape[1] > G:
+        raise ValueError("slab does not fit the label arrays")
+    if G < max_rank:
+        max_rank = G
+        print("Note: number of gallery samples is quite small, got {}".format(G))
+    plan = ops.plan(qp, gp, qc, gc)
+    try:
+        keys = _all_reduce_sum(ops.gather_keys(plan, dist_slab, g0), group)
+        counts = _all_reduce_sum(ops.count(plan, dist_slab, g0, keys), group)
+        cmc, mAP, details = ops.finalize(plan, keys, counts, Q, G, max_rank, accum)
+    finally:
+        ops.plan_destroy(plan)
+    return (cmc, mAP, details) if return_details else (cmc, mAP)
+
+
+def evaluate_features_sharded(qf, gf_slab, g0, q_pids, g_pids_all, q_camids, g_camids_all,
+                              metric="cosine", precision=metrics.DEFAULT_PRECISION,
+                              normalize=None, max_rank=50, accum="cy_f32", group=None, ops=None,
+                              return_details=False):
+    """Features in (all queries + this rank's gallery slab), ``(cmc, mAP)`` out."""
+    ops = ops or CudaOps(qf.device.index if getattr(qf, "is_cuda", False) else None)
+    if normalize is None:
+        normalize = metric == "cosine"
+    dist_slab = ops.distmat(qf, gf_slab, metric, precision, normalize)
+    if not isinstance(dist_slab, torch.Tensor):
+        dist_slab = torch.from_numpy(dist_slab)
+    return evaluate_rank_sharded(dist_slab, g0, q_pids, g_pids_all, q_camids, g_camids_all,
+                                 max_rank, accum, group, ops, return_details)
+
+
+def topk_features_sharded(qf, gf_slab, g0, k=20, metric="cosine", precision=metrics.DEFAULT_PRECISION,
+                          normalize=None, largest=False, group=None, ops=None):
+    """1:N identification over a sharded gallery: per-slab fused distance + top-k, all_gather of
+    the ``[Q,k]`` candidates, k-way merge with the global (value, gallery id) order."""
+    ops = ops or CudaOps(qf.device.index if getattr(qf, "is_cuda", False) else None)
+    if normalize is None:
+        normalize = metric == "cosine"
+    vals, ids = ops.topk_features(qf, gf_slab, k, metric, precision, normalize, largest, g0)
+    world, _ = _world(group)
+    if world == 1:
+        return vals, ids
+    vals = torch.as_tensor(vals)
+    ids = torch.as_tensor(ids)
+    vs = [torch.empty_like(vals) for _ in range(world)]
+    js = [torch.empty_like(ids) for _ in range(world)]
+    dist.all_gather(vs, vals.contiguous(), group=group)
+    dist.all_gather(js, ids.contiguous(), group=group)
+    cand_v = torch.cat(vs, dim=1).contiguous()
+    cand_i = torch.cat(js, dim=1).contiguous()
+    # padded entries (id -1, value +-inf) lose every comparison against real candidates
+    return ops.topk(cand_v, k, largest, cand_i)

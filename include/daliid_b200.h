@@ -1,0 +1,205 @@
+/*
+ * daliid_b200 -- C-ABI of the B200-native retrieval-evaluation hot path of DaliID.
+ *
+ * The reference (pure Python, /root/reference/Person-ReID) has no FFI of its own:
+ * its hot path is CPU torch/numpy plus the third-party `torchreid` evaluator.
+ * Each entry point below replaces one reference expression / call (cited as
+ * file:line under Person-ReID/); INTEGRATION.md shows the ctypes stub a reference
+ * maintainer would add at those lines.
+ *
+ * Conventions
+ *   - plain pointers and sizes, no C++/torch types, no exceptions across the ABI;
+ *   - every function returns DALI_OK (0) or a negative DALI_ERR_* code and records
+ *     a message retrievable with dali_last_error(ctx);
+ *   - data pointers may be HOST or DEVICE memory (queried with
+ *     cudaPointerGetAttributes); host buffers are staged through the context's
+ *     stream (pinned host memory gives full PCIe rate), device buffers are used
+ *     in place.  Label arrays (int32) and small results (cmc, mAP) are HOST.
+ *   - the caller owns all buffers; the context owns its stream (unless one is
+ *     attached), events and workspaces.  One context per host thread; calls are
+ *     synchronous with respect to the host unless stated otherwise;
+ *   - there is NO CPU fallback: without a usable sm_100 device every compute
+ *     entry point returns DALI_ERR_CUDA.
+ */
+#ifndef DALIID_B200_H_
+#define DALIID_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define DALI_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------- */
+#define DALI_OK 0
+#define DALI_ERR_INVALID (-1)        /* bad argument                                      */
+#define DALI_ERR_CUDA (-2)           /* CUDA runtime / driver failure, or no sm_100 GPU   */
+#define DALI_ERR_NO_VALID_QUERY (-3) /* torchreid: AssertionError('Error: all query
+                                        identities do not appear in gallery')             */
+#define DALI_ERR_UNSUPPORTED (-4)
+#define DALI_ERR_NOMEM (-5)
+
+/* ---- enums --------------------------------------------------------------- */
+/* distance metric (a2 / a2') */
+#define DALI_METRIC_COSINE 0      /* 1.0 - q.g          validateModels.py:47, evaluate.py:291      */
+#define DALI_METRIC_SQEUCLIDEAN 1 /* |q|^2+|g|^2-2q.g   compute_distance_matrix(..,"euclidean"),
+                                     commented call validateModels.py:44, evaluate.py:288          */
+#define DALI_METRIC_EUCLIDEAN 2   /* torch.cdist(p=2)   commented call validateModels.py:45         */
+#define DALI_METRIC_DOT 3         /* q.g similarity     validateModels.py:179, getFeatures.py:285  */
+
+/* arithmetic of the Q x G x D contraction */
+#define DALI_PREC_FP32 0   /* SIMT FFMA, one fmaf chain per element in k order (exact class) */
+#define DALI_PREC_TF32X3 1 /* tcgen05 kind::tf32, hi/lo split, 3 MMAs (fp32 class)           */
+#define DALI_PREC_TF32 2   /* tcgen05 kind::tf32, single pass (fast; <= 0.01 pp mAP)         */
+
+/* accumulation semantics of the CMC/AP reduction */
+#define DALI_ACCUM_CY_F32 0 /* torchreid Cython path: C float, sequential in rank order */
+#define DALI_ACCUM_PY_F64 1 /* torchreid Python path: float64 terms, numpy pairwise sum  */
+
+typedef struct dali_ctx dali_ctx;
+typedef struct dali_rank_plan dali_rank_plan;
+
+/* ---- context --------------------------------------------------------------- */
+int dali_abi_version(void);
+/* device: CUDA ordinal.  Fails with DALI_ERR_CUDA when it is not compute capability 10.x. */
+int dali_ctx_create(dali_ctx **out, int device);
+void dali_ctx_destroy(dali_ctx *ctx);
+/* Attach a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the
+ * context's own stream.  All kernels and copies of this context are issued on it. */
+int dali_ctx_set_stream(dali_ctx *ctx, void *cuda_stream);
+void *dali_ctx_get_stream(dali_ctx *ctx);
+const char *dali_last_error(dali_ctx *ctx);
+const char *dali_strerror(int code);
+/* Per-kernel device timing.  When enabled, every kernel launch of this context is
+ * bracketed by cudaEvents on the context's stream; dali_ctx_timing_read returns, for
+ * kernel slot `which` (DALI_K_*), the number of launches and their summed duration in
+ * milliseconds since the last dali_ctx_timing_reset.  Reading synchronises the stream. */
+#define DALI_K_NORMALIZE 0
+#define DALI_K_DISTMAT 1
+#define DALI_K_RANK_COUNT 2
+#define DALI_K_RANK_FINALIZE 3
+#define DALI_K_TOPK 4
+#define DALI_K_FUSE 5
+#define DALI_K_RANK_GATHER 6
+#define DALI_K_COUNT_ 7
+int dali_ctx_timing_enable(dali_ctx *ctx, int on);
+int dali_ctx_timing_reset(dali_ctx *ctx);
+int dali_ctx_timing_read(dali_ctx *ctx, int which, int *launches, float *total_ms);
+/* Number of this library's kernel launches issued by the context since creation. */
+int64_t dali_ctx_launch_count(dali_ctx *ctx);
+
+/* ---- a1: row L2 normalisation -------------------------------------------- */
+/* out[i,:] = x[i,:] / ||x[i,:]||  (no eps: a zero row yields NaN, as the reference does)
+ * replaces  x/torch.norm(x, dim=1, keepdim=True)   validateModels.py:41-42,
+ *           evaluate.py:285-286, evaluate_ensembled_models.py:278-279,
+ *           evaluateCleanATModels.py:106-107,115-119.
+ * norms_opt (may be NULL): [n] row norms (the "magnitudes" of
+ * evaluateCleanATModels.py:252).  x, out, norms_opt: host or device, fp32, row-major. */
+int dali_normalize_f32(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx,
+                       float *out, int64_t ldo, float *norms_opt);
+
+/* ---- a2 / a2': query x gallery distance matrix ----------------------------- */
+/* out[i,j] (fp32, row-major, leading dimension ld >= G) for q [Q,D], g [G,D] row-major
+ * contiguous.  normalize != 0 applies a1 to both operands first (the reference always
+ * does for cosine).  replaces  1.0 - torch.mm(q, g.T)  validateModels.py:47,
+ * evaluate.py:260-267,291, evaluate_ensembled_models.py:281,300,
+ * evaluateCleanATModels.py:109,121,124. */
+int dali_distmat_f32(dali_ctx *ctx, const float *q, int64_t Q, const float *g, int64_t G,
+                     int64_t D, int metric, int precision, int normalize, float *out,
+                     int64_t ld);
+
+/* ---- a4: multi-model distance fusion -------------------------------------- */
+/* wq == NULL: out = ((d[0]+d[1])+...+d[n-1]) / n   fp32, left to right, true division
+ *   replaces evaluate.py:278, evaluate_ensembled_models.py:313, evaluateCleanATModels.py:127.
+ * wq,wg != NULL: w_m[i,j] = max(wq[m][i], wg[m][j]);
+ *   out = (w_0*d_0 + w_1*d_1 + ...) / (w_0 + w_1 + ...)   each product and sum rounded
+ *   replaces evaluateCleanATModels.py:154-157,193-196,230-233.
+ * d[m]: [Q,G] fp32 with leading dimension ld (all equal), host or device (all alike);
+ * wq[m]: [Q], wg[m]: [G], host or device.  out may alias d[0]. */
+int dali_fuse_f32(dali_ctx *ctx, const float *const *d, int n, const float *const *wq,
+                  const float *const *wg, float *out, int64_t Q, int64_t G, int64_t ld);
+
+/* ---- a5: rank + junk mask + CMC/mAP from a distance matrix ------------------ */
+/* replaces torchreid.metrics.evaluate_rank(distmat, q_pids, g_pids, q_camids, g_camids,
+ *          use_metric_cuhk03=False)   validateModels.py:68-69, evaluate.py:312-313,
+ *          evaluate_ensembled_models.py:324-325, evaluateCleanATModels.py:266-267.
+ * dist: [Q,G] fp32, leading dimension ld, host or device.  Labels: HOST int32 (any
+ * values; only equality matters).  Canonical order: distance ascending, gallery index
+ * ascending, NaN last, -0 == +0 (== numpy stable argsort).  max_rank is clamped to G.
+ * Outputs (HOST): cmc[max_rank] float32, *mAP (double holding the value the chosen
+ * accumulation produces), ap_opt[Q] per-query AP (NaN for invalid queries),
+ * first_rank_opt[Q] 1-based kept rank of the first true match (-1 invalid),
+ * num_valid_opt.  Returns DALI_ERR_NO_VALID_QUERY when no query has a valid match. */
+int dali_eval_rank_f32(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t ld,
+                       const int32_t *q_pid, const int32_t *g_pid, const int32_t *q_cam,
+                       const int32_t *g_cam, int max_rank, int accum_mode, float *cmc,
+                       double *mAP, double *ap_opt, int32_t *first_rank_opt,
+                       int64_t *num_valid_opt);
+
+/* ---- a1+a2+a5 fused: features in, CMC/mAP out -------------------------------- */
+/* replaces validateModels.validate's arithmetic (validateModels.py:41-47,61-69) and the
+ * single-model branch of evaluate.py (285-302).  q,g: host or device fp32 row-major.
+ * distmat_opt (may be NULL): receives the [Q,G] matrix (ld_opt >= G), host or device. */
+int dali_eval_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float *g, int64_t G,
+                           int64_t D, const int32_t *q_pid, const int32_t *g_pid,
+                           const int32_t *q_cam, const int32_t *g_cam, int metric,
+                           int precision, int normalize, int max_rank, int accum_mode,
+                           float *cmc, double *mAP, double *ap_opt, int32_t *first_rank_opt,
+                           int64_t *num_valid_opt, float *distmat_opt, int64_t ld_opt);
+
+/* ---- a7 / a8: top-k ---------------------------------------------------------- */
+/* Per row the k best columns of dist [Q,G] (ld), smallest first (largest != 0: largest
+ * first), ties by ascending column id.  replaces torch.argsort(distmat, dim=1)[:, :20]
+ * validateModels.py:93 and torch.topk(S, k=5, largest=True) validateModels.py:180.
+ * col_ids_opt (may be NULL): int32 [Q,ld] ids reported and used for the tie-break instead
+ * of the column number (merging per-shard candidate lists).  d_out [Q,k] fp32 and
+ * i_out [Q,k] int32: host or device.  k <= 128.  Rows shorter than k are padded with
+ * (+inf | -inf, -1). */
+int dali_topk_f32(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t ld, int k,
+                  int largest, const int32_t *col_ids_opt, float *d_out, int32_t *i_out);
+
+/* Fused a1+a2+a7 for 1:N identification without materialising Q x G (BASELINE config 5):
+ * ids reported are g_base + column. */
+int dali_topk_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float *g, int64_t G,
+                           int64_t D, int metric, int precision, int normalize, int k,
+                           int largest, int32_t g_base, float *d_out, int32_t *i_out);
+
+/* ---- (e) gallery-sharded building blocks ------------------------------------ */
+/* One process per GPU holds all Q queries and a contiguous gallery slab
+ * [g0, g0+Gs).  Labels of the WHOLE gallery are replicated (small).  The host side
+ * (daliid_b200/sharded.py, torch.distributed) runs:
+ *   plan -> gather_keys -> allreduce(sum) -> count -> allreduce(sum) -> finalize.
+ * A "match" is a (query, gallery) pair with equal pid (valid positive or junk); the
+ * plan lays all matches out in one array of length M (query-major, gallery ascending). */
+int dali_rank_plan_create(dali_ctx *ctx, const int32_t *q_pid, const int32_t *g_pid,
+                          const int32_t *q_cam, const int32_t *g_cam, int64_t Q, int64_t G,
+                          dali_rank_plan **out);
+void dali_rank_plan_destroy(dali_rank_plan *plan);
+int64_t dali_rank_plan_num_matches(const dali_rank_plan *plan);
+/* keys_out[M] (DEVICE uint32): order-preserving key of dist[q, g-g0] for matches whose
+ * gallery item lies in the slab, 0 elsewhere (so a sum over ranks assembles all keys). */
+int dali_rank_gather_keys(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist_slab,
+                          int64_t ld, int64_t g0, int64_t Gs, uint32_t *keys_out);
+/* counts_out[M] (DEVICE int32): number of slab columns j with
+ * (key(dist[q,j]), g0+j) <lex (keys[m], gallery id of match m). */
+int dali_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist_slab,
+                    int64_t ld, int64_t g0, int64_t Gs, const uint32_t *keys,
+                    int32_t *counts_out);
+/* keys, counts: DEVICE, already summed over ranks.  Outputs as dali_eval_rank_f32. */
+int dali_rank_finalize(dali_ctx *ctx, const dali_rank_plan *plan, const uint32_t *keys,
+                       const int32_t *counts, int max_rank, int accum_mode, float *cmc,
+                       double *mAP, double *ap_opt, int32_t *first_rank_opt,
+                       int64_t *num_valid_opt);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* DALIID_B200_H_ */

@@ -1,0 +1,132 @@
+"""CPU tests of the oracle itself (no GPU): hand-derived known answers, agreement of the two
+independently written accumulation variants and of the C restatement, an independent
+cross-check against scikit-learn, and the committed golden fixtures."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, distmat_oracle, rank_oracle as ro
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _meta():
+    return json.load(open(os.path.join(GOLDEN, "meta.json")))
+
+
+@pytest.mark.parametrize("kat", _meta()["kat"], ids=lambda k: k["name"])
+@pytest.mark.parametrize("fn", [ro.eval_market1501_cy_f32, ro.eval_market1501_py_f64,
+                                c_oracle.evaluate_rank_c], ids=["cy_f32", "py_f64", "c"])
+def test_known_answers(kat, fn):
+    d = np.array(kat["dist"], dtype=np.float32)
+    cmc, mAP, ap, first = fn(d, kat["q_pid"], kat["g_pid"], kat["q_cam"], kat["g_cam"],
+                             return_details=True)
+    assert mAP == pytest.approx(kat["mAP"], abs=1e-7)
+    assert list(cmc) == kat["cmc"]
+    assert list(first) == kat["first_rank"]
+
+
+def test_all_invalid_raises():
+    d = np.zeros((2, 3), dtype=np.float32)
+    for fn in (ro.eval_market1501_cy_f32, ro.eval_market1501_py_f64, c_oracle.evaluate_rank_c):
+        with pytest.raises(AssertionError, match="all query identities do not appear in gallery"):
+            fn(d, [1, 2], [3, 4, 5], [0, 0], [1, 1, 1])
+
+
+def _random_case(seed, Q=120, G=900, ids=30, cams=5, quant=None):
+    rng = np.random.default_rng(seed)
+    d = rng.random((Q, G)).astype(np.float32)
+    if quant:
+        d = (np.round(d * quant) / quant).astype(np.float32)
+    return (d, rng.integers(0, ids + 3, Q), rng.integers(0, ids, G), rng.integers(0, cams, Q),
+            rng.integers(0, cams, G))
+
+
+@pytest.mark.parametrize("quant", [None, 128])
+def test_variants_agree(quant):
+    d, qp, gp, qc, gc = _random_case(3, quant=quant)
+    a = ro.eval_market1501_cy_f32(d, qp, gp, qc, gc, return_details=True)
+    b = ro.eval_market1501_py_f64(d, qp, gp, qc, gc, return_details=True)
+    c = c_oracle.evaluate_rank_c(d, qp, gp, qc, gc, return_details=True)
+    c2 = c_oracle.evaluate_rank_c(d, qp, gp, qc, gc, tie="c_stable", return_details=True)
+    # C restatement == numpy restatement of the Cython semantics, bit for bit
+    assert np.array_equal(a[0], c[0]) and a[1] == c[1]
+    assert np.array_equal(a[2].astype(np.float32), c[2].astype(np.float32), equal_nan=True)
+    assert np.array_equal(a[3], c[3]) and np.array_equal(c[3], c2[3]) and c[1] == c2[1]
+    # float32-sequential vs float64-pairwise differ only in rounding
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[3], b[3])
+    assert abs(a[1] - b[1]) < 1e-6
+    assert np.nanmax(np.abs(a[2] - b[2])) < 1e-6
+
+
+def test_sklearn_average_precision():
+    from sklearn.metrics import average_precision_score
+    d, qp, gp, qc, gc = _random_case(5, Q=40, G=300, ids=10)
+    _, _, ap, first = ro.eval_market1501_py_f64(d, qp, gp, qc, gc, return_details=True)
+    for q in range(len(qp)):
+        keep = ~((gp == qp[q]) & (gc == qc[q]))
+        y = (gp[keep] == qp[q]).astype(int)
+        if y.sum() == 0:
+            assert first[q] == -1
+            continue
+        assert ap[q] == pytest.approx(average_precision_score(y, -d[q][keep].astype(np.float64)), abs=1e-12)
+
+
+def test_string_labels_equal_int_labels():
+    d, qp, gp, qc, gc = _random_case(7)
+    a = ro.evaluate_rank(d, qp, gp, qc, gc)
+    b = ro.evaluate_rank(d, qp.astype(str), gp.astype(str), qc.astype(str), gc.astype(str))
+    assert np.array_equal(a[0], b[0]) and a[1] == b[1]
+
+
+def test_permutation_invariance_tie_free():
+    d, qp, gp, qc, gc = _random_case(11)
+    perm = np.random.default_rng(0).permutation(d.shape[1])
+    a = ro.evaluate_rank(d, qp, gp, qc, gc, accum="py_f64")
+    b = ro.evaluate_rank(d[:, perm], qp, gp[perm], qc, gc[perm], accum="py_f64")
+    assert np.array_equal(a[0], b[0]) and a[1] == b[1]
+    assert np.all(np.diff(a[0]) >= 0)
+
+
+@pytest.mark.parametrize("name", ["tiny", "ties", "small_gallery"])
+def test_golden_rank_fixtures(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    d = z["cosine"] if name == "tiny" else z["dist"]
+    for accum, fn in (("cy_f32", ro.eval_market1501_cy_f32), ("py_f64", ro.eval_market1501_py_f64)):
+        cmc, mAP, ap, first = fn(d, z["q_pid"], z["g_pid"], z["q_cam"], z["g_cam"], return_details=True)
+        assert np.array_equal(cmc, z[f"cmc_{accum}"])
+        assert mAP == float(z[f"mAP_{accum}"])
+        assert np.array_equal(ap, z[f"ap_{accum}"], equal_nan=True)
+        assert np.array_equal(first, z["first_rank"])
+    cmc, mAP = c_oracle.evaluate_rank_c(d, z["q_pid"], z["g_pid"], z["q_cam"], z["g_cam"])
+    assert np.array_equal(cmc, z["cmc_cy_f32"]) and mAP == float(z["mAP_cy_f32"])
+
+
+def test_golden_distance_fixtures():
+    import torch
+    z = np.load(os.path.join(GOLDEN, "tiny.npz"))
+    q, g = torch.from_numpy(z["qf"]), torch.from_numpy(z["gf"])
+    # CPU BLAS blocking may differ between hosts: tolerance, not bit equality
+    np.testing.assert_allclose(distmat_oracle.cosine_distmat(q, g).numpy(), z["cosine"], atol=2e-6)
+    np.testing.assert_allclose(distmat_oracle.sqeuclidean_distmat(q, g).numpy(), z["sqeuclidean"], rtol=1e-5)
+    np.testing.assert_allclose(distmat_oracle.euclidean_distmat(q, g).numpy(), z["euclidean"], rtol=1e-5)
+
+
+def test_golden_fusion_fixtures():
+    import torch
+    z = np.load(os.path.join(GOLDEN, "fusion.npz"))
+    assert np.array_equal(distmat_oracle.fuse_mean([z["d0"], z["d1"]]), z["mean2"])
+    assert np.array_equal(distmat_oracle.fuse_mean([z["d0"], z["d1"], z["d2"]]), z["mean3"])
+    w = [distmat_oracle.magnitude_weights(torch.from_numpy(z[f"qm{i}"]), torch.from_numpy(z[f"gm{i}"]))
+         for i in range(2)]
+    assert np.array_equal(distmat_oracle.fuse_weighted(w, [z["d0"], z["d1"]]).numpy(), z["weighted"])
+
+
+def test_briar_hits_match_reference_callsite():
+    z = np.load(os.path.join(GOLDEN, "tiny.npz"))
+    hits, top = ro.briar_rank_hits(z["cosine"], z["q_pid"], z["g_pid"])
+    ref = _meta()["callsites"]["validateBRIAR.calculateMetrics"]
+    assert hits == pytest.approx(ref["cmc"], abs=0)
+    assert np.array_equal(top.astype(np.int32), np.load(os.path.join(GOLDEN, "tiny_top20.npy")))
