@@ -1,0 +1,114 @@
+"""GPU tests of the drop-in entry points: same signatures, return values and printed text as
+the reference's call sites (the expected stdout in tests/golden/meta.json was captured by
+running the reference's own functions, lifted unmodified from /root/reference)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _rows(pid, cam):
+    return np.array([["img_%05d.jpg" % i, str(int(pid[i])), str(int(cam[i])), "person"]
+                     for i in range(len(pid))])
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    z = np.load(os.path.join(GOLDEN, "tiny.npz"))
+    meta = json.load(open(os.path.join(GOLDEN, "meta.json")))["callsites"]
+    return z, _rows(z["q_pid"], z["q_cam"]), _rows(z["g_pid"], z["g_cam"]), meta
+
+
+def test_validateModels_calculateMetrics(tiny, capsys):
+    from daliid_b200.validateModels import validationManager
+    z, queries, gallery, meta = tiny
+    v = validationManager.getValidator("Market")
+    cmc, mAP = v.calculateMetrics(torch.from_numpy(z["cosine"]), queries, gallery)
+    ref = meta["validateModels.calculateMetrics[cy_f32]"]
+    assert capsys.readouterr().out == ref["stdout"]
+    assert mAP == ref["mAP"] and [float(x) for x in cmc] == ref["cmc"]
+
+
+def test_calculate_metrics_scripts(tiny, capsys):
+    from daliid_b200 import evaluate as ev
+    z, queries, gallery, meta = tiny
+    assert ev.calculate_metrics(z["cosine"], queries, gallery) is None
+    assert capsys.readouterr().out == meta["evaluate.calculate_metrics[cy_f32]"]["stdout"]
+    ev.calculateMetrics(queries, gallery, torch.from_numpy(z["cosine"]))
+    assert capsys.readouterr().out == meta["evaluateCleanATModels.calculateMetrics[cy_f32]"]["stdout"]
+
+
+def test_validateBRIAR(tiny, capsys):
+    from daliid_b200.validateModels import validationManager
+    z, queries, gallery, meta = tiny
+    v = validationManager.getValidator("BRIAR")
+    cmc, zero = v.calculateMetrics(torch.from_numpy(z["cosine"]), queries, gallery)
+    ref = meta["validateBRIAR.calculateMetrics"]
+    assert capsys.readouterr().out == ref["stdout"]
+    assert [float(x) for x in cmc] == ref["cmc"] and zero == 0
+
+
+class _FakeModel:
+    def eval(self):
+        return self
+
+
+def test_validate_end_to_end(tiny, capsys):
+    """validateModels.validate(queries, gallery, model) with a stub extractor: same return
+    triple (cmc, mAP, distmat) and the same report as the reference on the same features."""
+    from daliid_b200.validateModels import validateModels
+    z, queries, gallery, meta = tiny
+    feats = {len(queries): torch.from_numpy(z["qf"]), len(gallery): torch.from_numpy(z["gf"])}
+    v = validateModels()
+    v.feature_extractor = staticmethod(lambda subset, h, w, model, bs, gpu: feats[len(subset)])
+    v.setParameters(256, 128, False, 0)
+    cmc, mAP, distmat = v.validate(queries, gallery, _FakeModel())
+    out = capsys.readouterr().out
+    assert out == meta["validateModels.calculateMetrics[cy_f32]"]["stdout"]
+    assert isinstance(distmat, torch.Tensor) and tuple(distmat.shape) == (len(queries), len(gallery))
+    np.testing.assert_allclose(distmat.cpu().numpy(), z["cosine"], atol=1e-5)
+    assert abs(mAP - meta["validateModels.calculateMetrics[cy_f32]"]["mAP"]) < 1e-4
+
+
+def test_ensemble_scripts(tiny, capsys):
+    from daliid_b200 import evaluate as ev
+    from oracle import distmat_oracle as do
+    z, queries, gallery, _ = tiny
+    q1, g1 = torch.from_numpy(z["qf"]), torch.from_numpy(z["gf"])
+    q2, g2 = q1.flip(1).contiguous() * 1.5, g1.flip(1).contiguous() * 0.5
+    d1, d2, de = ev.evaluate_ensembled_models(q1, g1, q2, g2, queries, gallery)
+    assert np.array_equal(de, do.fuse_mean([d1, d2]))
+    mags = [torch.norm(t, dim=1, keepdim=True) for t in (q1, g1, q2, g2)]
+    out = ev.evaluate_clean_at_models(q1, g1, q2, g2, queries, gallery, magnitudes=mags)
+    w = [do.magnitude_weights(mags[0], mags[1]), do.magnitude_weights(mags[2], mags[3])]
+    assert np.array_equal(out["weighted"], do.fuse_weighted(w, [out["clean"], out["distortion"]]).numpy())
+    assert capsys.readouterr().out.count("Computing CMC and mAP ...") == 3 + 5
+
+
+def test_msmt17_validator_balanced_accuracy(capsys):
+    from daliid_b200.validateModels import MSMT17_validator
+    rng = np.random.default_rng(4)
+    ids = rng.integers(0, 9, 200)
+    centers = rng.standard_normal((9, 48)).astype(np.float32)
+    tr = torch.from_numpy(centers[ids] + 0.4 * rng.standard_normal((200, 48)).astype(np.float32))
+    vids = rng.integers(0, 9, 90)
+    va = torch.from_numpy(centers[vids] + 0.4 * rng.standard_normal((90, 48)).astype(np.float32))
+    rows = lambda i: np.array([["x", str(int(v)), "0", "person"] for v in i])
+    trainer = type("T", (), dict(img_height=1, img_width=1, gpu_indexes=[0], model_name="m", version="v"))()
+    v = MSMT17_validator(rows(ids), rows(vids), trainer, ".")
+    acc = v.balanced_accuracy_from_features(tr, va)
+    # reference arithmetic (validateModels.py:159-195) on CPU
+    s = tr / torch.norm(tr, dim=1, keepdim=True)
+    labels = np.unique(ids)
+    cs = torch.cat([torch.mean(s[ids == l], dim=0, keepdim=True) for l in labels])
+    cs = cs / torch.norm(cs, dim=1, keepdim=True)
+    S = torch.mm(va / torch.norm(va, dim=1, keepdim=True), cs.T)
+    top = labels[torch.topk(S, k=5, dim=1, largest=True).indices.numpy()][:, 0]
+    tm = vids == top
+    ref = np.mean([tm[vids == l].mean() for l in np.unique(vids)])
+    assert acc == pytest.approx(ref, abs=1e-12)
