@@ -417,6 +417,8 @@ void dali_ctx_destroy(dali_ctx *ctx) {
   for (auto &b : ctx->ws)
     if (b.p) cudaFree(b.p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->plan_stage) cudaFreeHost(ctx->plan_stage);
+  if (ctx->plan_stage_done) cudaEventDestroy(ctx->plan_stage_done);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -621,26 +623,54 @@ int dali_rank_plan_create(dali_ctx *ctx, const int32_t *q_pid, const int32_t *g_
     return set_err(ctx, DALI_ERR_INVALID, "rank plan: bad arguments");
   if (G > INT32_MAX || Q > INT32_MAX) return set_err(ctx, DALI_ERR_UNSUPPORTED, "Q or G exceeds 2^31");
   *out = nullptr;
+  // ---- gallery CSR by identity: `order` = gallery indices sorted by (pid, index) ----------
+  std::vector<int32_t> order(G);
+  std::vector<int64_t> start;          // dense path: start[p - pmin] .. start[p - pmin + 1]
+  std::vector<int32_t> sorted_pid;     // sparse path
+  int32_t pmin = 0, pmax = -1;
+  bool dense = false;
+  if (G) {
+    pmin = pmax = g_pid[0];
+    for (int64_t i = 1; i < G; ++i) { pmin = std::min(pmin, g_pid[i]); pmax = std::max(pmax, g_pid[i]); }
+    const int64_t range = static_cast<int64_t>(pmax) - pmin + 1;
+    dense = range <= 4 * G + 1024;
+    if (dense) {  // counting sort, O(G + range), stable in the gallery index
+      start.assign(range + 1, 0);
+      for (int64_t i = 0; i < G; ++i) start[g_pid[i] - pmin + 1]++;
+      for (int64_t r = 0; r < range; ++r) start[r + 1] += start[r];
+      std::vector<int64_t> cur(start.begin(), start.end() - 1);
+      for (int64_t i = 0; i < G; ++i) order[cur[g_pid[i] - pmin]++] = static_cast<int32_t>(i);
+    } else {
+      std::iota(order.begin(), order.end(), 0);
+      std::stable_sort(order.begin(), order.end(),
+                       [&](int32_t a, int32_t b) { return g_pid[a] < g_pid[b]; });
+      sorted_pid.resize(G);
+      for (int64_t i = 0; i < G; ++i) sorted_pid[i] = g_pid[order[i]];
+    }
+  }
   dali_rank_plan *p = new dali_rank_plan();
   p->ctx = ctx;
   p->Q = Q;
   p->G = G;
-  // gallery CSR by identity: indices sorted by (pid, index)
-  std::vector<int32_t> order(G);
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(),
-                   [&](int32_t a, int32_t b) { return g_pid[a] < g_pid[b]; });
-  std::vector<int32_t> sorted_pid(G);
-  for (int64_t i = 0; i < G; ++i) sorted_pid[i] = g_pid[order[i]];
   p->h_off.assign(Q + 1, 0);
   p->h_nv.assign(Q, 0);
   p->h_njunk.assign(Q, 0);
-  std::vector<std::pair<int64_t, int64_t>> range(Q);
+  std::vector<std::pair<int64_t, int64_t>> range_of(Q);
   int64_t M = 0;
   for (int64_t q = 0; q < Q; ++q) {
-    auto lo = std::lower_bound(sorted_pid.begin(), sorted_pid.end(), q_pid[q]);
-    auto hi = std::upper_bound(lo, sorted_pid.end(), q_pid[q]);
-    range[q] = {lo - sorted_pid.begin(), hi - sorted_pid.begin()};
+    int64_t lo = 0, hi = 0;
+    if (G) {
+      if (dense) {
+        const int64_t r = static_cast<int64_t>(q_pid[q]) - pmin;
+        if (r >= 0 && r <= static_cast<int64_t>(pmax) - pmin) { lo = start[r]; hi = start[r + 1]; }
+      } else {
+        auto l = std::lower_bound(sorted_pid.begin(), sorted_pid.end(), q_pid[q]);
+        auto h = std::upper_bound(l, sorted_pid.end(), q_pid[q]);
+        lo = l - sorted_pid.begin();
+        hi = h - sorted_pid.begin();
+      }
+    }
+    range_of[q] = {lo, hi};
     p->h_off[q] = M;
     M += hi - lo;
   }
@@ -650,41 +680,71 @@ int dali_rank_plan_create(dali_ctx *ctx, const int32_t *q_pid, const int32_t *g_
     return set_err(ctx, DALI_ERR_UNSUPPORTED, "more than 2^31 same-identity (query, gallery) pairs");
   }
   p->M = M;
-  std::vector<int32_t> gid(std::max<int64_t>(M, 1));
+  // ---- build the device image in pinned staging, upload asynchronously -----------------
+  const size_t b_off = sizeof(int64_t) * (Q + 1);
+  const size_t b_nv = sizeof(int32_t) * std::max<int64_t>(Q, 1);
+  const size_t b_gid = sizeof(int32_t) * std::max<int64_t>(M, 1);
+  const size_t total = b_off + b_nv + b_gid;
+  auto fail = [&](cudaError_t e, const char *what) {
+    std::string m = cudaGetErrorString(e);
+    dali_rank_plan_destroy(p);
+    return set_err(ctx, DALI_ERR_CUDA, std::string("rank plan ") + what + ": " + m);
+  };
+  cudaError_t e;
+  if (!ctx->plan_stage_done &&
+      (e = cudaEventCreateWithFlags(&ctx->plan_stage_done, cudaEventDisableTiming)) != cudaSuccess)
+    return fail(e, "event");
+  if ((e = cudaEventSynchronize(ctx->plan_stage_done)) != cudaSuccess) return fail(e, "staging wait");
+  if (total > ctx->plan_stage_cap) {
+    if (ctx->plan_stage) cudaFreeHost(ctx->plan_stage);
+    ctx->plan_stage = nullptr;
+    ctx->plan_stage_cap = 0;
+    if ((e = cudaMallocHost(&ctx->plan_stage, total + total / 4 + 4096)) != cudaSuccess)
+      return fail(e, "pinned staging");
+    ctx->plan_stage_cap = total + total / 4 + 4096;
+  }
+  char *hs = static_cast<char *>(ctx->plan_stage);
+  int64_t *s_off = reinterpret_cast<int64_t *>(hs);
+  int32_t *s_nv = reinterpret_cast<int32_t *>(hs + b_off);
+  int32_t *s_gid = reinterpret_cast<int32_t *>(hs + b_off + b_nv);
+  std::memcpy(s_off, p->h_off.data(), b_off);
   for (int64_t q = 0; q < Q; ++q) {
     int64_t w = p->h_off[q];
     int nv = 0, nj = 0;
-    for (int64_t i = range[q].first; i < range[q].second; ++i)  // valid positives first
-      if (g_cam[order[i]] != q_cam[q]) { gid[w++] = order[i]; ++nv; }
-    for (int64_t i = range[q].first; i < range[q].second; ++i)  // then junk (same id, same camera)
-      if (g_cam[order[i]] == q_cam[q]) { gid[w++] = order[i]; ++nj; }
+    const int32_t qc = q_cam[q];
+    for (int64_t i = range_of[q].first; i < range_of[q].second; ++i)  // valid positives first
+      if (g_cam[order[i]] != qc) { s_gid[w++] = order[i]; ++nv; }
+    for (int64_t i = range_of[q].first; i < range_of[q].second; ++i)  // then junk (same id, same camera)
+      if (g_cam[order[i]] == qc) { s_gid[w++] = order[i]; ++nj; }
     p->h_nv[q] = nv;
     p->h_njunk[q] = nj;
+    s_nv[q] = nv;
     p->max_nv = std::max(p->max_nv, nv);
     p->max_m = std::max(p->max_m, nv + nj);
   }
-  auto fail = [&](cudaError_t e) {
-    std::string m = cudaGetErrorString(e);
-    dali_rank_plan_destroy(p);
-    return set_err(ctx, DALI_ERR_CUDA, "rank plan upload: " + m);
-  };
-  cudaError_t e;
-  if ((e = cudaMalloc(&p->d_off, sizeof(int64_t) * (Q + 1))) != cudaSuccess) return fail(e);
-  if ((e = cudaMalloc(&p->d_nv, sizeof(int32_t) * std::max<int64_t>(Q, 1))) != cudaSuccess) return fail(e);
-  if ((e = cudaMalloc(&p->d_gid, sizeof(int32_t) * std::max<int64_t>(M, 1))) != cudaSuccess) return fail(e);
-  if ((e = cudaMemcpyAsync(p->d_off, p->h_off.data(), sizeof(int64_t) * (Q + 1), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return fail(e);
-  if (Q && (e = cudaMemcpyAsync(p->d_nv, p->h_nv.data(), sizeof(int32_t) * Q, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return fail(e);
-  if (M && (e = cudaMemcpyAsync(p->d_gid, gid.data(), sizeof(int32_t) * M, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return fail(e);
-  if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail(e);  // gid is a local
+  if (!ctx->pool_ready) {  // keep freed blocks in the default pool: allocation becomes ~free
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    ctx->pool_ready = true;
+  }
+  if ((e = cudaMallocAsync(&p->d_block, total, ctx->stream)) != cudaSuccess) return fail(e, "allocation");
+  char *db = static_cast<char *>(p->d_block);
+  p->d_off = reinterpret_cast<int64_t *>(db);
+  p->d_nv = reinterpret_cast<int32_t *>(db + b_off);
+  p->d_gid = reinterpret_cast<int32_t *>(db + b_off + b_nv);
+  if ((e = cudaMemcpyAsync(p->d_block, hs, total, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+    return fail(e, "upload");
+  if ((e = cudaEventRecord(ctx->plan_stage_done, ctx->stream)) != cudaSuccess) return fail(e, "event record");
   *out = p;
   return DALI_OK;
 }
 
 void dali_rank_plan_destroy(dali_rank_plan *plan) {
   if (!plan) return;
-  if (plan->d_off) cudaFree(plan->d_off);
-  if (plan->d_nv) cudaFree(plan->d_nv);
-  if (plan->d_gid) cudaFree(plan->d_gid);
+  if (plan->d_block) cudaFreeAsync(plan->d_block, plan->ctx->stream);
   delete plan;
 }
 
@@ -751,15 +811,19 @@ int dali_eval_rank_f32(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, i
   if (rc) return rc;
   if (Q < 0 || G < 0 || ld < G || (!dist && Q && G) || !cmc || !mAP || max_rank < 1)
     return set_err(ctx, DALI_ERR_INVALID, "eval_rank: bad shape or null pointer");
+  // stage the matrix first (asynchronous when the host buffer is pinned) so the host-side
+  // plan construction overlaps the copy
+  const float *dd = dist;
+  int64_t ldd = ld;
+  if (Q && G) {
+    rc = stage_in(ctx, WS_DIST, dist, Q, G, ld, &dd, &ldd);
+    if (rc) return rc;
+  }
   dali_rank_plan *plan = nullptr;
   rc = dali_rank_plan_create(ctx, q_pid, g_pid, q_cam, g_cam, Q, G, &plan);
   if (rc) return rc;
-  const float *dd = dist;
-  int64_t ldd = ld;
-  if (Q && G) rc = stage_in(ctx, WS_DIST, dist, Q, G, ld, &dd, &ldd);
-  if (!rc)
-    rc = rank_from_device(ctx, plan, dd, ldd, max_rank, accum_mode, cmc, mAP, ap_opt,
-                          first_rank_opt, num_valid_opt);
+  rc = rank_from_device(ctx, plan, dd, ldd, max_rank, accum_mode, cmc, mAP, ap_opt,
+                        first_rank_opt, num_valid_opt);
   dali_rank_plan_destroy(plan);
   return rc;
 }
@@ -779,9 +843,6 @@ int dali_eval_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float
   if (rc) return rc;
   if (metric == DALI_METRIC_DOT)
     return set_err(ctx, DALI_ERR_INVALID, "eval_features ranks distances; DOT is a similarity");
-  dali_rank_plan *plan = nullptr;
-  rc = dali_rank_plan_create(ctx, q_pid, g_pid, q_cam, g_cam, Q, G, &plan);
-  if (rc) return rc;
   const bool user_dev = distmat_opt && is_device_ptr(distmat_opt);
   float *dd = distmat_opt;
   int64_t ldd = ld_opt;
@@ -789,17 +850,23 @@ int dali_eval_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float
     ldd = round_up(std::max<int64_t>(G, 1), 4);
     void *t;
     rc = ws_ensure(ctx, WS_DIST, sizeof(float) * std::max<int64_t>(Q, 1) * ldd, &t);
+    if (rc) return rc;
     dd = static_cast<float *>(t);
   }
-  if (!rc && Q && G) rc = distmat_to(ctx, q, Q, g, G, D, metric, precision, normalize, dd, ldd);
-  if (!rc && distmat_opt && !user_dev && Q && G) {
-    cudaError_t e = cudaMemcpy2DAsync(distmat_opt, sizeof(float) * ld_opt, dd, sizeof(float) * ldd,
-                                      sizeof(float) * G, Q, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e != cudaSuccess) rc = set_err(ctx, DALI_ERR_CUDA, cudaGetErrorString(e));
+  // 1. operand preparation + contraction are enqueued first (asynchronous) ...
+  if (Q && G) {
+    rc = distmat_to(ctx, q, Q, g, G, D, metric, precision, normalize, dd, ldd);
+    if (rc) return rc;
   }
-  if (!rc)
-    rc = rank_from_device(ctx, plan, dd, ldd, max_rank, accum_mode, cmc, mAP, ap_opt,
-                          first_rank_opt, num_valid_opt);
+  if (distmat_opt && !user_dev && Q && G)
+    DALI_CUDA_OK(ctx, cudaMemcpy2DAsync(distmat_opt, sizeof(float) * ld_opt, dd, sizeof(float) * ldd,
+                                        sizeof(float) * G, Q, cudaMemcpyDeviceToHost, ctx->stream));
+  // 2. ... so the host builds the rank plan (gallery CSR by identity) while the GPU works
+  dali_rank_plan *plan = nullptr;
+  rc = dali_rank_plan_create(ctx, q_pid, g_pid, q_cam, g_cam, Q, G, &plan);
+  if (rc) return rc;
+  rc = rank_from_device(ctx, plan, dd, ldd, max_rank, accum_mode, cmc, mAP, ap_opt,
+                        first_rank_opt, num_valid_opt);
   dali_rank_plan_destroy(plan);
   return rc;
 }

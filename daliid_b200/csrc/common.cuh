@@ -85,6 +85,10 @@ struct dali_ctx {
   dali::DevBuf ws[dali::WS_COUNT_];
   void *pinned = nullptr;  // small pinned scratch for results
   size_t pinned_cap = 0;
+  void *plan_stage = nullptr;  // pinned staging of the rank plan (async upload)
+  size_t plan_stage_cap = 0;
+  cudaEvent_t plan_stage_done = nullptr;  // the last upload out of plan_stage
+  bool pool_ready = false;
   // timing
   bool timing = false;
   int t_launches[DALI_K_COUNT_] = {0};
@@ -105,7 +109,8 @@ struct dali_rank_plan {
   std::vector<int64_t> h_off;    // [Q+1] offsets into the match arrays
   std::vector<int32_t> h_nv;     // [Q]   number of valid positives (they come first)
   std::vector<int32_t> h_njunk;  // [Q]
-  // device copies
+  // device copies: one stream-ordered allocation [off (Q+1) int64 | nv Q int32 | gid M int32]
+  void *d_block = nullptr;
   int64_t *d_off = nullptr;
   int32_t *d_nv = nullptr;
   int32_t *d_gid = nullptr;  // [M] gallery id of each match (valid ascending, then junk ascending)

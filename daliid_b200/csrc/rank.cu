@@ -7,6 +7,9 @@
 //     1 + #{ j : (key(d[q,j]), j) <lex (key(d[q,p]), p) }  -  #{ junk u : (key_u,u) < (key_p,p) }
 // which needs ONE streaming pass over the distance row (4 B / pair, HBM bound) and no
 // label reads in the hot loop (junk items are all inside the query's match list).
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace dali {
@@ -149,6 +152,156 @@ rank_count_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int64_
     count_row<32>(row, c0, c1, gbase, keys + o, gid + o, n, counts + o, atom, s_acc);
 }
 
+// ------------------------------ count, v2 -----------------------------------
+// LUT-bucketed counting: per-element work independent of the number of positives.
+//   1. the CTA sorts its (<= 254) thresholds T[0..n) by composite (key, gallery id);
+//   2. a lookup table over NB uniform bins of the key range [key(T[0]), key(T[n-1])] gives, for a
+//      bin, how many thresholds lie in lower bins and how many lie in this bin (almost always 0);
+//   3. each streamed element finds bucket b = #{i : T[i] <= element} with one table lookup
+//      (+ exact 64-bit compares only inside a threshold-holding bin) and bumps a PRIVATE 16-bit
+//      counter cnt[b][thread] in shared memory: no atomics, at most 2-way bank conflicts;
+//   4. counters are reduced per bucket; count_below(T[i]) = sum_{b <= i} hist[b].
+constexpr int kV2Threads = 256;
+constexpr int kV2Chunk = 254;  // thresholds per pass; buckets 0..n fit 8 bits
+
+
+template <int LOG2NB>
+__global__ void __launch_bounds__(kV2Threads)
+rank_count_v2_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int64_t Gs,
+                     const int64_t *__restrict__ off, const int32_t *__restrict__ nvalid,
+                     const int32_t *__restrict__ gid, const uint32_t *__restrict__ keys,
+                     int32_t *__restrict__ counts, int nsplit) {
+  constexpr int NB = 1 << LOG2NB;
+  extern __shared__ __align__(16) uint8_t smem_v2[];
+  uint64_t *Tu = reinterpret_cast<uint64_t *>(smem_v2);            // [256] unsorted
+  uint64_t *T = Tu + 256;                                          // [256] sorted
+  uint32_t *hist = reinterpret_cast<uint32_t *>(T + 256);          // [256]
+  uint16_t *orig = reinterpret_cast<uint16_t *>(hist + 256);       // [256]
+  uint16_t *lut = orig + 256;                                      // [NB]
+  uint16_t *cnt = lut + NB;                                        // [(n) * 256] private counters
+
+  const int64_t q = blockIdx.x;
+  const int chunk = blockIdx.y;
+  const int nv = nvalid[q];
+  if (chunk * kV2Chunk >= nv) return;  // uniform exit
+  const int n = min(kV2Chunk, nv - chunk * kV2Chunk);
+  const int64_t o = off[q] + static_cast<int64_t>(chunk) * kV2Chunk;
+  const int tid = threadIdx.x;
+
+  // 1. sort the thresholds by counting (composites are distinct: gallery ids differ)
+  if (tid < n) Tu[tid] = composite(__ldg(keys + o + tid), static_cast<uint32_t>(__ldg(gid + o + tid)));
+  __syncthreads();
+  if (tid < n) {
+    const uint64_t c = Tu[tid];
+    int pos = 0;
+    for (int u = 0; u < n; ++u) pos += (Tu[u] < c) ? 1 : 0;
+    T[pos] = c;
+    orig[pos] = static_cast<uint16_t>(tid);
+  }
+  __syncthreads();
+  const uint32_t klo = static_cast<uint32_t>(T[0] >> 32);
+  const uint32_t khi = static_cast<uint32_t>(T[n - 1] >> 32);
+  const int bits = 32 - __clz(khi - klo);  // 0 when khi == klo
+  const int sh = bits > LOG2NB ? bits - LOG2NB : 0;
+
+  // 2. lookup table: lut[b] = (#thresholds in lower bins) | (#thresholds in bin b) << 8
+  {
+    constexpr int BPT = NB / kV2Threads;
+    const int b0 = tid * BPT;
+    int lo = 0, hi = n;  // first threshold whose bin >= b0
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const int bm = static_cast<int>((static_cast<uint32_t>(T[mid] >> 32) - klo) >> sh);
+      if (bm < b0) lo = mid + 1; else hi = mid;
+    }
+    int i = lo;
+#pragma unroll 1
+    for (int b = b0; b < b0 + BPT; ++b) {
+      const int base = i;
+      while (i < n && static_cast<int>((static_cast<uint32_t>(T[i] >> 32) - klo) >> sh) == b) ++i;
+      lut[b] = static_cast<uint16_t>(base | ((i - base) << 8));
+    }
+  }
+  // 3. zero the private counters (bucket n = "above every threshold" is never counted)
+  {
+    uint32_t *w = reinterpret_cast<uint32_t *>(cnt);
+    for (int i = tid; i < n * (kV2Threads / 2); i += kV2Threads) w[i] = 0u;
+  }
+  __syncthreads();
+
+  // 4. stream the row segment of this split
+  const int64_t per = (((Gs + nsplit - 1) / nsplit) + 3) & ~int64_t(3);
+  const int64_t c0r = per * static_cast<int64_t>(blockIdx.z);
+  const int64_t c0 = c0r < Gs ? c0r : Gs;
+  const int64_t c1 = (c0 + per) < Gs ? (c0 + per) : Gs;
+  const float *row = dist + q * ld;
+  const uint32_t gbase = static_cast<uint32_t>(g0);
+  uint16_t *mycnt = cnt + tid;
+
+  auto visit = [&](float d, uint32_t g) {
+    const uint32_t key = dist_key(d);
+    const uint32_t dk = max(key, klo) - klo;
+    const uint32_t bin = min(dk >> sh, static_cast<uint32_t>(NB - 1));
+    const uint32_t e = lut[bin];
+    uint32_t b = e & 0xFFu;
+    const uint32_t ni = e >> 8;
+    if (ni) {  // rare: the bin holds thresholds -> exact compares against just those
+      const uint64_t c = composite(key, g);
+      const uint32_t base = b;
+      for (uint32_t j = 0; j < ni; ++j) b += (T[base + j] <= c) ? 1u : 0u;
+    }
+    if (b < static_cast<uint32_t>(n)) mycnt[b * kV2Threads] += 1;
+  };
+
+  const int mis = static_cast<int>((reinterpret_cast<uintptr_t>(row + c0) >> 2) & 3);
+  int64_t head = (4 - mis) & 3;
+  if (head > c1 - c0) head = c1 - c0;
+  if (tid < head) visit(__ldg(row + c0 + tid), gbase + static_cast<uint32_t>(c0 + tid));
+  const int64_t cv0 = c0 + head;
+  const int64_t nvec = (c1 - cv0) >> 2;
+  int64_t v = tid;
+  for (; v + kV2Threads < nvec; v += 2 * kV2Threads) {
+    const float4 x0 = ld_stream_f4(row + cv0 + 4 * v);
+    const float4 x1 = ld_stream_f4(row + cv0 + 4 * (v + kV2Threads));
+    const uint32_t ga = gbase + static_cast<uint32_t>(cv0 + 4 * v);
+    const uint32_t gb = gbase + static_cast<uint32_t>(cv0 + 4 * (v + kV2Threads));
+    visit(x0.x, ga); visit(x0.y, ga + 1); visit(x0.z, ga + 2); visit(x0.w, ga + 3);
+    visit(x1.x, gb); visit(x1.y, gb + 1); visit(x1.z, gb + 2); visit(x1.w, gb + 3);
+  }
+  if (v < nvec) {
+    const float4 x0 = ld_stream_f4(row + cv0 + 4 * v);
+    const uint32_t ga = gbase + static_cast<uint32_t>(cv0 + 4 * v);
+    visit(x0.x, ga); visit(x0.y, ga + 1); visit(x0.z, ga + 2); visit(x0.w, ga + 3);
+  }
+  const int64_t ct0 = cv0 + 4 * nvec;
+  if (tid < c1 - ct0) visit(__ldg(row + ct0 + tid), gbase + static_cast<uint32_t>(ct0 + tid));
+  __syncthreads();
+
+  // 5. reduce the private counters per bucket (one warp per bucket, 8 counters per lane)
+  {
+    const int w = tid >> 5, l = tid & 31;
+    for (int b = w; b < n; b += kV2Threads / 32) {
+      const uint4 x = *reinterpret_cast<const uint4 *>(cnt + b * kV2Threads + l * 8);
+      uint32_t sum = (x.x & 0xFFFFu) + (x.x >> 16) + (x.y & 0xFFFFu) + (x.y >> 16) +
+                     (x.z & 0xFFFFu) + (x.z >> 16) + (x.w & 0xFFFFu) + (x.w >> 16);
+      sum = __reduce_add_sync(0xffffffffu, sum);
+      if (l == 0) hist[b] = sum;
+    }
+  }
+  __syncthreads();
+  // 6. count_below(T[i]) = sum_{b <= i} hist[b]; scatter back to plan order
+  if (tid < n) {
+    uint32_t below = 0;
+    for (int b = 0; b <= tid; ++b) below += hist[b];
+    int32_t *dst = counts + o + orig[tid];
+    if (nsplit > 1) {
+      if (below) atomicAdd(dst, static_cast<int32_t>(below));
+    } else {
+      *dst = static_cast<int32_t>(below);
+    }
+  }
+}
+
 // ------------------------------ finalize -----------------------------------
 constexpr int kFinThreads = 128;
 constexpr int kFinCap = 2048;  // matches staged in shared memory
@@ -220,24 +373,60 @@ int launch_rank_gather(dali_ctx *ctx, const dali_rank_plan *plan, const float *d
   return DALI_OK;
 }
 
+static size_t v2_smem_bytes(int log2nb, int nbuckets) {
+  return 256 * 8 * 2 + 256 * 4 + 256 * 2 + (size_t(1) << log2nb) * 2 + size_t(nbuckets) * kV2Threads * 2;
+}
+
 int launch_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist, int64_t ld,
                       int64_t g0, int64_t Gs, const uint32_t *keys, int32_t *counts) {
   if (plan->M == 0 || plan->Q == 0) return DALI_OK;
   DALI_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, sizeof(int32_t) * plan->M, ctx->stream));
   if (plan->max_nv == 0 || Gs == 0) return DALI_OK;
-  const int nchunk = (plan->max_nv + kChunk - 1) / kChunk;
-  if (nchunk > 65535) return set_err(ctx, DALI_ERR_UNSUPPORTED, "more than 2M positives for one query");
-  // enough CTAs for >= 4 per SM; never split a row below 4096 columns
-  int64_t want = (4ll * ctx->num_sms + plan->Q - 1) / (plan->Q > 0 ? plan->Q : 1);
-  int64_t max_split = (Gs + 4095) / 4096;
-  int nsplit = static_cast<int>(want < 1 ? 1 : (want > max_split ? max_split : want));
-  if (nsplit < 1) nsplit = 1;
-  if (nsplit > 1024) nsplit = 1024;
+  static const bool use_v1 = getenv("DALI_RANK_V1") != nullptr;  // debugging cross-check only
+  const int per_cta = use_v1 ? kChunk : kV2Chunk;
+  const int nchunk = (plan->max_nv + per_cta - 1) / per_cta;
+  if (nchunk > 65535) return set_err(ctx, DALI_ERR_UNSUPPORTED, "too many positives for one query");
+  // enough CTAs for >= 4 per SM; never split a row below 4096 columns; a v2 CTA counts in
+  // 16-bit private counters, so it may see at most 65535 * 256 columns
+  int64_t want = (4ll * ctx->num_sms + plan->Q * nchunk - 1) / (plan->Q * nchunk);
+  const int64_t max_split = (Gs + 4095) / 4096;
+  const int64_t min_split = (Gs + (8ll << 20) - 1) / (8ll << 20);
+  int64_t ns = std::max<int64_t>(1, std::min(want, max_split));
+  ns = std::max(ns, min_split);
+  if (ns > 65535) return set_err(ctx, DALI_ERR_UNSUPPORTED, "slab too wide for one launch");
+  const int nsplit = static_cast<int>(ns);
   dim3 grid(static_cast<unsigned>(plan->Q), nchunk, nsplit);
   KTimer t(ctx, DALI_K_RANK_COUNT);
-  rank_count_kernel<<<grid, kCountThreads, 0, ctx->stream>>>(dist, ld, g0, Gs, plan->d_off,
-                                                            plan->d_nv, plan->d_gid, keys, counts,
-                                                            nsplit);
+  if (use_v1) {
+    rank_count_kernel<<<grid, kCountThreads, 0, ctx->stream>>>(dist, ld, g0, Gs, plan->d_off,
+                                                              plan->d_nv, plan->d_gid, keys, counts,
+                                                              nsplit);
+  } else {
+    const int nb = std::min(plan->max_nv, kV2Chunk);
+    // finer table when many thresholds share the key range
+    const int log2nb = nb > 64 ? 12 : 11;
+    const size_t smem = v2_smem_bytes(log2nb, nb);
+    static size_t attr11 = 0, attr12 = 0;
+    if (log2nb == 11) {
+      if (smem > attr11) {
+        DALI_CUDA_OK(ctx, cudaFuncSetAttribute(rank_count_v2_kernel<11>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>(std::max<size_t>(smem, 48 * 1024))));
+        attr11 = std::max<size_t>(smem, 48 * 1024);
+      }
+      rank_count_v2_kernel<11><<<grid, kV2Threads, smem, ctx->stream>>>(
+          dist, ld, g0, Gs, plan->d_off, plan->d_nv, plan->d_gid, keys, counts, nsplit);
+    } else {
+      if (smem > attr12) {
+        DALI_CUDA_OK(ctx, cudaFuncSetAttribute(rank_count_v2_kernel<12>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>(std::max<size_t>(smem, 48 * 1024))));
+        attr12 = std::max<size_t>(smem, 48 * 1024);
+      }
+      rank_count_v2_kernel<12><<<grid, kV2Threads, smem, ctx->stream>>>(
+          dist, ld, g0, Gs, plan->d_off, plan->d_nv, plan->d_gid, keys, counts, nsplit);
+    }
+  }
   DALI_CUDA_OK(ctx, cudaGetLastError());
   return DALI_OK;
 }
