@@ -11,10 +11,6 @@
 
 namespace dali {
 
-int launch_prep(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx, float *plane0,
-                float *plane1, int64_t ldo, int64_t d_pad, int64_t rows_pad, int do_normalize,
-                int round_mode, float *norms, float *sq);
-
 int set_err(dali_ctx *ctx, int code, const std::string &msg) {
   if (ctx) ctx->err = msg;
   return code;
@@ -279,26 +275,28 @@ static int check_ctx(dali_ctx *ctx) {
 
 // Prepared operand planes for the contraction kernels.
 struct Prepared {
-  float *planes = nullptr;  // [npl][rows_pad][Dp]
+  float *planes = nullptr;  // [npl][rows_pad][Dp] fp32
+  void *planes16 = nullptr; // [2][rows_pad][Dp] bf16 (TF32C)
   float *sq = nullptr;      // [rows] sum of squares (euclidean metrics)
   int64_t rows_pad = 0, Dp = 0;
   int npl = 1;
 };
 
-static int prepare_operand(dali_ctx *ctx, int ws_in, int ws_planes, int ws_sq, const float *x,
-                           int64_t n, int64_t D, int metric, int precision, int normalize,
-                           Prepared *out) {
-  const float *xd = nullptr;
-  int64_t ldx = D;
-  int rc = stage_in(ctx, ws_in, x, n, D, D, &xd, &ldx);
-  if (rc) return rc;
+static int alloc_operand(dali_ctx *ctx, int ws_planes, int ws_p16, int ws_sq, int64_t n, int64_t D,
+                         int metric, int precision, Prepared *out) {
   out->Dp = round_up(D, 32);
   out->rows_pad = round_up(std::max<int64_t>(n, 1), 256);
   out->npl = precision == DALI_PREC_TF32X3 ? 2 : 1;
   void *pl = nullptr;
-  rc = ws_ensure(ctx, ws_planes, sizeof(float) * out->npl * out->rows_pad * out->Dp, &pl);
+  int rc = ws_ensure(ctx, ws_planes, sizeof(float) * out->npl * out->rows_pad * out->Dp, &pl);
   if (rc) return rc;
   out->planes = static_cast<float *>(pl);
+  if (precision == DALI_PREC_TF32C) {
+    void *t = nullptr;
+    rc = ws_ensure(ctx, ws_p16, 2 * 2 * out->rows_pad * out->Dp, &t);
+    if (rc) return rc;
+    out->planes16 = t;
+  }
   const bool need_sq = metric == DALI_METRIC_SQEUCLIDEAN || metric == DALI_METRIC_EUCLIDEAN;
   if (need_sq) {
     void *s = nullptr;
@@ -306,25 +304,48 @@ static int prepare_operand(dali_ctx *ctx, int ws_in, int ws_planes, int ws_sq, c
     if (rc) return rc;
     out->sq = static_cast<float *>(s);
   }
-  return launch_prep(ctx, xd, n, D, ldx, out->planes,
-                     out->npl == 2 ? out->planes + out->rows_pad * out->Dp : nullptr, out->Dp,
-                     out->Dp, out->rows_pad, normalize, precision == DALI_PREC_FP32 ? 0 : 1, nullptr,
-                     out->sq);
+  return DALI_OK;
 }
 
-static int contract(dali_ctx *ctx, const Prepared &a, const Prepared &b, int64_t Q, int64_t G,
-                    int metric, int precision, float *out, int64_t ld) {
+// Prepare rows [r0, r1) of an operand (r1 - r0 may include zero padding rows) from device rows xd.
+static int prep_rows(dali_ctx *ctx, const Prepared &o, const float *xd, int64_t ldx, int64_t D,
+                     int64_t r0, int64_t n_valid, int64_t r1, int precision, int normalize) {
+  char *p16 = static_cast<char *>(o.planes16);
+  const int64_t off = r0 * o.Dp;
+  return launch_prep(ctx, xd, n_valid, D, ldx, o.planes + off,
+                     o.npl == 2 ? o.planes + o.rows_pad * o.Dp + off : nullptr, o.Dp, o.Dp, r1 - r0,
+                     normalize, precision == DALI_PREC_FP32 ? 0 : 1, nullptr,
+                     o.sq ? o.sq + r0 : nullptr, p16 ? p16 + 2 * off : nullptr,
+                     p16 ? p16 + 2 * (o.rows_pad * o.Dp + off) : nullptr);
+}
+
+static int prepare_operand(dali_ctx *ctx, int ws_in, int ws_planes, int ws_p16, int ws_sq, const float *x,
+                           int64_t n, int64_t D, int metric, int precision, int normalize,
+                           Prepared *out) {
+  const float *xd = nullptr;
+  int64_t ldx = D;
+  int rc = stage_in(ctx, ws_in, x, n, D, D, &xd, &ldx);
+  if (rc) return rc;
+  rc = alloc_operand(ctx, ws_planes, ws_p16, ws_sq, n, D, metric, precision, out);
+  if (rc) return rc;
+  return prep_rows(ctx, *out, xd, ldx, D, 0, n, out->rows_pad, precision, normalize);
+}
+
+// out[:, 0:Gs] = distances of all Q queries to gallery rows [g_row0, g_row0 + Gs)
+static int contract(dali_ctx *ctx, const Prepared &a, const Prepared &b, int64_t Q, int64_t g_row0,
+                    int64_t Gs, int metric, int precision, float *out, int64_t ld) {
+  const float *gsq = b.sq ? b.sq + g_row0 : nullptr;
   if (precision == DALI_PREC_FP32)
-    return launch_distmat_simt(ctx, a.planes, b.planes, Q, G, a.Dp, a.Dp, b.Dp, metric, a.sq, b.sq,
-                               out, ld);
-  return launch_distmat_umma(ctx, a.planes, b.planes, Q, G, a.Dp, a.rows_pad, b.rows_pad,
-                             precision == DALI_PREC_TF32X3, metric, a.sq, b.sq, out, ld);
+    return launch_distmat_simt(ctx, a.planes, b.planes + g_row0 * b.Dp, Q, Gs, a.Dp, a.Dp, b.Dp, metric,
+                               a.sq, gsq, out, ld);
+  return launch_distmat_umma(ctx, a.planes, b.planes, a.planes16, b.planes16, Q, Gs, a.Dp, a.rows_pad,
+                             b.rows_pad, g_row0, precision, metric, a.sq, gsq, out, ld);
 }
 
 static int check_metric_prec(dali_ctx *ctx, int metric, int precision) {
   if (metric < DALI_METRIC_COSINE || metric > DALI_METRIC_DOT)
     return set_err(ctx, DALI_ERR_INVALID, "unknown metric");
-  if (precision < DALI_PREC_FP32 || precision > DALI_PREC_TF32)
+  if (precision < DALI_PREC_FP32 || precision > DALI_PREC_TF32C)
     return set_err(ctx, DALI_ERR_INVALID, "unknown precision");
   return DALI_OK;
 }
@@ -419,6 +440,8 @@ void dali_ctx_destroy(dali_ctx *ctx) {
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->plan_stage) cudaFreeHost(ctx->plan_stage);
   if (ctx->plan_stage_done) cudaEventDestroy(ctx->plan_stage_done);
+  for (auto e : ctx->chunk_events) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -508,14 +531,61 @@ int dali_normalize_f32(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int6
 }
 
 // ---------------------------------------------------------------------------
+// Host gallery: chunked H2D on a copy stream overlapped with preparation + contraction of the
+// previous chunk on the compute stream (chunks are multiples of 256 rows = whole N tiles).
+static int gallery_pipelined(dali_ctx *ctx, const Prepared &a, const float *g_host, int64_t Q,
+                             int64_t G, int64_t D, int metric, int precision, int normalize,
+                             float *out_dev, int64_t ld) {
+  Prepared b;
+  int rc = alloc_operand(ctx, WS_GN, WS_GN16, WS_GNORM, G, D, metric, precision, &b);
+  if (rc) return rc;
+  void *gin_v = nullptr;
+  rc = ws_ensure(ctx, WS_GIN, sizeof(float) * G * D, &gin_v);
+  if (rc) return rc;
+  float *gin = static_cast<float *>(gin_v);
+  if (!ctx->copy_stream)
+    DALI_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  int64_t chunk = round_up(std::max<int64_t>(256, (12ll << 20) / (sizeof(float) * D)), 256);
+  if ((G + chunk - 1) / chunk > 24) chunk = round_up((G + 23) / 24, 256);
+  const int nchunks = static_cast<int>((b.rows_pad + chunk - 1) / chunk);
+  while (static_cast<int>(ctx->chunk_events.size()) < nchunks + 1) {
+    cudaEvent_t e;
+    DALI_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->chunk_events.push_back(e);
+  }
+  // the copy stream starts after everything already enqueued on the compute stream
+  DALI_CUDA_OK(ctx, cudaEventRecord(ctx->chunk_events[nchunks], ctx->stream));
+  DALI_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_events[nchunks], 0));
+  for (int c = 0; c < nchunks; ++c) {
+    const int64_t r0 = c * chunk;
+    const int64_t r1 = std::min(b.rows_pad, r0 + chunk);
+    const int64_t n_valid = std::max<int64_t>(0, std::min(G, r1) - r0);
+    if (n_valid > 0) {
+      DALI_CUDA_OK(ctx, cudaMemcpyAsync(gin + r0 * D, g_host + r0 * D, sizeof(float) * n_valid * D,
+                                        cudaMemcpyHostToDevice, ctx->copy_stream));
+      DALI_CUDA_OK(ctx, cudaEventRecord(ctx->chunk_events[c], ctx->copy_stream));
+      DALI_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_events[c], 0));
+    }
+    rc = prep_rows(ctx, b, gin + r0 * D, D, D, r0, n_valid, r1, precision, normalize);
+    if (rc) return rc;
+    if (n_valid > 0) {
+      rc = contract(ctx, a, b, Q, r0, n_valid, metric, precision, out_dev + r0, ld);
+      if (rc) return rc;
+    }
+  }
+  return DALI_OK;
+}
+
 static int distmat_to(dali_ctx *ctx, const float *q, int64_t Q, const float *g, int64_t G, int64_t D,
                       int metric, int precision, int normalize, float *out_dev, int64_t ld) {
   Prepared a, b;
-  int rc = prepare_operand(ctx, WS_QIN, WS_QN, WS_QNORM, q, Q, D, metric, precision, normalize, &a);
+  int rc = prepare_operand(ctx, WS_QIN, WS_QN, WS_QN16, WS_QNORM, q, Q, D, metric, precision, normalize, &a);
   if (rc) return rc;
-  rc = prepare_operand(ctx, WS_GIN, WS_GN, WS_GNORM, g, G, D, metric, precision, normalize, &b);
+  if (!is_device_ptr(g) && static_cast<int64_t>(sizeof(float)) * G * D >= (24ll << 20))
+    return gallery_pipelined(ctx, a, g, Q, G, D, metric, precision, normalize, out_dev, ld);
+  rc = prepare_operand(ctx, WS_GIN, WS_GN, WS_GN16, WS_GNORM, g, G, D, metric, precision, normalize, &b);
   if (rc) return rc;
-  return contract(ctx, a, b, Q, G, metric, precision, out_dev, ld);
+  return contract(ctx, a, b, Q, 0, G, metric, precision, out_dev, ld);
 }
 
 int dali_distmat_f32(dali_ctx *ctx, const float *q, int64_t Q, const float *g, int64_t G, int64_t D,
@@ -941,7 +1011,7 @@ int dali_topk_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float
   // Round 1: the gallery is processed in one slab through an internal [Qc, G] matrix per
   // query band (bounded workspace); the band results are final because each band owns its rows.
   Prepared a, b;
-  rc = prepare_operand(ctx, WS_GIN, WS_GN, WS_GNORM, g, G, D, metric, precision, normalize, &b);
+  rc = prepare_operand(ctx, WS_GIN, WS_GN, WS_GN16, WS_GNORM, g, G, D, metric, precision, normalize, &b);
   if (rc) return rc;
   const int64_t ldd = round_up(std::max<int64_t>(G, 1), 4);
   const int64_t budget = 8ll << 30;  // bytes of internal distance matrix per band
@@ -955,11 +1025,11 @@ int dali_topk_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float
   const bool qdev = is_device_ptr(q);
   for (int64_t q0 = 0; q0 < Q; q0 += band) {
     const int64_t qc = std::min(band, Q - q0);
-    rc = prepare_operand(ctx, WS_QIN, WS_QN, WS_QNORM, q + q0 * D, qc, D, metric, precision,
+    rc = prepare_operand(ctx, WS_QIN, WS_QN, WS_QN16, WS_QNORM, q + q0 * D, qc, D, metric, precision,
                          normalize, &a);
     if (rc) return rc;
     if (G) {
-      rc = contract(ctx, a, b, qc, G, metric, precision, dist, ldd);
+      rc = contract(ctx, a, b, qc, 0, G, metric, precision, dist, ldd);
       if (rc) return rc;
     }
     rc = topk_out(ctx, dist, qc, G, ldd, k, largest, nullptr, g_base, d_out + q0 * k, i_out + q0 * k);

@@ -52,6 +52,8 @@ struct DevBuf {
 enum WsSlot {
   WS_QN = 0,   // normalised queries (fp32, padded rows) / hi+lo planes
   WS_GN,       // normalised gallery
+  WS_QN16,     // bf16 hi / residual planes (TF32C)
+  WS_GN16,
   WS_QIN,      // staged host queries
   WS_GIN,      // staged host gallery
   WS_QNORM,    // row norms
@@ -89,6 +91,8 @@ struct dali_ctx {
   size_t plan_stage_cap = 0;
   cudaEvent_t plan_stage_done = nullptr;  // the last upload out of plan_stage
   bool pool_ready = false;
+  cudaStream_t copy_stream = nullptr;  // H2D of host operands, overlapped with compute
+  std::vector<cudaEvent_t> chunk_events;
   // timing
   bool timing = false;
   int t_launches[DALI_K_COUNT_] = {0};
@@ -142,15 +146,17 @@ struct KTimer {
 // normalize.cu
 int launch_prep(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx, float *plane0,
                 float *plane1, int64_t ldo, int64_t d_pad, int64_t rows_pad, int do_normalize,
-                int round_mode, float *norms, float *sq);
+                int round_mode, float *norms, float *sq, void *hi16 = nullptr,
+                void *lo16 = nullptr);
 // distmat_simt.cu
 int launch_distmat_simt(dali_ctx *ctx, const float *qn, const float *gn, int64_t Q, int64_t G,
                         int64_t D, int64_t ldq, int64_t ldg, int metric, const float *qsq,
                         const float *gsq, float *out, int64_t ld);
 // distmat_umma.cu
-int launch_distmat_umma(dali_ctx *ctx, const float *q_planes, const float *g_planes, int64_t Q,
-                        int64_t G, int64_t Dp, int64_t q_rows_pad, int64_t g_rows_pad, int split3,
-                        int metric, const float *qsq, const float *gsq, float *out, int64_t ld);
+int launch_distmat_umma(dali_ctx *ctx, const float *q32, const float *g32, const void *q16,
+                        const void *g16, int64_t Q, int64_t G, int64_t Dp, int64_t q_rows_pad,
+                        int64_t g_rows_pad, int64_t g_row0, int precision, int metric,
+                        const float *qsq, const float *gsq, float *out, int64_t ld);
 // rank.cu
 int launch_rank_gather(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist, int64_t ld,
                        int64_t g0, int64_t Gs, uint32_t *keys);

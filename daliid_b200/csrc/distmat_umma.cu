@@ -1,17 +1,20 @@
 // Q x G x D distance contraction on the 5th-generation tensor cores (SURVEY 8a rows a2/a2',
-// precisions DALI_PREC_TF32 and DALI_PREC_TF32X3).
+// precisions DALI_PREC_TF32, DALI_PREC_TF32X3 and DALI_PREC_TF32C).
 //
 //   out[i,j] = epilogue( sum_k A[i,k] * B[j,k] )        A = prepared queries, B = gallery
 //
-// Both operands are K-major fp32 planes written by normalize.cu (zero padded, rounded to
-// TF32; the 3xTF32 mode adds the residual plane and issues hi*hi + hi*lo + lo*hi into the
-// same TMEM accumulator, which recovers fp32-class accuracy on the tensor pipe).
+// Operands are K-major planes written by normalize.cu (zero padded):
+//   hi    fp32 rounded to TF32                              (all modes)
+//   lo    fp32 residual x - hi, rounded to TF32             (TF32X3: hi*hi + hi*lo + lo*hi)
+//   hi16, lo16  bf16 copies of hi and of the residual       (TF32C : hi*hi on kind::tf32 plus the
+//               two correction products on kind::f16/bf16 at twice the rate; error <= 2^-18/product)
+// All MMAs of one output tile accumulate into the same fp32 TMEM accumulator.
 //
 // Structure (one persistent CTA per SM, 192 threads):
-//   warp 0    TMA producer: cp.async.bulk.tensor 2D tiles (128B swizzle) into a ring of
-//             shared-memory stages, completion on mbarriers
+//   warp 0    TMA producer: cp.async.bulk.tensor 2D tiles (128B / 64B swizzle) into a ring of four
+//             48 KiB shared-memory slots, completion on mbarriers
 //   warp 1    allocates TMEM (512 columns = two 128x256 fp32 accumulators) and issues
-//             tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=256, K=8) from one elected lane
+//             tcgen05.mma.cta_group::1 (M=128, N=256; K=8 tf32 / K=16 bf16) from one elected lane
 //   warps 2-5 epilogue: tcgen05.ld the finished accumulator (32 lanes x 32 columns at a
 //             time), apply the metric, transpose through shared memory and store coalesced
 //             rows; overlaps the next tile's MMAs through the second accumulator
@@ -28,21 +31,20 @@ namespace {
 
 constexpr int BM = 128;        // UMMA M (TMEM lanes)
 constexpr int BN = 256;        // UMMA N (TMEM columns per accumulator)
-constexpr int BK = 32;         // floats per stage row = 128 bytes = one swizzle atom
-constexpr int UMMA_K = 8;      // tf32: 32 bytes of K per instruction
+constexpr int BK = 32;         // K elements per pipeline slot
 constexpr int kThreads = 192;
-constexpr int A_BYTES = BM * BK * 4;  // 16 KiB
-constexpr int B_BYTES = BN * BK * 4;  // 32 KiB
+constexpr int A_BYTES = BM * BK * 4;    // 16 KiB fp32 tile (rows of 128 B, SWIZZLE_128B)
+constexpr int B_BYTES = BN * BK * 4;    // 32 KiB
+constexpr int A16_BYTES = BM * BK * 2;  // 8 KiB bf16 tile (rows of 64 B, SWIZZLE_64B)
+constexpr int B16_BYTES = BN * BK * 2;  // 16 KiB
+constexpr int kSlotBytes = A_BYTES + B_BYTES;  // 48 KiB = 2*A16 + 2*B16 as well
+constexpr int kSlots = 4;
 constexpr int EPI_LD = 33;
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+constexpr int kSmemBytes = kSlots * kSlotBytes + EPI_BYTES + 256 + 1024;
 constexpr uint64_t kWatchdogCycles = 4000000000ull;  // ~2 s: trap instead of hanging the box
 
-template <int NPL>
-struct Cfg {
-  static constexpr int kStages = (NPL == 1) ? 4 : 2;
-  static constexpr int kStageBytes = NPL * (A_BYTES + B_BYTES);
-  static constexpr int kSmemBytes = kStages * kStageBytes + EPI_BYTES + 256 + 1024;
-};
+enum Mode { kTf32 = 0, kTf32x3 = 1, kTf32c = 2 };
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -104,6 +106,15 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -121,16 +132,24 @@ __device__ __forceinline__ void tc_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart.
-// start address [0,14) (>>4), LBO [16,30) = 1 (unused for swizzled K-major), SBO [32,46) = 64
-// (1024 B), descriptor version [46,48) = 1 (sm_100), layout type [61,64) = 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+// K-major operand tiles (cute::UMMA::SmemDescriptor): start address [0,14) (>>4), LBO [16,30) = 1
+// (unused for swizzled K-major), SBO [32,46) = bytes between 8-row groups (>>4), descriptor
+// version [46,48) = 1 (sm_100), layout type [61,64): 2 = SWIZZLE_128B (fp32 tiles, rows of 128 B,
+// SBO 1024), 4 = SWIZZLE_64B (bf16 tiles, rows of 64 B, SBO 512).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
   return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) |
          (1ull << 46) | (2ull << 61);
 }
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (32ull << 32) |
+         (1ull << 46) | (4ull << 61);
+}
 
-// kind::tf32, fp32 accumulate, A and B K-major, N=256, M=128 (cute::UMMA::InstrDescriptor).
-constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) |
+// cute::UMMA::InstrDescriptor: fp32 accumulate (bit 4), A/B format [7,10)/[10,13)
+// (2 = TF32, 1 = BF16), both K-major, N>>3 at [17,23), M>>4 at [24,29).
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) |
+                                (uint32_t(BM >> 4) << 24);
+constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
                                 (uint32_t(BM >> 4) << 24);
 
 __device__ __forceinline__ float epilogue(float acc, int metric, float qs, float gs) {
@@ -146,29 +165,33 @@ struct UmmaParams {
   int64_t Q, G;
   int num_m_tiles, num_n_tiles, num_kb;
   int32_t a_plane_rows, b_plane_rows;  // row offset of plane 1 inside the tensor maps
+  int32_t b_row0;                      // first gallery row of this slab inside the B planes
   int metric;
   const float *qsq, *gsq;
   float *out;
   int64_t ld;
 };
 
-template <int NPL>
+// Slots per k-block: kTf32 1 (A_hi|B_hi); kTf32x3 2 (A_hi|B_hi, A_lo|B_lo);
+// kTf32c 2 (A_hi|B_hi fp32, then A_hi16|A_lo16|B_hi16|B_lo16 bf16).
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 distmat_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const UmmaParams p) {
-  using C = Cfg<NPL>;
+                    const __grid_constant__ CUtensorMap tmA16,
+                    const __grid_constant__ CUtensorMap tmB16, const UmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~uintptr_t(1023));
-  float *epi = reinterpret_cast<float *>(smem + C::kStages * C::kStageBytes);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kStages * C::kStageBytes + EPI_BYTES);
+  float *epi = reinterpret_cast<float *>(smem + kSlots * kSlotBytes);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kSlots * kSlotBytes + EPI_BYTES);
   // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty, then tmem ptr
-  uint32_t *tmem_ptr_s = reinterpret_cast<uint32_t *>(bars + 2 * C::kStages + 4);
+  uint32_t *tmem_ptr_s = reinterpret_cast<uint32_t *>(bars + 2 * kSlots + 4);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (C::kStages + s); };
-  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * C::kStages + s); };
-  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * C::kStages + 2 + s); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kSlots + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kSlots + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kSlots + 2 + s); };
+  auto slot_addr = [&](int s) { return smem_u32(smem + s * kSlotBytes); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -177,7 +200,11 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    for (int s = 0; s < C::kStages; ++s) {
+    if (MODE == kTf32c) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA16) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB16) : "memory");
+    }
+    for (int s = 0; s < kSlots; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
@@ -202,22 +229,36 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int stage = 0;
+      int slot = 0;
       uint32_t phase = 0;
+      auto advance = [&]() { if (++slot == kSlots) { slot = 0; phase ^= 1u; } };
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m = t % p.num_m_tiles, n = t / p.num_m_tiles;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sbase = smem_u32(smem + stage * C::kStageBytes);
-          mbar_expect_tx(full_bar(stage), C::kStageBytes);
-#pragma unroll
-          for (int pl = 0; pl < NPL; ++pl) {
-            tma_load_2d(sbase + pl * A_BYTES, &tmA, full_bar(stage), kb * BK,
-                        pl * p.a_plane_rows + m * BM);
-            tma_load_2d(sbase + NPL * A_BYTES + pl * B_BYTES, &tmB, full_bar(stage), kb * BK,
-                        pl * p.b_plane_rows + n * BN);
+          // slot 0 of the k-block: TF32 operands
+          mbar_wait(empty_bar(slot), phase ^ 1u);
+          mbar_expect_tx(full_bar(slot), kSlotBytes);
+          tma_load_2d(slot_addr(slot), &tmA, full_bar(slot), kb * BK, m * BM);
+          tma_load_2d(slot_addr(slot) + A_BYTES, &tmB, full_bar(slot), kb * BK, p.b_row0 + n * BN);
+          advance();
+          if (MODE == kTf32x3) {  // residual planes (fp32, TF32-rounded)
+            mbar_wait(empty_bar(slot), phase ^ 1u);
+            mbar_expect_tx(full_bar(slot), kSlotBytes);
+            tma_load_2d(slot_addr(slot), &tmA, full_bar(slot), kb * BK, p.a_plane_rows + m * BM);
+            tma_load_2d(slot_addr(slot) + A_BYTES, &tmB, full_bar(slot), kb * BK,
+                        p.b_plane_rows + p.b_row0 + n * BN);
+            advance();
+          } else if (MODE == kTf32c) {  // bf16 hi and residual planes
+            mbar_wait(empty_bar(slot), phase ^ 1u);
+            mbar_expect_tx(full_bar(slot), kSlotBytes);
+            const uint32_t sb = slot_addr(slot);
+            tma_load_2d(sb, &tmA16, full_bar(slot), kb * BK, m * BM);
+            tma_load_2d(sb + A16_BYTES, &tmA16, full_bar(slot), kb * BK, p.a_plane_rows + m * BM);
+            tma_load_2d(sb + 2 * A16_BYTES, &tmB16, full_bar(slot), kb * BK, p.b_row0 + n * BN);
+            tma_load_2d(sb + 2 * A16_BYTES + B16_BYTES, &tmB16, full_bar(slot), kb * BK,
+                        p.b_plane_rows + p.b_row0 + n * BN);
+            advance();
           }
-          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -225,8 +266,9 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      int stage = 0;
+      int slot = 0;
       uint32_t phase = 0;
+      auto advance = [&]() { if (++slot == kSlots) { slot = 0; phase ^= 1u; } };
       int it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         const int as = it & 1;
@@ -234,29 +276,50 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait(full_bar(slot), phase);
           tc_fence_after();
-          const uint32_t sbase = smem_u32(smem + stage * C::kStageBytes);
-          const uint32_t a0 = sbase, b0 = sbase + NPL * A_BYTES;
+          const uint32_t a0 = slot_addr(slot), b0 = a0 + A_BYTES;
+          if (MODE == kTf32 || MODE == kTf32c) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint32_t koff = k * UMMA_K * 4;  // bytes inside the 128 B swizzle atom
-            const uint32_t first = (kb | k) ? 1u : 0u;
-            if (NPL == 1) {
-              tc_mma_tf32(tmem_d, make_smem_desc(a0 + koff), make_smem_desc(b0 + koff), kInstrDesc,
-                          first);
-            } else {
-              const uint64_t ahi = make_smem_desc(a0 + koff);
-              const uint64_t alo = make_smem_desc(a0 + A_BYTES + koff);
-              const uint64_t bhi = make_smem_desc(b0 + koff);
-              const uint64_t blo = make_smem_desc(b0 + B_BYTES + koff);
-              tc_mma_tf32(tmem_d, alo, bhi, kInstrDesc, first);
-              tc_mma_tf32(tmem_d, ahi, blo, kInstrDesc, 1u);
-              tc_mma_tf32(tmem_d, ahi, bhi, kInstrDesc, 1u);
+            for (int k = 0; k < BK / 8; ++k)  // 32 bytes of K per tf32 MMA inside the 128 B atom
+              tc_mma_tf32(tmem_d, make_desc_sw128(a0 + k * 32), make_desc_sw128(b0 + k * 32),
+                          kIdescTf32, (kb | k) ? 1u : 0u);
+            tc_commit(empty_bar(slot));  // frees the slot when these MMAs retire
+            advance();
+            if (MODE == kTf32c) {
+              mbar_wait(full_bar(slot), phase);
+              tc_fence_after();
+              const uint32_t ahi = slot_addr(slot), alo = ahi + A16_BYTES;
+              const uint32_t bhi = ahi + 2 * A16_BYTES, blo = bhi + B16_BYTES;
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {  // 32 bytes of K per bf16 MMA inside the 64 B atom
+                tc_mma_bf16(tmem_d, make_desc_sw64(alo + k * 32), make_desc_sw64(bhi + k * 32),
+                            kIdescBf16, 1u);
+                tc_mma_bf16(tmem_d, make_desc_sw64(ahi + k * 32), make_desc_sw64(blo + k * 32),
+                            kIdescBf16, 1u);
+              }
+              tc_commit(empty_bar(slot));
+              advance();
             }
+          } else {  // kTf32x3: both slots are needed by the cross terms
+            const int slot_hi = slot;
+            advance();
+            mbar_wait(full_bar(slot), phase);
+            tc_fence_after();
+            const uint32_t a1 = slot_addr(slot), b1 = a1 + A_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {
+              tc_mma_tf32(tmem_d, make_desc_sw128(a1 + k * 32), make_desc_sw128(b0 + k * 32),
+                          kIdescTf32, (kb | k) ? 1u : 0u);                       // lo * hi
+              tc_mma_tf32(tmem_d, make_desc_sw128(a0 + k * 32), make_desc_sw128(b1 + k * 32),
+                          kIdescTf32, 1u);                                        // hi * lo
+              tc_mma_tf32(tmem_d, make_desc_sw128(a0 + k * 32), make_desc_sw128(b0 + k * 32),
+                          kIdescTf32, 1u);                                        // hi * hi
+            }
+            tc_commit(empty_bar(slot_hi));
+            tc_commit(empty_bar(slot));
+            advance();
           }
-          tc_commit(empty_bar(stage));  // frees the stage when these MMAs retire
-          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
         tc_commit(tfull_bar(as));  // accumulator complete
       }
@@ -317,8 +380,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_map(dali_ctx *ctx, CUtensorMap *map, const float *base, int64_t rows, int64_t Dp,
-             int box_rows) {
+// 2-D K-major operand map: dims {Dp, rows}, box {BK, box_rows}; fp32 tiles use the 128-byte
+// swizzle (BK * 4 = 128 B), bf16 tiles the 64-byte swizzle (BK * 2 = 64 B).
+int make_map(dali_ctx *ctx, CUtensorMap *map, const void *base, int64_t rows, int64_t Dp,
+             int box_rows, bool bf16) {
   if (!ctx->encode_tiled) {
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -327,55 +392,67 @@ int make_map(dali_ctx *ctx, CUtensorMap *map, const float *base, int64_t rows, i
       return set_err(ctx, DALI_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     ctx->encode_tiled = fn;
   }
+  const int esz = bf16 ? 2 : 4;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(Dp), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(Dp) * 4};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(Dp) * esz};
   cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
-      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+      const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_err(ctx, DALI_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
   return DALI_OK;
 }
 
-template <int NPL>
-int launch_t(dali_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const UmmaParams &p) {
-  using C = Cfg<NPL>;
+template <int MODE>
+int launch_t(dali_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmA16,
+             const CUtensorMap &tmB16, const UmmaParams &p) {
   static bool attr_set = false;
   if (!attr_set) {
-    DALI_CUDA_OK(ctx, cudaFuncSetAttribute(distmat_umma_kernel<NPL>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           C::kSmemBytes));
+    DALI_CUDA_OK(ctx, cudaFuncSetAttribute(distmat_umma_kernel<MODE>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
   KTimer t(ctx, DALI_K_DISTMAT);
-  distmat_umma_kernel<NPL><<<grid, kThreads, C::kSmemBytes, ctx->stream>>>(tmA, tmB, p);
+  distmat_umma_kernel<MODE><<<grid, kThreads, kSmemBytes, ctx->stream>>>(tmA, tmB, tmA16, tmB16, p);
   DALI_CUDA_OK(ctx, cudaGetLastError());
   return DALI_OK;
 }
 
 }  // namespace
 
-// q_planes: [NPL][q_rows_pad][Dp] fp32 (plane 0 = tf32-rounded operand, plane 1 = residual),
-// g_planes likewise; rows_pad multiples of 256, Dp multiple of 32.
-int launch_distmat_umma(dali_ctx *ctx, const float *q_planes, const float *g_planes, int64_t Q,
-                        int64_t G, int64_t Dp, int64_t q_rows_pad, int64_t g_rows_pad, int split3,
-                        int metric, const float *qsq, const float *gsq, float *out, int64_t ld) {
+// q32/g32: [npl32][rows_pad][Dp] fp32 planes (plane 0 = TF32-rounded operand, plane 1 = residual,
+// TF32X3 only); q16/g16: [2][rows_pad][Dp] bf16 planes (hi16, lo16; TF32C only).
+// rows_pad multiples of 256, Dp multiple of 32.  mode: DALI_PREC_TF32 / TF32X3 / TF32C.
+int launch_distmat_umma(dali_ctx *ctx, const float *q32, const float *g32, const void *q16,
+                        const void *g16, int64_t Q, int64_t G, int64_t Dp, int64_t q_rows_pad,
+                        int64_t g_rows_pad, int64_t g_row0, int precision, int metric,
+                        const float *qsq, const float *gsq, float *out, int64_t ld) {
   if (Q == 0 || G == 0) return DALI_OK;
-  const int npl = split3 ? 2 : 1;
-  if (Dp % BK != 0 || q_rows_pad % BM != 0 || g_rows_pad % BN != 0)
+  const int npl32 = precision == DALI_PREC_TF32X3 ? 2 : 1;
+  if (Dp % BK != 0 || q_rows_pad % BM != 0 || g_rows_pad % BN != 0 || g_row0 % BN != 0)
     return set_err(ctx, DALI_ERR_INVALID, "umma operands must be padded (rows 128/256, D 32)");
-  if (q_rows_pad * npl > INT32_MAX || g_rows_pad * npl > INT32_MAX)
+  if (q_rows_pad * 2 > INT32_MAX || g_rows_pad * 2 > INT32_MAX)
     return set_err(ctx, DALI_ERR_UNSUPPORTED, "operand too tall for one tensor map");
-  CUtensorMap tmA, tmB;
-  int rc = make_map(ctx, &tmA, q_planes, q_rows_pad * npl, Dp, BM);
+  CUtensorMap tmA, tmB, tmA16, tmB16;
+  int rc = make_map(ctx, &tmA, q32, q_rows_pad * npl32, Dp, BM, false);
   if (rc) return rc;
-  rc = make_map(ctx, &tmB, g_planes, g_rows_pad * npl, Dp, BN);
+  rc = make_map(ctx, &tmB, g32, g_rows_pad * npl32, Dp, BN, false);
   if (rc) return rc;
+  if (precision == DALI_PREC_TF32C) {
+    rc = make_map(ctx, &tmA16, q16, q_rows_pad * 2, Dp, BM, true);
+    if (rc) return rc;
+    rc = make_map(ctx, &tmB16, g16, g_rows_pad * 2, Dp, BN, true);
+    if (rc) return rc;
+  } else {
+    tmA16 = tmA;
+    tmB16 = tmB;
+  }
   UmmaParams p;
   p.Q = Q; p.G = G;
   p.num_m_tiles = static_cast<int>((Q + BM - 1) / BM);
@@ -383,10 +460,16 @@ int launch_distmat_umma(dali_ctx *ctx, const float *q_planes, const float *g_pla
   p.num_kb = static_cast<int>(Dp / BK);
   p.a_plane_rows = static_cast<int32_t>(q_rows_pad);
   p.b_plane_rows = static_cast<int32_t>(g_rows_pad);
+  p.b_row0 = static_cast<int32_t>(g_row0);
   p.metric = metric; p.qsq = qsq; p.gsq = gsq; p.out = out; p.ld = ld;
   if (static_cast<int64_t>(p.num_m_tiles) * p.num_n_tiles > INT32_MAX)
     return set_err(ctx, DALI_ERR_UNSUPPORTED, "too many tiles (chunk the queries)");
-  return split3 ? launch_t<2>(ctx, tmA, tmB, p) : launch_t<1>(ctx, tmA, tmB, p);
+  switch (precision) {
+    case DALI_PREC_TF32: return launch_t<kTf32>(ctx, tmA, tmB, tmA16, tmB16, p);
+    case DALI_PREC_TF32X3: return launch_t<kTf32x3>(ctx, tmA, tmB, tmA16, tmB16, p);
+    case DALI_PREC_TF32C: return launch_t<kTf32c>(ctx, tmA, tmB, tmA16, tmB16, p);
+    default: return set_err(ctx, DALI_ERR_INVALID, "not a tensor-core precision");
+  }
 }
 
 }  // namespace dali

@@ -6,6 +6,8 @@
 //   validateModels.py:41-42, evaluate.py:251-258,285-286,
 //   evaluate_ensembled_models.py:278-279,297-298, evaluateCleanATModels.py:106-107,115-119,252-254
 // No eps, as in the reference: a zero row divides 0/0 and becomes NaN.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace dali {
@@ -43,6 +45,8 @@ struct PrepParams {
   int round_mode;  // 0 keep fp32, 1 round plane0 to tf32
   float *norms;    // nullable: ||x|| of the input row
   float *sq;       // nullable: sum of squares of the OUTPUT row (fp32 values before tf32 rounding)
+  __nv_bfloat16 *hi16;  // nullable: bf16 copy of plane0 (TF32C correction operand)
+  __nv_bfloat16 *lo16;  // nullable: bf16 copy of the residual x - plane0
 };
 
 __global__ void __launch_bounds__(kPrepThreads) prep_rows_kernel(PrepParams p) {
@@ -50,10 +54,13 @@ __global__ void __launch_bounds__(kPrepThreads) prep_rows_kernel(PrepParams p) {
   const int64_t r = blockIdx.x;
   float *o0 = p.plane0 + r * p.ldo;
   float *o1 = p.plane1 ? p.plane1 + r * p.ldo : nullptr;
+  __nv_bfloat16 *h16 = p.hi16 ? p.hi16 + r * p.ldo : nullptr;
+  __nv_bfloat16 *l16 = p.lo16 ? p.lo16 + r * p.ldo : nullptr;
   if (r >= p.n) {  // padding rows: zeros
     for (int64_t c = threadIdx.x; c < p.d_pad; c += kPrepThreads) {
       o0[c] = 0.f;
       if (o1) o1[c] = 0.f;
+      if (h16) { h16[c] = __float2bfloat16_rn(0.f); l16[c] = __float2bfloat16_rn(0.f); }
     }
     return;
   }
@@ -80,6 +87,10 @@ __global__ void __launch_bounds__(kPrepThreads) prep_rows_kernel(PrepParams p) {
       const float hi = round_tf32(v);
       o0[c] = hi;
       if (o1) o1[c] = round_tf32(v - hi);
+      if (h16) {
+        h16[c] = __float2bfloat16_rn(hi);
+        l16[c] = __float2bfloat16_rn(v - hi);
+      }
     } else {
       o0[c] = v;
     }
@@ -94,9 +105,10 @@ __global__ void __launch_bounds__(kPrepThreads) prep_rows_kernel(PrepParams p) {
 
 int launch_prep(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx, float *plane0,
                 float *plane1, int64_t ldo, int64_t d_pad, int64_t rows_pad, int do_normalize,
-                int round_mode, float *norms, float *sq) {
+                int round_mode, float *norms, float *sq, void *hi16, void *lo16) {
   if (rows_pad == 0) return DALI_OK;
-  PrepParams p{x, n, d, ldx, plane0, plane1, ldo, d_pad, rows_pad, do_normalize, round_mode, norms, sq};
+  PrepParams p{x, n, d, ldx, plane0, plane1, ldo, d_pad, rows_pad, do_normalize, round_mode, norms, sq,
+               static_cast<__nv_bfloat16 *>(hi16), static_cast<__nv_bfloat16 *>(lo16)};
   KTimer t(ctx, DALI_K_NORMALIZE);
   prep_rows_kernel<<<static_cast<unsigned>(rows_pad), kPrepThreads, 0, ctx->stream>>>(p);
   DALI_CUDA_OK(ctx, cudaGetLastError());

@@ -44,7 +44,7 @@ __all__ = [
     "evaluate_features",
 ]
 
-DEFAULT_PRECISION = "tf32x3"  # fp32-class result on the tensor pipe
+DEFAULT_PRECISION = "tf32c"  # fp32-class result on the tensor pipe (TF32 + bf16 corrections)
 
 
 def canonicalize_labels(q, g):

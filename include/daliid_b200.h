@@ -56,6 +56,8 @@ extern "C" {
 #define DALI_PREC_FP32 0   /* SIMT FFMA, one fmaf chain per element in k order (exact class) */
 #define DALI_PREC_TF32X3 1 /* tcgen05 kind::tf32, hi/lo split, 3 MMAs (fp32 class)           */
 #define DALI_PREC_TF32 2   /* tcgen05 kind::tf32, single pass (fast; <= 0.01 pp mAP)         */
+#define DALI_PREC_TF32C 3  /* tcgen05: TF32 hi*hi + two bf16 correction MMAs (fp32 class,
+                              error <= 2^-18 per product; 2 instead of 3 tensor passes)      */
 
 /* accumulation semantics of the CMC/AP reduction */
 #define DALI_ACCUM_CY_F32 0 /* torchreid Cython path: C float, sequential in rank order */

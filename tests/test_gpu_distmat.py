@@ -55,7 +55,7 @@ def test_normalize_matches_reference():
     assert np.isnan(o[0]).all() and o[1, 3] == 1.0  # no eps, like the reference
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "tf32c"])
 @pytest.mark.parametrize("metric", ["cosine", "sqeuclidean", "euclidean", "dot"])
 def test_golden_distances(metric, precision):
     from daliid_b200 import metrics
@@ -70,7 +70,7 @@ def test_golden_distances(metric, precision):
 
 @pytest.mark.parametrize("Q,G,D", [(1, 1, 1), (5, 3, 7), (130, 257, 33), (128, 256, 32),
                                    (300, 1000, 768), (129, 513, 2048), (257, 300, 3840)])
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "tf32c"])
 def test_random_shapes_cosine(Q, G, D, precision):
     from daliid_b200 import metrics
     g = torch.Generator().manual_seed(Q * 7 + G)
@@ -102,7 +102,7 @@ def test_exact_path_is_tile_position_independent():
     g = torch.Generator().manual_seed(3)
     qf = torch.randn(200, 384, generator=g).cuda()
     gf = torch.randn(1500, 384, generator=g).cuda()
-    for precision in ("fp32", "tf32x3", "tf32"):
+    for precision in ("fp32", "tf32x3", "tf32c", "tf32"):
         full = metrics.compute_distance_matrix(qf, gf, "cosine", precision)
         part = metrics.compute_distance_matrix(qf, gf[700:1333].contiguous(), "cosine", precision)
         assert torch.equal(full[:, 700:1333], part), precision
@@ -113,7 +113,7 @@ def test_evaluate_features_end_to_end():
     rounding of the oracle fed the reference's CPU matrix."""
     from daliid_b200 import metrics, synth
     qf, gf, qp, gp, qc, gc = synth.make_config("small")
-    for precision in ("fp32", "tf32x3"):
+    for precision in ("fp32", "tf32x3", "tf32c"):
         cmc, mAP, dist, det = metrics.evaluate_features(qf, gf, qp, gp, qc, gc, precision=precision,
                                                         return_distmat=True, return_details=True)
         e = ro.eval_market1501_cy_f32(dist, qp, gp, qc, gc, return_details=True)

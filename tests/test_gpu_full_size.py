@@ -26,7 +26,7 @@ def test_market_exact_paths_vs_cpu_reference(market):
     qf, gf, qp, gp, qc, gc = market
     sel = torch.arange(0, qf.shape[0], 17, device="cuda")[:160]
     ref = do.cosine_distmat(qf[sel].cpu(), gf.cpu()).numpy()
-    for precision in ("fp32", "tf32x3"):
+    for precision in ("fp32", "tf32x3", "tf32c"):
         d = metrics.compute_distance_matrix(qf, gf, "cosine", precision)
         sub = d[sel].cpu().numpy()
         err = np.abs(sub.astype(np.float64) - ref) / np.maximum(1.0, np.abs(ref))
@@ -42,7 +42,7 @@ def test_market_tf32_within_001pp_and_under_50ms(market):
     from daliid_b200 import metrics
     qf, gf, qp, gp, qc, gc = market
     res = {}
-    for precision in ("fp32", "tf32x3", "tf32"):
+    for precision in ("fp32", "tf32x3", "tf32c", "tf32"):
         metrics.evaluate_features(qf, gf, qp, gp, qc, gc, precision=precision)  # warm-up
         torch.cuda.synchronize()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
@@ -54,6 +54,7 @@ def test_market_tf32_within_001pp_and_under_50ms(market):
     assert 0.05 < res["fp32"][1] < 0.999  # non-degenerate synthetic quality
     assert abs(res["tf32"][1] - res["fp32"][1]) * 100 <= 0.01
     assert abs(res["tf32x3"][1] - res["fp32"][1]) * 100 <= 0.01
+    assert abs(res["tf32c"][1] - res["fp32"][1]) * 100 <= 0.01
     assert np.all(np.diff(res["tf32x3"][0]) >= 0)
     # BASELINE.json target: full Market-shaped eval in under 50 ms on one B200
     assert res["tf32x3_ms"] < 50.0, res["tf32x3_ms"]
@@ -108,3 +109,20 @@ def test_market_fusion_and_topk_properties(market):
     ref = torch.argsort(d1, dim=1, stable=True)[:, :20]
     assert torch.equal(i.long(), ref)
     assert torch.equal(v, torch.gather(d1, 1, ref))
+
+
+def test_market_host_features_pipelined_equal_device(market):
+    """Host (pinned or pageable) features take the chunked H2D/compute-overlap path; because the
+    contraction is tile-position independent the result is bit-identical to the device path."""
+    from daliid_b200 import metrics
+    qf, gf, qp, gp, qc, gc = market
+    dev = metrics.evaluate_features(qf, gf, qp, gp, qc, gc, return_distmat=True)
+    qh, gh = qf.cpu().pin_memory(), gf.cpu().pin_memory()
+    host = metrics.evaluate_features(qh, gh, qp, gp, qc, gc, return_distmat=True)
+    assert np.array_equal(host[0], dev[0]) and host[1] == dev[1]
+    assert np.array_equal(host[2], dev[2].cpu().numpy())
+    pageable = metrics.evaluate_features(qf.cpu().numpy(), gf.cpu().numpy(), qp, gp, qc, gc)
+    assert np.array_equal(pageable[0], dev[0]) and pageable[1] == dev[1]
+    d2 = metrics.compute_distance_matrix(qh, gh, "sqeuclidean", "tf32c")
+    d3 = metrics.compute_distance_matrix(qf, gf, "sqeuclidean", "tf32c")
+    assert np.array_equal(d2, d3.cpu().numpy())
