@@ -204,9 +204,9 @@ def run_ours(args):
                                                  g_cam, metric="cosine", precision=prec)
 
     def step_host():
-        if world == 1:
-            return step(qf_h, gf_h)  # host pointers: the library stages them (H2D in the call)
-        return step(qf_h.to(dev, non_blocking=True), gf_h.to(dev, non_blocking=True))
+        # host (pinned) pointers: the library stages them -- chunked H2D overlapped with the
+        # preparation + contraction of the previous chunk -- inside the call
+        return step(qf_h, gf_h)
 
     def barrier():
         if world > 1:
@@ -245,6 +245,65 @@ def run_ours(args):
     for _ in range(2):
         step_host()
     ms_e2e, _ = timed(step_host, args.steps)
+
+    if args.breakdown:
+        ops = sharded.CudaOps(local_rank)
+        acc = {}
+
+        def ph(name, fn):
+            t0 = time.perf_counter()
+            r = fn()
+            t1 = time.perf_counter()
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            a = acc.setdefault(name, [0.0, 0.0])
+            a[0] += t1 - t0
+            a[1] += t2 - t0
+            return r
+        for it in range(10):
+            d = ph("distmat", lambda: ops.distmat(qf_d, gf_d, "cosine", prec, True))
+            qp_, gp_ = ph("labels", lambda: metrics.canonicalize_labels(wl["q_pid"], g_pid))
+            qc_, gc_ = ph("labels", lambda: metrics.canonicalize_labels(wl["q_cam"], g_cam))
+            plan = ph("plan", lambda: ops.plan(qp_, gp_, qc_, gc_))
+            keys = ph("gather", lambda: ops.gather_keys(plan, d, wl["g0"]))
+            ph("allreduce1", lambda: sharded._all_reduce_sum(keys, None))
+            counts = ph("count", lambda: ops.count(plan, d, wl["g0"], keys))
+            ph("allreduce2", lambda: sharded._all_reduce_sum(counts, None))
+            ph("finalize", lambda: ops.finalize(plan, keys, counts, Q, G * world, 50, "cy_f32"))
+            ops.plan_destroy(plan)
+        # GPU-timeline version: no host syncs, CUDA events between the phases
+        names = ["distmat", "plan", "gather", "allreduce1", "count", "allreduce2", "finalize"]
+        tl = {n: 0.0 for n in names}
+        host_total = 0.0
+        for it in range(10):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+            h0 = time.perf_counter()
+            evs[0].record()
+            d = ops.distmat(qf_d, gf_d, "cosine", prec, True); evs[1].record()
+            qp_, gp_ = metrics.canonicalize_labels(wl["q_pid"], g_pid)
+            qc_, gc_ = metrics.canonicalize_labels(wl["q_cam"], g_cam)
+            plan = ops.plan(qp_, gp_, qc_, gc_); evs[2].record()
+            keys = ops.gather_keys(plan, d, wl["g0"]); evs[3].record()
+            sharded._all_reduce_sum(keys, None); evs[4].record()
+            counts = ops.count(plan, d, wl["g0"], keys); evs[5].record()
+            sharded._all_reduce_sum(counts, None); evs[6].record()
+            h1 = time.perf_counter()
+            ops.finalize(plan, keys, counts, Q, G * world, 50, "cy_f32"); evs[7].record()
+            ops.plan_destroy(plan)
+            torch.cuda.synchronize()
+            host_total += h1 - h0
+            for i, n in enumerate(names):
+                tl[n] += evs[i].elapsed_time(evs[i + 1])
+        if rank == 0:
+            print("gpu timeline (ms/step): " + ", ".join(f"{k}={v / 10:.3f}" for k, v in tl.items()) +
+                  f", total={sum(tl.values()) / 10:.3f}, host enqueue before finalize={host_total * 100:.3f}",
+                  file=sys.stderr, flush=True)
+            print("breakdown (ms: host call, call+sync): " +
+                  ", ".join(f"{k}={v[0] * 100:.3f}/{v[1] * 100:.3f}" for k, v in acc.items()),
+                  file=sys.stderr, flush=True)
 
     if rank != 0:
         if world > 1:
@@ -312,6 +371,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="tf32c", choices=["fp32", "tf32x3", "tf32c", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="diagnostic per-phase host timing (stderr)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

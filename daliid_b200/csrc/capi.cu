@@ -236,12 +236,18 @@ static int finish_on_host(dali_ctx *ctx, const dali_rank_plan *plan, const int32
         ap_opt[q] = h_first[q] < 0 ? std::numeric_limits<double>::quiet_NaN()
                                    : static_cast<double>(h_ap[q]);
   } else {
+    std::vector<int32_t> h_nv(Q), h_njunk(Q);
+    if (Q) {
+      DALI_CUDA_OK(ctx, cudaMemcpyAsync(h_nv.data(), plan->d_nv, sizeof(int32_t) * Q, cudaMemcpyDeviceToHost, ctx->stream));
+      DALI_CUDA_OK(ctx, cudaMemcpyAsync(h_njunk.data(), plan->d_njunk, sizeof(int32_t) * Q, cudaMemcpyDeviceToHost, ctx->stream));
+      DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     std::vector<double> aps;
     aps.reserve(nvalid);
     std::vector<int64_t> pos;
     std::vector<double> val;
     for (int64_t q = 0; q < Q; ++q) {
-      const int nv = plan->h_nv[q];
+      const int nv = h_nv[q];
       if (nv == 0) {
         if (ap_opt) ap_opt[q] = std::numeric_limits<double>::quiet_NaN();
         continue;
@@ -254,7 +260,7 @@ static int finish_on_host(dali_ctx *ctx, const dali_rank_plan *plan, const int32
         pos[k] = r - 1;
         val[k] = static_cast<double>(k + 1) / static_cast<double>(r);
       }
-      const int64_t kept = plan->G - plan->h_njunk[q];
+      const int64_t kept = plan->G - h_njunk[q];
       const double sum = 0.0 + np_pairwise_sparse(pos.data(), val.data(), nv, 0, kept);
       const double ap = sum / static_cast<double>(nv);
       aps.push_back(ap);
@@ -609,11 +615,12 @@ int dali_distmat_f32(dali_ctx *ctx, const float *q, int64_t Q, const float *g, i
   }
   rc = distmat_to(ctx, q, Q, g, G, D, metric, precision, normalize, od, ldd);
   if (rc) return rc;
-  if (!out_dev)
+  if (!out_dev) {
     DALI_CUDA_OK(ctx, cudaMemcpy2DAsync(out, sizeof(float) * ld, od, sizeof(float) * ldd,
                                         sizeof(float) * G, Q, cudaMemcpyDeviceToHost, ctx->stream));
-  DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  return DALI_OK;
+    DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return DALI_OK;  // device output: stream-ordered, no host synchronisation
 }
 
 // ---------------------------------------------------------------------------
@@ -676,10 +683,14 @@ int dali_fuse_f32(dali_ctx *ctx, const float *const *d, int n, const float *cons
                      G, ldd);
     if (rc) return rc;
   }
-  if (!dev)
+  if (!dev) {
     DALI_CUDA_OK(ctx, cudaMemcpy2DAsync(out, sizeof(float) * ld, od, sizeof(float) * ldd,
                                         sizeof(float) * G, Q, cudaMemcpyDeviceToHost, ctx->stream));
-  DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  } else if (wq) {
+    // the staged weight vectors live in a workspace the next call may overwrite
+    DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   return DALI_OK;
 }
 
@@ -693,68 +704,21 @@ int dali_rank_plan_create(dali_ctx *ctx, const int32_t *q_pid, const int32_t *g_
     return set_err(ctx, DALI_ERR_INVALID, "rank plan: bad arguments");
   if (G > INT32_MAX || Q > INT32_MAX) return set_err(ctx, DALI_ERR_UNSUPPORTED, "Q or G exceeds 2^31");
   *out = nullptr;
-  // ---- gallery CSR by identity: `order` = gallery indices sorted by (pid, index) ----------
-  std::vector<int32_t> order(G);
-  std::vector<int64_t> start;          // dense path: start[p - pmin] .. start[p - pmin + 1]
-  std::vector<int32_t> sorted_pid;     // sparse path
+  // ---- host part: gallery CSR by identity (counting sort) + per-query ranges -------------
+  // identities are looked up through `start` (dense ids) or a sorted copy (sparse ids)
   int32_t pmin = 0, pmax = -1;
-  bool dense = false;
   if (G) {
     pmin = pmax = g_pid[0];
     for (int64_t i = 1; i < G; ++i) { pmin = std::min(pmin, g_pid[i]); pmax = std::max(pmax, g_pid[i]); }
-    const int64_t range = static_cast<int64_t>(pmax) - pmin + 1;
-    dense = range <= 4 * G + 1024;
-    if (dense) {  // counting sort, O(G + range), stable in the gallery index
-      start.assign(range + 1, 0);
-      for (int64_t i = 0; i < G; ++i) start[g_pid[i] - pmin + 1]++;
-      for (int64_t r = 0; r < range; ++r) start[r + 1] += start[r];
-      std::vector<int64_t> cur(start.begin(), start.end() - 1);
-      for (int64_t i = 0; i < G; ++i) order[cur[g_pid[i] - pmin]++] = static_cast<int32_t>(i);
-    } else {
-      std::iota(order.begin(), order.end(), 0);
-      std::stable_sort(order.begin(), order.end(),
-                       [&](int32_t a, int32_t b) { return g_pid[a] < g_pid[b]; });
-      sorted_pid.resize(G);
-      for (int64_t i = 0; i < G; ++i) sorted_pid[i] = g_pid[order[i]];
-    }
   }
+  const int64_t range = G ? static_cast<int64_t>(pmax) - pmin + 1 : 0;
+  const bool dense = G && range <= 4 * G + 1024;
   dali_rank_plan *p = new dali_rank_plan();
   p->ctx = ctx;
   p->Q = Q;
   p->G = G;
   p->h_off.assign(Q + 1, 0);
-  p->h_nv.assign(Q, 0);
-  p->h_njunk.assign(Q, 0);
-  std::vector<std::pair<int64_t, int64_t>> range_of(Q);
-  int64_t M = 0;
-  for (int64_t q = 0; q < Q; ++q) {
-    int64_t lo = 0, hi = 0;
-    if (G) {
-      if (dense) {
-        const int64_t r = static_cast<int64_t>(q_pid[q]) - pmin;
-        if (r >= 0 && r <= static_cast<int64_t>(pmax) - pmin) { lo = start[r]; hi = start[r + 1]; }
-      } else {
-        auto l = std::lower_bound(sorted_pid.begin(), sorted_pid.end(), q_pid[q]);
-        auto h = std::upper_bound(l, sorted_pid.end(), q_pid[q]);
-        lo = l - sorted_pid.begin();
-        hi = h - sorted_pid.begin();
-      }
-    }
-    range_of[q] = {lo, hi};
-    p->h_off[q] = M;
-    M += hi - lo;
-  }
-  p->h_off[Q] = M;
-  if (M > INT32_MAX) {
-    delete p;
-    return set_err(ctx, DALI_ERR_UNSUPPORTED, "more than 2^31 same-identity (query, gallery) pairs");
-  }
-  p->M = M;
-  // ---- build the device image in pinned staging, upload asynchronously -----------------
-  const size_t b_off = sizeof(int64_t) * (Q + 1);
-  const size_t b_nv = sizeof(int32_t) * std::max<int64_t>(Q, 1);
-  const size_t b_gid = sizeof(int32_t) * std::max<int64_t>(M, 1);
-  const size_t total = b_off + b_nv + b_gid;
+  // staging layout (pinned): off | lo | nv | njunk | q_cam | [gid: device only] | order | g_cam
   auto fail = [&](cudaError_t e, const char *what) {
     std::string m = cudaGetErrorString(e);
     dali_rank_plan_destroy(p);
@@ -765,33 +729,72 @@ int dali_rank_plan_create(dali_ctx *ctx, const int32_t *q_pid, const int32_t *g_
       (e = cudaEventCreateWithFlags(&ctx->plan_stage_done, cudaEventDisableTiming)) != cudaSuccess)
     return fail(e, "event");
   if ((e = cudaEventSynchronize(ctx->plan_stage_done)) != cudaSuccess) return fail(e, "staging wait");
-  if (total > ctx->plan_stage_cap) {
+  const size_t b_off = sizeof(int64_t) * (Q + 1), b_lo = sizeof(int64_t) * std::max<int64_t>(Q, 1);
+  const size_t b_q32 = sizeof(int32_t) * std::max<int64_t>(Q, 1);
+  const size_t b_g32 = sizeof(int32_t) * std::max<int64_t>(G, 1);
+  const size_t stage_bytes = b_off + b_lo + b_q32 + 2 * b_g32;  // off, lo, q_cam, order, g_cam
+  if (stage_bytes > ctx->plan_stage_cap) {
     if (ctx->plan_stage) cudaFreeHost(ctx->plan_stage);
     ctx->plan_stage = nullptr;
     ctx->plan_stage_cap = 0;
-    if ((e = cudaMallocHost(&ctx->plan_stage, total + total / 4 + 4096)) != cudaSuccess)
+    if ((e = cudaMallocHost(&ctx->plan_stage, stage_bytes + stage_bytes / 4 + 4096)) != cudaSuccess)
       return fail(e, "pinned staging");
-    ctx->plan_stage_cap = total + total / 4 + 4096;
+    ctx->plan_stage_cap = stage_bytes + stage_bytes / 4 + 4096;
   }
   char *hs = static_cast<char *>(ctx->plan_stage);
   int64_t *s_off = reinterpret_cast<int64_t *>(hs);
-  int32_t *s_nv = reinterpret_cast<int32_t *>(hs + b_off);
-  int32_t *s_gid = reinterpret_cast<int32_t *>(hs + b_off + b_nv);
-  std::memcpy(s_off, p->h_off.data(), b_off);
-  for (int64_t q = 0; q < Q; ++q) {
-    int64_t w = p->h_off[q];
-    int nv = 0, nj = 0;
-    const int32_t qc = q_cam[q];
-    for (int64_t i = range_of[q].first; i < range_of[q].second; ++i)  // valid positives first
-      if (g_cam[order[i]] != qc) { s_gid[w++] = order[i]; ++nv; }
-    for (int64_t i = range_of[q].first; i < range_of[q].second; ++i)  // then junk (same id, same camera)
-      if (g_cam[order[i]] == qc) { s_gid[w++] = order[i]; ++nj; }
-    p->h_nv[q] = nv;
-    p->h_njunk[q] = nj;
-    s_nv[q] = nv;
-    p->max_nv = std::max(p->max_nv, nv);
-    p->max_m = std::max(p->max_m, nv + nj);
+  int64_t *s_lo = reinterpret_cast<int64_t *>(hs + b_off);
+  int32_t *s_qcam = reinterpret_cast<int32_t *>(hs + b_off + b_lo);
+  int32_t *s_order = reinterpret_cast<int32_t *>(hs + b_off + b_lo + b_q32);
+  int32_t *s_gcam = reinterpret_cast<int32_t *>(hs + b_off + b_lo + b_q32 + b_g32);
+  std::vector<int64_t> start;
+  std::vector<int32_t> sorted_pid;
+  if (G) {
+    if (dense) {  // counting sort, O(G + range), stable in the gallery index
+      start.assign(range + 1, 0);
+      for (int64_t i = 0; i < G; ++i) start[g_pid[i] - pmin + 1]++;
+      for (int64_t r = 0; r < range; ++r) start[r + 1] += start[r];
+      std::vector<int64_t> cur(start.begin(), start.end() - 1);
+      for (int64_t i = 0; i < G; ++i) s_order[cur[g_pid[i] - pmin]++] = static_cast<int32_t>(i);
+    } else {
+      std::iota(s_order, s_order + G, 0);
+      std::stable_sort(s_order, s_order + G, [&](int32_t a, int32_t b) { return g_pid[a] < g_pid[b]; });
+      sorted_pid.resize(G);
+      for (int64_t i = 0; i < G; ++i) sorted_pid[i] = g_pid[s_order[i]];
+    }
+    std::memcpy(s_gcam, g_cam, sizeof(int32_t) * G);
   }
+  int64_t M = 0;
+  for (int64_t q = 0; q < Q; ++q) {
+    int64_t lo = 0, hi = 0;
+    if (G) {
+      if (dense) {
+        const int64_t r = static_cast<int64_t>(q_pid[q]) - pmin;
+        if (r >= 0 && r < range) { lo = start[r]; hi = start[r + 1]; }
+      } else {
+        auto l = std::lower_bound(sorted_pid.begin(), sorted_pid.end(), q_pid[q]);
+        auto h = std::upper_bound(l, sorted_pid.end(), q_pid[q]);
+        lo = l - sorted_pid.begin();
+        hi = h - sorted_pid.begin();
+      }
+    }
+    s_off[q] = M;
+    s_lo[q] = lo;
+    s_qcam[q] = q_cam[q];
+    M += hi - lo;
+    p->max_m = std::max<int>(p->max_m, static_cast<int>(std::min<int64_t>(hi - lo, INT32_MAX)));
+  }
+  s_off[Q] = M;
+  if (M > INT32_MAX) {
+    delete p;
+    return set_err(ctx, DALI_ERR_UNSUPPORTED, "more than 2^31 same-identity (query, gallery) pairs");
+  }
+  p->M = M;
+  p->max_nv = p->max_m;
+  std::memcpy(p->h_off.data(), s_off, b_off);
+  // ---- device image: upload the CSR, expand the per-query match lists on the GPU ---------
+  const size_t b_gid = sizeof(int32_t) * std::max<int64_t>(M, 1);
+  const size_t total = b_off + b_lo + 3 * b_q32 + b_gid + 2 * b_g32 + 64;
   if (!ctx->pool_ready) {  // keep freed blocks in the default pool: allocation becomes ~free
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
@@ -803,11 +806,21 @@ int dali_rank_plan_create(dali_ctx *ctx, const int32_t *q_pid, const int32_t *g_
   if ((e = cudaMallocAsync(&p->d_block, total, ctx->stream)) != cudaSuccess) return fail(e, "allocation");
   char *db = static_cast<char *>(p->d_block);
   p->d_off = reinterpret_cast<int64_t *>(db);
-  p->d_nv = reinterpret_cast<int32_t *>(db + b_off);
-  p->d_gid = reinterpret_cast<int32_t *>(db + b_off + b_nv);
-  if ((e = cudaMemcpyAsync(p->d_block, hs, total, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+  p->d_lo = reinterpret_cast<int64_t *>(db + b_off);
+  p->d_qcam = reinterpret_cast<int32_t *>(db + b_off + b_lo);
+  p->d_order = reinterpret_cast<int32_t *>(db + b_off + b_lo + b_q32);
+  p->d_gcam = reinterpret_cast<int32_t *>(db + b_off + b_lo + b_q32 + b_g32);
+  p->d_nv = reinterpret_cast<int32_t *>(db + stage_bytes);
+  p->d_njunk = reinterpret_cast<int32_t *>(db + stage_bytes + b_q32);
+  p->d_gid = reinterpret_cast<int32_t *>(db + stage_bytes + 2 * b_q32);
+  if ((e = cudaMemcpyAsync(p->d_block, hs, stage_bytes, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
     return fail(e, "upload");
   if ((e = cudaEventRecord(ctx->plan_stage_done, ctx->stream)) != cudaSuccess) return fail(e, "event record");
+  rc = launch_plan_expand(ctx, p);
+  if (rc) {
+    dali_rank_plan_destroy(p);
+    return rc;
+  }
   *out = p;
   return DALI_OK;
 }
@@ -967,7 +980,7 @@ static int topk_out(dali_ctx *ctx, const float *dist_dev, int64_t Q, int64_t G, 
     DALI_CUDA_OK(ctx, cudaMemcpyAsync(d_out, dd, sizeof(float) * Q * k, cudaMemcpyDeviceToHost, ctx->stream));
   if (!oi)
     DALI_CUDA_OK(ctx, cudaMemcpyAsync(i_out, ii, sizeof(int32_t) * Q * k, cudaMemcpyDeviceToHost, ctx->stream));
-  DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (!od || !oi) DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   return DALI_OK;
 }
 

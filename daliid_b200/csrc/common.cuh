@@ -107,17 +107,22 @@ struct dali_ctx {
 struct dali_rank_plan {
   dali_ctx *ctx = nullptr;
   int64_t Q = 0, G = 0, M = 0;
-  int max_m = 0;   // largest number of matches of one query
-  int max_nv = 0;  // largest number of valid positives of one query
-  // host copies
-  std::vector<int64_t> h_off;    // [Q+1] offsets into the match arrays
-  std::vector<int32_t> h_nv;     // [Q]   number of valid positives (they come first)
-  std::vector<int32_t> h_njunk;  // [Q]
-  // device copies: one stream-ordered allocation [off (Q+1) int64 | nv Q int32 | gid M int32]
+  int max_m = 0;   // largest number of matches (same identity) of one query
+  int max_nv = 0;  // upper bound of the valid positives of one query (== max_m; the exact
+                   // per-query numbers live on the device, written by the expansion kernel)
+  std::vector<int64_t> h_off;  // [Q+1] offsets into the match arrays (host copy)
+  // device image, one stream-ordered allocation:
+  //   off [Q+1] i64 | lo [Q] i64 | nv [Q] i32 | njunk [Q] i32 | q_cam [Q] i32 | gid [M] i32 |
+  //   order [G] i32 (gallery ids sorted by identity) | g_cam [G] i32
   void *d_block = nullptr;
   int64_t *d_off = nullptr;
-  int32_t *d_nv = nullptr;
-  int32_t *d_gid = nullptr;  // [M] gallery id of each match (valid ascending, then junk ascending)
+  int64_t *d_lo = nullptr;    // start of each query's range inside `order`
+  int32_t *d_nv = nullptr;    // number of valid positives (they come first in gid)
+  int32_t *d_njunk = nullptr;
+  int32_t *d_qcam = nullptr;
+  int32_t *d_gid = nullptr;   // [M] gallery id of each match (valid ascending, then junk)
+  int32_t *d_order = nullptr;
+  int32_t *d_gcam = nullptr;
 };
 
 namespace dali {
@@ -158,6 +163,7 @@ int launch_distmat_umma(dali_ctx *ctx, const float *q32, const float *g32, const
                         int64_t g_rows_pad, int64_t g_row0, int precision, int metric,
                         const float *qsq, const float *gsq, float *out, int64_t ld);
 // rank.cu
+int launch_plan_expand(dali_ctx *ctx, const dali_rank_plan *plan);
 int launch_rank_gather(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist, int64_t ld,
                        int64_t g0, int64_t Gs, uint32_t *keys);
 int launch_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist, int64_t ld,

@@ -27,6 +27,47 @@ __device__ __forceinline__ float4 ld_stream_f4(const float *p) {
   return v;
 }
 
+// ------------------------------ plan expansion ------------------------------
+// One warp per query: walks the query's identity range of the gallery CSR and writes its match
+// list -- valid positives (different camera) first in ascending gallery id, junk (same identity,
+// same camera) after them -- plus the two counts.  Replaces the host loop that used to dominate
+// the plan construction.
+__global__ void __launch_bounds__(128)
+plan_expand_kernel(int64_t Q, const int64_t *__restrict__ off, const int64_t *__restrict__ lo,
+                   const int32_t *__restrict__ qcam, const int32_t *__restrict__ order,
+                   const int32_t *__restrict__ gcam, int32_t *__restrict__ gid,
+                   int32_t *__restrict__ nv_out, int32_t *__restrict__ njunk_out) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t o = off[q];
+  const int m = static_cast<int>(off[q + 1] - o);
+  const int64_t l = lo[q];
+  const int32_t qc = qcam[q];
+  int nv = 0, nj = 0;
+  for (int i0 = 0; i0 < m; i0 += 32) {
+    const int i = i0 + lane;
+    int32_t g = 0;
+    bool valid = false, junk = false;
+    if (i < m) {
+      g = order[l + i];
+      valid = gcam[g] != qc;
+      junk = !valid;
+    }
+    const unsigned bv = __ballot_sync(0xffffffffu, valid);
+    const unsigned bj = __ballot_sync(0xffffffffu, junk);
+    const unsigned below = (1u << lane) - 1u;
+    if (valid) gid[o + nv + __popc(bv & below)] = g;
+    if (junk) gid[o + (m - 1) - (nj + __popc(bj & below))] = g;  // filled from the back
+    nv += __popc(bv);
+    nj += __popc(bj);
+  }
+  if (lane == 0) {
+    nv_out[q] = nv;
+    njunk_out[q] = nj;
+  }
+}
+
 // ------------------------------ gather ------------------------------------
 __global__ void rank_gather_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0,
                                    int64_t Gs, const int64_t *__restrict__ off,
@@ -362,6 +403,16 @@ rank_finalize_kernel(const int64_t *__restrict__ off, const int32_t *__restrict_
 }
 
 }  // namespace
+
+int launch_plan_expand(dali_ctx *ctx, const dali_rank_plan *plan) {
+  if (plan->Q == 0) return DALI_OK;
+  plan_expand_kernel<<<static_cast<unsigned>((plan->Q + 3) / 4), 128, 0, ctx->stream>>>(
+      plan->Q, plan->d_off, plan->d_lo, plan->d_qcam, plan->d_order, plan->d_gcam, plan->d_gid,
+      plan->d_nv, plan->d_njunk);
+  DALI_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches++;
+  return DALI_OK;
+}
 
 int launch_rank_gather(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist, int64_t ld,
                        int64_t g0, int64_t Gs, uint32_t *keys) {

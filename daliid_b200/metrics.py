@@ -156,13 +156,16 @@ def normalize(x, return_norms=False):
 
 
 def compute_distance_matrix(input1, input2, metric="cosine", precision=DEFAULT_PRECISION,
-                            normalize=None, out=None):
+                            normalize=None, out=None, device=None):
     """``[Q,G]`` fp32 distance matrix between feature rows.
 
     ``metric``: ``cosine`` (``1 - q.g`` on L2-normalised rows), ``sqeuclidean`` (what
     torchreid's ``compute_distance_matrix(.., "euclidean")`` returns), ``euclidean``
     (``torch.cdist``) or ``dot``.  ``normalize`` defaults to True for cosine only.
-    The result lives where the inputs live (CUDA tensor in, CUDA tensor out)."""
+    The result lives where the inputs live (CUDA tensor in, CUDA tensor out) unless ``out``
+    (a contiguous float32 CUDA tensor or numpy array) or ``device`` (a CUDA ordinal: host
+    features are streamed to the GPU in chunks overlapped with compute, the matrix stays
+    there) says otherwise."""
     a = as_matrix(input1, np.float32, "input1")
     b = as_matrix(input2, np.float32, "input2")
     if a.shape[1] != b.shape[1]:
@@ -174,16 +177,22 @@ def compute_distance_matrix(input1, input2, metric="cosine", precision=DEFAULT_P
     m = _enum(METRICS, metric, "metric")
     if normalize is None:
         normalize = m == METRICS["cosine"]
-    ctx = _ctx_for(a, b)
     dev = _device_of(a, b)
-    if out is None:
+    if out is not None:
+        ob = as_matrix(out, np.float32, "out")
+        own = out.data_ptr() if hasattr(out, "data_ptr") else np.asarray(out).ctypes.data
+        if ob.ptr != own or ob.shape != (Q, G):
+            raise ValueError("out must be a [Q,G] float32 array with unit column stride")
+        optr, ld = ob.ptr, ob.ld
+        if dev is None:
+            dev = ob.device
+    else:
+        if dev is None and device is not None:
+            dev = int(device)
         out, optr = _alloc_out((Q, G), dev)
         ld = G
-    else:
-        ob = as_matrix(out, np.float32, "out")
-        if ob.keep is not out and not (hasattr(out, "data_ptr") and ob.keep.data_ptr() == out.data_ptr()):
-            raise ValueError("out must be a contiguous float32 array")
-        optr, ld = ob.ptr, ob.ld
+    ctx = get_ctx(dev)
+    ctx.attach_torch_stream()
     if Q and G:
         ctx.check(ctx.lib.dali_distmat_f32(ctx.h, c_vp(a.ptr), Q, c_vp(b.ptr), G, D, m,
                                            _enum(PRECISIONS, precision, "precision"),

@@ -39,7 +39,10 @@ class CudaOps:
         self.device = torch.device(f"cuda:{self.ctx.device}")
 
     def distmat(self, qf, gf_slab, metric, precision, normalize):
-        return metrics.compute_distance_matrix(qf, gf_slab, metric, precision, normalize)
+        # host features are streamed in (chunked H2D overlapped with compute); the slab
+        # matrix always stays on this rank's GPU
+        return metrics.compute_distance_matrix(qf, gf_slab, metric, precision, normalize,
+                                               device=self.ctx.device)
 
     def plan(self, q_pid, g_pid, q_cam, g_cam):
         self.ctx.attach_torch_stream()
@@ -126,7 +129,10 @@ def gather_gallery_labels(g_pid_slab, g_cam_slab, group=None):
 def evaluate_rank_sharded(dist_slab, g0, q_pids, g_pids_all, q_camids, g_camids_all, max_rank=50,
                           accum="cy_f32", group=None, ops=None, return_details=False):
     """CMC/mAP from a per-rank distance slab ``[Q, Gs]`` (columns = gallery ``g0 .. g0+Gs``).
-    Labels are those of the whole gallery.  Every rank returns the same ``(cmc, mAP)``."""
+    Labels are those of the whole gallery.  Every rank returns the same ``(cmc, mAP)``.
+
+    ``dist_slab`` may still be in flight on the GPU (stream-ordered): the host-side plan
+    construction below overlaps the contraction that produces it."""
     ops = ops or CudaOps(dist_slab.device.index if dist_slab.is_cuda else None)
     qp, gp = metrics.canonicalize_labels(q_pids, g_pids_all)
     qc, gc = metrics.canonicalize_labels(q_camids, g_camids_all)

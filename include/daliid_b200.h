@@ -16,8 +16,10 @@
  *     stream (pinned host memory gives full PCIe rate), device buffers are used
  *     in place.  Label arrays (int32) and small results (cmc, mAP) are HOST.
  *   - the caller owns all buffers; the context owns its stream (unless one is
- *     attached), events and workspaces.  One context per host thread; calls are
- *     synchronous with respect to the host unless stated otherwise;
+ *     attached), events and workspaces.  One context per host thread.  A call that
+ *     writes any HOST output returns after that output is complete; a call whose
+ *     outputs are all DEVICE buffers only enqueues work on the context's stream
+ *     (stream-ordered, like a kernel launch) and may return before it has run;
  *   - there is NO CPU fallback: without a usable sm_100 device every compute
  *     entry point returns DALI_ERR_CUDA.
  */
