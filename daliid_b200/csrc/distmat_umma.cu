@@ -23,26 +23,39 @@
 //           evaluate_ensembled_models.py:281,300, evaluateCleanATModels.py:109,121,124
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace dali {
 
 namespace {
 
-constexpr int BM = 128;        // UMMA M (TMEM lanes)
+constexpr int UM = 128;        // UMMA M (TMEM lanes) per instruction
 constexpr int BN = 256;        // UMMA N (TMEM columns per accumulator)
 constexpr int BK = 32;         // K elements per pipeline slot
 constexpr int kThreads = 192;
-constexpr int A_BYTES = BM * BK * 4;    // 16 KiB fp32 tile (rows of 128 B, SWIZZLE_128B)
-constexpr int B_BYTES = BN * BK * 4;    // 32 KiB
-constexpr int A16_BYTES = BM * BK * 2;  // 8 KiB bf16 tile (rows of 64 B, SWIZZLE_64B)
-constexpr int B16_BYTES = BN * BK * 2;  // 16 KiB
-constexpr int kSlotBytes = A_BYTES + B_BYTES;  // 48 KiB = 2*A16 + 2*B16 as well
-constexpr int kSlots = 4;
 constexpr int EPI_LD = 33;
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
-constexpr int kSmemBytes = kSlots * kSlotBytes + EPI_BYTES + 256 + 1024;
 constexpr uint64_t kWatchdogCycles = 4000000000ull;  // ~2 s: trap instead of hanging the box
+
+// MH = number of 128-row UMMA halves per CTA tile.
+//   MH = 1: 128 x 256 tile, 4 slots of 48 KiB, two accumulators (epilogue overlaps the next tile)
+//   MH = 2: 256 x 256 tile, 3 slots of 64 KiB, both TMEM accumulators belong to one tile: a third
+//           less operand traffic per FLOP on the SM->L2 request path, which ncu showed saturated
+//           (l1tex2xbar 81 %) with the 128-row tile; the epilogue (~3 % of a tile) is not hidden.
+template <int MH>
+struct Cfg {
+  static constexpr int BM = UM * MH;
+  static constexpr int A_BYTES = BM * BK * 4;    // fp32 tile (rows of 128 B, SWIZZLE_128B)
+  static constexpr int B_BYTES = BN * BK * 4;    // 32 KiB
+  static constexpr int A16_BYTES = BM * BK * 2;  // bf16 tile (rows of 64 B, SWIZZLE_64B)
+  static constexpr int B16_BYTES = BN * BK * 2;  // 16 KiB
+  static constexpr int kSlotBytes = A_BYTES + B_BYTES;  // == 2*A16 + 2*B16
+  static constexpr int kSlots = MH == 1 ? 4 : 3;
+  static constexpr int kAcc = MH == 1 ? 2 : 1;   // accumulator stages
+  static constexpr int kSmemBytes = kSlots * kSlotBytes + EPI_BYTES + 256 + 1024;
+};
 
 enum Mode { kTf32 = 0, kTf32x3 = 1, kTf32c = 2 };
 
@@ -84,6 +97,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
       "[%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap *map, uint32_t bar,
+                                                 int32_t x, int32_t y, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() {
@@ -148,9 +169,9 @@ __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
 // cute::UMMA::InstrDescriptor: fp32 accumulate (bit 4), A/B format [7,10)/[10,13)
 // (2 = TF32, 1 = BF16), both K-major, N>>3 at [17,23), M>>4 at [24,29).
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) |
-                                (uint32_t(BM >> 4) << 24);
+                                (uint32_t(UM >> 4) << 24);
 constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
-                                (uint32_t(BM >> 4) << 24);
+                                (uint32_t(UM >> 4) << 24);
 
 __device__ __forceinline__ float epilogue(float acc, int metric, float qs, float gs) {
   switch (metric) {
@@ -170,15 +191,20 @@ struct UmmaParams {
   const float *qsq, *gsq;
   float *out;
   int64_t ld;
+  uint64_t hint_a, hint_b;  // L2 eviction policies of the operand loads (0 = none)
+  int stream_out;           // 1: evict-first stores of the distance tile
 };
 
 // Slots per k-block: kTf32 1 (A_hi|B_hi); kTf32x3 2 (A_hi|B_hi, A_lo|B_lo);
 // kTf32c 2 (A_hi|B_hi fp32, then A_hi16|A_lo16|B_hi16|B_lo16 bf16).
-template <int MODE>
+template <int MODE, int MH>
 __global__ void __launch_bounds__(kThreads, 1)
 distmat_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmA16,
                     const __grid_constant__ CUtensorMap tmB16, const UmmaParams p) {
+  using C = Cfg<MH>;
+  constexpr int kSlots = C::kSlots, kSlotBytes = C::kSlotBytes, kAcc = C::kAcc, BM = C::BM;
+  constexpr int A_BYTES = C::A_BYTES, A16_BYTES = C::A16_BYTES, B16_BYTES = C::B16_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~uintptr_t(1023));
@@ -232,31 +258,37 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int slot = 0;
       uint32_t phase = 0;
       auto advance = [&]() { if (++slot == kSlots) { slot = 0; phase ^= 1u; } };
+      auto load_a = [&](uint32_t dst, const CUtensorMap *mp, uint32_t bar, int x, int y) {
+        if (p.hint_a) tma_load_2d_hint(dst, mp, bar, x, y, p.hint_a); else tma_load_2d(dst, mp, bar, x, y);
+      };
+      auto load_b = [&](uint32_t dst, const CUtensorMap *mp, uint32_t bar, int x, int y) {
+        if (p.hint_b) tma_load_2d_hint(dst, mp, bar, x, y, p.hint_b); else tma_load_2d(dst, mp, bar, x, y);
+      };
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m = t % p.num_m_tiles, n = t / p.num_m_tiles;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           // slot 0 of the k-block: TF32 operands
           mbar_wait(empty_bar(slot), phase ^ 1u);
           mbar_expect_tx(full_bar(slot), kSlotBytes);
-          tma_load_2d(slot_addr(slot), &tmA, full_bar(slot), kb * BK, m * BM);
-          tma_load_2d(slot_addr(slot) + A_BYTES, &tmB, full_bar(slot), kb * BK, p.b_row0 + n * BN);
+          load_a(slot_addr(slot), &tmA, full_bar(slot), kb * BK, m * BM);
+          load_b(slot_addr(slot) + A_BYTES, &tmB, full_bar(slot), kb * BK, p.b_row0 + n * BN);
           advance();
           if (MODE == kTf32x3) {  // residual planes (fp32, TF32-rounded)
             mbar_wait(empty_bar(slot), phase ^ 1u);
             mbar_expect_tx(full_bar(slot), kSlotBytes);
-            tma_load_2d(slot_addr(slot), &tmA, full_bar(slot), kb * BK, p.a_plane_rows + m * BM);
-            tma_load_2d(slot_addr(slot) + A_BYTES, &tmB, full_bar(slot), kb * BK,
-                        p.b_plane_rows + p.b_row0 + n * BN);
+            load_a(slot_addr(slot), &tmA, full_bar(slot), kb * BK, p.a_plane_rows + m * BM);
+            load_b(slot_addr(slot) + A_BYTES, &tmB, full_bar(slot), kb * BK,
+                   p.b_plane_rows + p.b_row0 + n * BN);
             advance();
           } else if (MODE == kTf32c) {  // bf16 hi and residual planes
             mbar_wait(empty_bar(slot), phase ^ 1u);
             mbar_expect_tx(full_bar(slot), kSlotBytes);
             const uint32_t sb = slot_addr(slot);
-            tma_load_2d(sb, &tmA16, full_bar(slot), kb * BK, m * BM);
-            tma_load_2d(sb + A16_BYTES, &tmA16, full_bar(slot), kb * BK, p.a_plane_rows + m * BM);
-            tma_load_2d(sb + 2 * A16_BYTES, &tmB16, full_bar(slot), kb * BK, p.b_row0 + n * BN);
-            tma_load_2d(sb + 2 * A16_BYTES + B16_BYTES, &tmB16, full_bar(slot), kb * BK,
-                        p.b_plane_rows + p.b_row0 + n * BN);
+            load_a(sb, &tmA16, full_bar(slot), kb * BK, m * BM);
+            load_a(sb + A16_BYTES, &tmA16, full_bar(slot), kb * BK, p.a_plane_rows + m * BM);
+            load_b(sb + 2 * A16_BYTES, &tmB16, full_bar(slot), kb * BK, p.b_row0 + n * BN);
+            load_b(sb + 2 * A16_BYTES + B16_BYTES, &tmB16, full_bar(slot), kb * BK,
+                   p.b_plane_rows + p.b_row0 + n * BN);
             advance();
           }
         }
@@ -271,10 +303,10 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       auto advance = [&]() { if (++slot == kSlots) { slot = 0; phase ^= 1u; } };
       int it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int as = it & 1;
-        mbar_wait(tempty_bar(as), ((it >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
+        const int as = it % kAcc;
+        mbar_wait(tempty_bar(as), ((it / kAcc) & 1u) ^ 1u);  // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * MH * BN);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(full_bar(slot), phase);
           tc_fence_after();
@@ -282,8 +314,10 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (MODE == kTf32 || MODE == kTf32c) {
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k)  // 32 bytes of K per tf32 MMA inside the 128 B atom
-              tc_mma_tf32(tmem_d, make_desc_sw128(a0 + k * 32), make_desc_sw128(b0 + k * 32),
-                          kIdescTf32, (kb | k) ? 1u : 0u);
+#pragma unroll
+              for (int h = 0; h < MH; ++h)
+                tc_mma_tf32(tmem_d + h * BN, make_desc_sw128(a0 + h * (UM * 128) + k * 32),
+                            make_desc_sw128(b0 + k * 32), kIdescTf32, (kb | k) ? 1u : 0u);
             tc_commit(empty_bar(slot));  // frees the slot when these MMAs retire
             advance();
             if (MODE == kTf32c) {
@@ -293,10 +327,13 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const uint32_t bhi = ahi + 2 * A16_BYTES, blo = bhi + B16_BYTES;
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {  // 32 bytes of K per bf16 MMA inside the 64 B atom
-                tc_mma_bf16(tmem_d, make_desc_sw64(alo + k * 32), make_desc_sw64(bhi + k * 32),
-                            kIdescBf16, 1u);
-                tc_mma_bf16(tmem_d, make_desc_sw64(ahi + k * 32), make_desc_sw64(blo + k * 32),
-                            kIdescBf16, 1u);
+#pragma unroll
+                for (int h = 0; h < MH; ++h) {
+                  tc_mma_bf16(tmem_d + h * BN, make_desc_sw64(alo + h * (UM * 64) + k * 32),
+                              make_desc_sw64(bhi + k * 32), kIdescBf16, 1u);
+                  tc_mma_bf16(tmem_d + h * BN, make_desc_sw64(ahi + h * (UM * 64) + k * 32),
+                              make_desc_sw64(blo + k * 32), kIdescBf16, 1u);
+                }
               }
               tc_commit(empty_bar(slot));
               advance();
@@ -309,19 +346,23 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t a1 = slot_addr(slot), b1 = a1 + A_BYTES;
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) {
-              tc_mma_tf32(tmem_d, make_desc_sw128(a1 + k * 32), make_desc_sw128(b0 + k * 32),
-                          kIdescTf32, (kb | k) ? 1u : 0u);                       // lo * hi
-              tc_mma_tf32(tmem_d, make_desc_sw128(a0 + k * 32), make_desc_sw128(b1 + k * 32),
-                          kIdescTf32, 1u);                                        // hi * lo
-              tc_mma_tf32(tmem_d, make_desc_sw128(a0 + k * 32), make_desc_sw128(b0 + k * 32),
-                          kIdescTf32, 1u);                                        // hi * hi
+#pragma unroll
+              for (int h = 0; h < MH; ++h) {
+                const uint32_t ho = h * (UM * 128) + k * 32;
+                tc_mma_tf32(tmem_d + h * BN, make_desc_sw128(a1 + ho), make_desc_sw128(b0 + k * 32),
+                            kIdescTf32, (kb | k) ? 1u : 0u);                      // lo * hi
+                tc_mma_tf32(tmem_d + h * BN, make_desc_sw128(a0 + ho), make_desc_sw128(b1 + k * 32),
+                            kIdescTf32, 1u);                                       // hi * lo
+                tc_mma_tf32(tmem_d + h * BN, make_desc_sw128(a0 + ho), make_desc_sw128(b0 + k * 32),
+                            kIdescTf32, 1u);                                       // hi * hi
+              }
             }
             tc_commit(empty_bar(slot_hi));
             tc_commit(empty_bar(slot));
             advance();
           }
         }
-        tc_commit(tfull_bar(as));  // accumulator complete
+        tc_commit(tfull_bar(as));  // accumulator(s) complete
       }
     }
     __syncwarp();
@@ -332,33 +373,38 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int m = t % p.num_m_tiles, n = t / p.num_m_tiles;
-      const int as = it & 1;
-      mbar_wait(tfull_bar(as), (it >> 1) & 1u);
+      const int as = it % kAcc;
+      mbar_wait(tfull_bar(as), (it / kAcc) & 1u);
       tc_fence_after();
-      const int64_t row0 = static_cast<int64_t>(m) * BM + quarter * 32;
       const int64_t colt = static_cast<int64_t>(n) * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                               static_cast<uint32_t>(as * BN + c * 32);
-        tc_ld_32x32(taddr, v);
-        tc_wait_ld();
+      for (int h = 0; h < MH; ++h) {
+        const int64_t row0 = static_cast<int64_t>(m) * BM + h * UM + quarter * 32;
+        if (row0 >= p.Q) break;  // this half holds padding rows only (warp-uniform)
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                 static_cast<uint32_t>((as * MH + h) * BN + c * 32);
+          tc_ld_32x32(taddr, v);
+          tc_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * EPI_LD + j] = __uint_as_float(v[j]);
-        __syncwarp();
-        const int64_t col = colt + c * 32 + lane;
-        const bool col_ok = col < p.G;
-        const float gs = (p.gsq && col_ok) ? __ldg(p.gsq + col) : 0.f;
+          for (int j = 0; j < 32; ++j) stg[lane * EPI_LD + j] = __uint_as_float(v[j]);
+          __syncwarp();
+          const int64_t col = colt + c * 32 + lane;
+          const bool col_ok = col < p.G;
+          const float gs = (p.gsq && col_ok) ? __ldg(p.gsq + col) : 0.f;
 #pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
-          const int64_t r = row0 + rr;
-          if (r < p.Q && col_ok) {
-            const float qs = p.qsq ? __ldg(p.qsq + r) : 0.f;
-            p.out[r * p.ld + col] = epilogue(stg[rr * EPI_LD + lane], p.metric, qs, gs);
+          for (int rr = 0; rr < 32; ++rr) {
+            const int64_t r = row0 + rr;
+            if (r < p.Q && col_ok) {
+              const float qs = p.qsq ? __ldg(p.qsq + r) : 0.f;
+              const float val = epilogue(stg[rr * EPI_LD + lane], p.metric, qs, gs);
+              if (p.stream_out) __stcs(p.out + r * p.ld + col, val); else p.out[r * p.ld + col] = val;
+            }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -407,19 +453,22 @@ int make_map(dali_ctx *ctx, CUtensorMap *map, const void *base, int64_t rows, in
   return DALI_OK;
 }
 
-template <int MODE>
+template <int MODE, int MH>
 int launch_t(dali_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmA16,
              const CUtensorMap &tmB16, const UmmaParams &p) {
+  using C = Cfg<MH>;
   static bool attr_set = false;
   if (!attr_set) {
-    DALI_CUDA_OK(ctx, cudaFuncSetAttribute(distmat_umma_kernel<MODE>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    DALI_CUDA_OK(ctx, cudaFuncSetAttribute(distmat_umma_kernel<MODE, MH>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           C::kSmemBytes));
     attr_set = true;
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
   KTimer t(ctx, DALI_K_DISTMAT);
-  distmat_umma_kernel<MODE><<<grid, kThreads, kSmemBytes, ctx->stream>>>(tmA, tmB, tmA16, tmB16, p);
+  distmat_umma_kernel<MODE, MH><<<grid, kThreads, C::kSmemBytes, ctx->stream>>>(tmA, tmB, tmA16,
+                                                                               tmB16, p);
   DALI_CUDA_OK(ctx, cudaGetLastError());
   return DALI_OK;
 }
@@ -435,10 +484,15 @@ int launch_distmat_umma(dali_ctx *ctx, const float *q32, const float *g32, const
                         const float *qsq, const float *gsq, float *out, int64_t ld) {
   if (Q == 0 || G == 0) return DALI_OK;
   const int npl32 = precision == DALI_PREC_TF32X3 ? 2 : 1;
-  if (Dp % BK != 0 || q_rows_pad % BM != 0 || g_rows_pad % BN != 0 || g_row0 % BN != 0)
+  if (Dp % BK != 0 || q_rows_pad % 256 != 0 || g_rows_pad % BN != 0 || g_row0 % BN != 0)
     return set_err(ctx, DALI_ERR_INVALID, "umma operands must be padded (rows 128/256, D 32)");
   if (q_rows_pad * 2 > INT32_MAX || g_rows_pad * 2 > INT32_MAX)
     return set_err(ctx, DALI_ERR_UNSUPPORTED, "operand too tall for one tensor map");
+  // 256-row CTA tiles unless the query block is a single 128-row tile (or forced by the env)
+  static const char *force_mh = getenv("DALI_UMMA_MH");
+  int mh = 1;  // the 256-row tile (MH=2) measured slower in round 1 (shallower ring, exposed epilogue)
+  if (force_mh) mh = atoi(force_mh) == 2 ? 2 : 1;
+  const int BM = UM * mh;
   CUtensorMap tmA, tmB, tmA16, tmB16;
   int rc = make_map(ctx, &tmA, q32, q_rows_pad * npl32, Dp, BM, false);
   if (rc) return rc;
@@ -462,14 +516,30 @@ int launch_distmat_umma(dali_ctx *ctx, const float *q32, const float *g32, const
   p.b_plane_rows = static_cast<int32_t>(g_rows_pad);
   p.b_row0 = static_cast<int32_t>(g_row0);
   p.metric = metric; p.qsq = qsq; p.gsq = gsq; p.out = out; p.ld = ld;
+  // L2 policies (CUTLASS TMA::CacheHintSm90 encodings): EVICT_FIRST 0x12F0.., EVICT_LAST 0x14F0..
+  static const char *env_hint = getenv("DALI_UMMA_HINTS");
+  const int hints = env_hint ? atoi(env_hint) : 0;
+  p.hint_a = (hints & 1) ? 0x14F0000000000000ull : 0ull;  // queries: reused by every gallery tile
+  p.hint_b = (hints & 2) ? 0x12F0000000000000ull : 0ull;  // gallery tile: short-lived
+  p.stream_out = (hints & 4) ? 1 : 0;
   if (static_cast<int64_t>(p.num_m_tiles) * p.num_n_tiles > INT32_MAX)
     return set_err(ctx, DALI_ERR_UNSUPPORTED, "too many tiles (chunk the queries)");
-  switch (precision) {
-    case DALI_PREC_TF32: return launch_t<kTf32>(ctx, tmA, tmB, tmA16, tmB16, p);
-    case DALI_PREC_TF32X3: return launch_t<kTf32x3>(ctx, tmA, tmB, tmA16, tmB16, p);
-    case DALI_PREC_TF32C: return launch_t<kTf32c>(ctx, tmA, tmB, tmA16, tmB16, p);
-    default: return set_err(ctx, DALI_ERR_INVALID, "not a tensor-core precision");
+  if (mh == 2) {
+    switch (precision) {
+      case DALI_PREC_TF32: return launch_t<kTf32, 2>(ctx, tmA, tmB, tmA16, tmB16, p);
+      case DALI_PREC_TF32X3: return launch_t<kTf32x3, 2>(ctx, tmA, tmB, tmA16, tmB16, p);
+      case DALI_PREC_TF32C: return launch_t<kTf32c, 2>(ctx, tmA, tmB, tmA16, tmB16, p);
+      default: break;
+    }
+  } else {
+    switch (precision) {
+      case DALI_PREC_TF32: return launch_t<kTf32, 1>(ctx, tmA, tmB, tmA16, tmB16, p);
+      case DALI_PREC_TF32X3: return launch_t<kTf32x3, 1>(ctx, tmA, tmB, tmA16, tmB16, p);
+      case DALI_PREC_TF32C: return launch_t<kTf32c, 1>(ctx, tmA, tmB, tmA16, tmB16, p);
+      default: break;
+    }
   }
+  return set_err(ctx, DALI_ERR_INVALID, "not a tensor-core precision");
 }
 
 }  // namespace dali

@@ -1,0 +1,63 @@
+"""Ad-hoc performance probe (not a test): times the path on the other BASELINE shapes.
+    python tests/perf_probe.py [market_vit|deepchange|topk|faceid]"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from daliid_b200 import _lib, metrics, synth  # noqa: E402
+
+
+def timeit(fn, n=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n, out
+
+
+def main():
+    what = sys.argv[1] if len(sys.argv) > 1 else "market_vit"
+    ctx = _lib.get_ctx(0)
+    if what in ("market_vit", "deepchange", "market_resnet50"):
+        qf, gf, qp, gp, qc, gc = synth.make_config(what, device="cuda")
+        Q, G = qf.shape[0], gf.shape[0]
+        for prec in ("tf32c", "tf32", "fp32"):
+            if prec == "fp32" and what == "deepchange":
+                continue
+            ctx.timing_enable(True); ctx.timing_reset()
+            ms, (cmc, mAP) = timeit(lambda: metrics.evaluate_features(qf, gf, qp, gp, qc, gc, precision=prec))
+            kt = {k: round(v[1] / max(v[0], 1), 4) for k, v in ctx.timing_read().items() if v[0]}
+            ctx.timing_enable(False)
+            print(f"{what} {prec}: {ms:.3f} ms/eval, {Q * G / ms / 1e6:.2f} Gpairs/s, mAP={mAP:.5f} "
+                  f"R1={cmc[0]:.4f}, kernel ms: {kt}", flush=True)
+        d = metrics.compute_distance_matrix(qf, gf, "cosine", "tf32c")
+        ms, _ = timeit(lambda: metrics.topk_identify(d, k=20))
+        print(f"{what} topk k=20 from distmat: {ms:.3f} ms -> {4 * Q * G / ms / 1e6:.0f} GB/s", flush=True)
+        ms, _ = timeit(lambda: metrics.evaluate_rank(d, qp, gp, qc, gc))
+        print(f"{what} evaluate_rank from device distmat: {ms:.3f} ms", flush=True)
+        d2 = d.clone()
+        ms, _ = timeit(lambda: metrics.fuse_distmats([d, d2]))
+        print(f"{what} fuse 2: {ms:.3f} ms -> {12 * Q * G / ms / 1e6:.0f} GB/s", flush=True)
+    elif what == "faceid":
+        # scaled-down BASELINE config 5 (100k x 1M, D=512): 16k x 262k here, k=20
+        Q, G, D = 16384, 262144, 512
+        g = torch.Generator(device="cuda").manual_seed(12)
+        qf = torch.randn(Q, D, generator=g, device="cuda")
+        gf = torch.randn(G, D, generator=g, device="cuda")
+        for prec in ("tf32c", "tf32"):
+            ms, (v, i) = timeit(lambda: metrics.topk_features(qf, gf, k=20, precision=prec), n=2, warm=1)
+            print(f"faceid {Q}x{G} D={D} {prec}: {ms:.1f} ms, {Q * G / ms / 1e6:.2f} Gpairs/s, "
+                  f"{2 * Q * G * D / ms / 1e9:.0f} TFLOP/s", flush=True)
+
+
+if __name__ == "__main__":
+    main()
