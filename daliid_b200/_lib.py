@@ -60,6 +60,7 @@ _SIGNATURES = {
     "dali_ctx_timing_reset": (ci, [c_vp]),
     "dali_ctx_timing_read": (ci, [c_vp, ci, ctypes.POINTER(ci), c_f32p]),
     "dali_ctx_launch_count": (i64, [c_vp]),
+    "dali_ctx_fallback_count": (i64, [c_vp]),
     "dali_normalize_f32": (ci, [c_vp, c_vp, i64, i64, i64, c_vp, i64, c_vp]),
     "dali_distmat_f32": (ci, [c_vp, c_vp, i64, c_vp, i64, i64, ci, ci, ci, c_vp, i64]),
     "dali_fuse_f32": (ci, [c_vp, ctypes.POINTER(c_vp), ci, ctypes.POINTER(c_vp),
@@ -161,6 +162,9 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.dali_ctx_launch_count(self.h))
+
+    def fallback_count(self):
+        return int(self.lib.dali_ctx_fallback_count(self.h))
 
 
 _tls = threading.local()

@@ -3,6 +3,7 @@
 // host-side tail of the CMC/mAP reduction in both upstream accumulation modes.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <numeric>
@@ -489,6 +490,7 @@ int dali_ctx_timing_read(dali_ctx *ctx, int which, int *launches, float *total_m
 }
 
 int64_t dali_ctx_launch_count(dali_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t dali_ctx_fallback_count(dali_ctx *ctx) { return ctx ? ctx->fallbacks : 0; }
 
 // ---------------------------------------------------------------------------
 int dali_normalize_f32(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx, float *out,
@@ -1011,6 +1013,101 @@ int dali_topk_f32(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_
   return topk_out(ctx, dd, Q, G, ldd, k, largest, ids, 0, d_out, i_out);
 }
 
+// a7 from features, materialised: the gallery is processed in one slab through an internal
+// [band, G] matrix per query band (bounded workspace); each band owns its rows.
+static int topk_features_unfused(dali_ctx *ctx, const Prepared &b, const float *q, int64_t Q, int64_t G,
+                                 int64_t D, int metric, int precision, int normalize, int k,
+                                 int largest, int32_t g_base, float *d_out, int32_t *i_out) {
+  const int64_t ldd = round_up(std::max<int64_t>(G, 1), 4);
+  const int64_t budget = 8ll << 30;  // bytes of internal distance matrix per band
+  int64_t band = std::max<int64_t>(128, (budget / (sizeof(float) * ldd)) / 128 * 128);
+  band = std::min(band, round_up(Q, 128));
+  void *t;
+  int rc = ws_ensure(ctx, WS_DIST, sizeof(float) * band * ldd, &t);
+  if (rc) return rc;
+  float *dist = static_cast<float *>(t);
+  for (int64_t q0 = 0; q0 < Q; q0 += band) {
+    const int64_t qc = std::min(band, Q - q0);
+    Prepared a;
+    rc = prepare_operand(ctx, WS_QIN, WS_QN, WS_QN16, WS_QNORM, q + q0 * D, qc, D, metric, precision,
+                         normalize, &a);
+    if (rc) return rc;
+    if (G) {
+      rc = contract(ctx, a, b, qc, 0, G, metric, precision, dist, ldd);
+      if (rc) return rc;
+    }
+    rc = topk_out(ctx, dist, qc, G, ldd, k, largest, nullptr, g_base, d_out + q0 * k, i_out + q0 * k);
+    if (rc) return rc;
+  }
+  return DALI_OK;
+}
+
+// a7 from features, fused (BASELINE config 5): the Q x G matrix is never written.  The gallery
+// is swept in growing chunks; the contraction's epilogue keeps only distances not worse than the
+// row's current k-th best (distmat_umma2.cu, kFilter), a compaction pass after every chunk
+// re-selects the k best and tightens the threshold (topk.cu).  With the chunk a multiple `f` of
+// the columns already seen, a chunk yields about f*k survivors per row on exchangeable data.
+static int topk_features_fused(dali_ctx *ctx, const Prepared &b, const float *q, int64_t Q, int64_t G,
+                               int64_t D, int metric, int precision, int normalize, int k,
+                               int largest, int32_t g_base, float *d_out, int32_t *i_out,
+                               int *overflow_out) {
+  constexpr int kCapList = 1024;
+  const bool od = is_device_ptr(d_out), oi = is_device_ptr(i_out);
+  const int64_t band = std::min<int64_t>(round_up(Q, 256), 1ll << 18);  // 2 GiB of lists at most
+  void *cand_v, *cnt_v, *thr_v, *flag_v, *dd_v = d_out, *ii_v = i_out;
+  int rc = ws_ensure(ctx, WS_CAND, sizeof(uint64_t) * band * kCapList, &cand_v);
+  if (rc) return rc;
+  if ((rc = ws_ensure(ctx, WS_CAND_CNT, sizeof(int32_t) * band, &cnt_v))) return rc;
+  if ((rc = ws_ensure(ctx, WS_THR, sizeof(float) * band, &thr_v))) return rc;
+  if ((rc = ws_ensure(ctx, WS_FLAG, 256, &flag_v))) return rc;
+  if (!od && (rc = ws_ensure(ctx, WS_TOPK_D, sizeof(float) * Q * k, &dd_v))) return rc;
+  if (!oi && (rc = ws_ensure(ctx, WS_TOPK_I, sizeof(int32_t) * Q * k, &ii_v))) return rc;
+  uint64_t *cand = static_cast<uint64_t *>(cand_v);
+  int32_t *cnt = static_cast<int32_t *>(cnt_v);
+  float *thr = static_cast<float *>(thr_v);
+  int32_t *flag = static_cast<int32_t *>(flag_v);
+  float *dd = static_cast<float *>(dd_v);
+  int32_t *ii = static_cast<int32_t *>(ii_v);
+  DALI_CUDA_OK(ctx, cudaMemsetAsync(flag, 0, sizeof(int32_t), ctx->stream));
+  const int64_t growth = std::max<int64_t>(1, std::min<int64_t>(8, kCapList / (8 * k)));
+  for (int64_t q0 = 0; q0 < Q; q0 += band) {
+    const int64_t qc = std::min(band, Q - q0);
+    Prepared a;
+    rc = prepare_operand(ctx, WS_QIN, WS_QN, WS_QN16, WS_QNORM, q + q0 * D, qc, D, metric, precision,
+                         normalize, &a);
+    if (rc) return rc;
+    int64_t seen = 0;
+    while (seen < G) {
+      const bool first = seen == 0;
+      int64_t chunk = first ? std::min<int64_t>(G, kCapList)
+                            : std::min<int64_t>(G - seen, std::max<int64_t>(256, growth * seen / 256 * 256));
+      if (first && chunk < G) chunk = chunk / 256 * 256;  // later chunks must start on a tile edge
+      rc = launch_distmat_filter_umma(ctx, a.planes, b.planes, a.planes16, b.planes16, qc, chunk, a.Dp,
+                                      a.rows_pad, b.rows_pad, seen, precision, metric, a.sq,
+                                      b.sq ? b.sq + seen : nullptr, thr, cnt, cand, kCapList, largest,
+                                      first ? 1 : 0, g_base + static_cast<int32_t>(seen));
+      if (rc) return rc;
+      seen += chunk;
+      const bool last = seen >= G;
+      rc = launch_topk_compact(ctx, cand, cnt, thr, qc, kCapList, k, largest,
+                               first ? static_cast<int>(chunk) : -1, flag, last ? dd + q0 * k : nullptr,
+                               last ? ii + q0 * k : nullptr);
+      if (rc) return rc;
+    }
+  }
+  rc = pinned_ensure(ctx, 64);
+  if (rc) return rc;
+  int32_t *hflag = static_cast<int32_t *>(ctx->pinned);
+  DALI_CUDA_OK(ctx, cudaMemcpyAsync(hflag, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (!od)
+    DALI_CUDA_OK(ctx, cudaMemcpyAsync(d_out, dd, sizeof(float) * Q * k, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!oi)
+    DALI_CUDA_OK(ctx, cudaMemcpyAsync(i_out, ii, sizeof(int32_t) * Q * k, cudaMemcpyDeviceToHost, ctx->stream));
+  DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  *overflow_out = *hflag;
+  return DALI_OK;
+}
+
 int dali_topk_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float *g, int64_t G,
                            int64_t D, int metric, int precision, int normalize, int k, int largest,
                            int32_t g_base, float *d_out, int32_t *i_out) {
@@ -1021,35 +1118,23 @@ int dali_topk_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float
   rc = check_metric_prec(ctx, metric, precision);
   if (rc) return rc;
   if (Q == 0) return DALI_OK;
-  // Round 1: the gallery is processed in one slab through an internal [Qc, G] matrix per
-  // query band (bounded workspace); the band results are final because each band owns its rows.
-  Prepared a, b;
+  static const char *env_fused = getenv("DALI_TOPK_FUSED");
+  const bool fused = precision != DALI_PREC_FP32 && G > 0 && !(env_fused && atoi(env_fused) == 0);
+  Prepared b;
   rc = prepare_operand(ctx, WS_GIN, WS_GN, WS_GN16, WS_GNORM, g, G, D, metric, precision, normalize, &b);
   if (rc) return rc;
-  const int64_t ldd = round_up(std::max<int64_t>(G, 1), 4);
-  const int64_t budget = 8ll << 30;  // bytes of internal distance matrix per band
-  int64_t band = std::max<int64_t>(128, (budget / (sizeof(float) * ldd)) / 128 * 128);
-  band = std::min(band, round_up(Q, 128));
-  void *t;
-  rc = ws_ensure(ctx, WS_DIST, sizeof(float) * band * ldd, &t);
-  if (rc) return rc;
-  float *dist = static_cast<float *>(t);
-  const bool od = is_device_ptr(d_out), oi = is_device_ptr(i_out);
-  const bool qdev = is_device_ptr(q);
-  for (int64_t q0 = 0; q0 < Q; q0 += band) {
-    const int64_t qc = std::min(band, Q - q0);
-    rc = prepare_operand(ctx, WS_QIN, WS_QN, WS_QN16, WS_QNORM, q + q0 * D, qc, D, metric, precision,
-                         normalize, &a);
+  if (fused) {
+    int overflow = 0;
+    rc = topk_features_fused(ctx, b, q, Q, G, D, metric, precision, normalize, k, largest, g_base,
+                             d_out, i_out, &overflow);
     if (rc) return rc;
-    if (G) {
-      rc = contract(ctx, a, b, qc, 0, G, metric, precision, dist, ldd);
-      if (rc) return rc;
-    }
-    rc = topk_out(ctx, dist, qc, G, ldd, k, largest, nullptr, g_base, d_out + q0 * k, i_out + q0 * k);
-    if (rc) return rc;
-    (void)od; (void)oi; (void)qdev;
+    if (!overflow) return DALI_OK;
+    ctx->fallbacks++;
+    // a chunk produced more survivors than a candidate list holds (adversarial gallery order or
+    // massive ties): redo the call through the materialised path below
   }
-  return DALI_OK;
+  return topk_features_unfused(ctx, b, q, Q, G, D, metric, precision, normalize, k, largest, g_base,
+                               d_out, i_out);
 }
 
 }  // extern "C"

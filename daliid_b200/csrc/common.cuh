@@ -72,6 +72,10 @@ enum WsSlot {
   WS_TOPK_I,
   WS_PTRS,     // device arrays of pointers (fusion)
   WS_MISC,
+  WS_CAND,      // fused top-k: candidate lists [Q][cap] uint64
+  WS_CAND_CNT,  // [Q] int32
+  WS_THR,       // [Q] fp32 running k-th best distance
+  WS_FLAG,      // overflow flag
   WS_COUNT_
 };
 
@@ -100,6 +104,7 @@ struct dali_ctx {
   std::vector<cudaEvent_t> t_pool;
   float t_ms[DALI_K_COUNT_] = {0};
   int64_t launches = 0;
+  int64_t fallbacks = 0;  // fused calls that had to be redone through the materialised path
   // tensor-map encoder (driver entry point, resolved lazily)
   void *encode_tiled = nullptr;
 };
@@ -162,6 +167,13 @@ int launch_distmat_umma(dali_ctx *ctx, const float *q32, const float *g32, const
                         const void *g16, int64_t Q, int64_t G, int64_t Dp, int64_t q_rows_pad,
                         int64_t g_rows_pad, int64_t g_row0, int precision, int metric,
                         const float *qsq, const float *gsq, float *out, int64_t ld);
+// distmat_umma2.cu
+int launch_distmat_filter_umma(dali_ctx *ctx, const float *q32, const float *g32, const void *q16,
+                               const void *g16, int64_t Q, int64_t G, int64_t Dp,
+                               int64_t q_rows_pad, int64_t g_rows_pad, int64_t g_row0,
+                               int precision, int metric, const float *qsq, const float *gsq,
+                               const float *thr, int32_t *cand_cnt, uint64_t *cand, int cap,
+                               int largest, int direct, int32_t id_base);
 // rank.cu
 int launch_plan_expand(dali_ctx *ctx, const dali_rank_plan *plan);
 int launch_rank_gather(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist, int64_t ld,
@@ -175,6 +187,9 @@ int launch_rank_finalize(dali_ctx *ctx, const dali_rank_plan *plan, const uint32
 int launch_topk(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t ld, int k,
                 int largest, const int32_t *col_ids, int32_t id_base, float *d_out,
                 int32_t *i_out);
+int launch_topk_compact(dali_ctx *ctx, uint64_t *cand, int32_t *cand_cnt, float *thr, int64_t Q,
+                        int cap, int k, int largest, int fixed_cnt, int32_t *overflow, float *d_out,
+                        int32_t *i_out);
 // fuse.cu
 int launch_fuse(dali_ctx *ctx, const float *const *d_ptrs_dev, int n, const float *const *wq_dev,
                 const float *const *wg_dev, float *out, int64_t Q, int64_t G, int64_t ld);

@@ -21,23 +21,16 @@
 //
 // replaces  1.0 - torch.mm(q, g.T)   validateModels.py:47, evaluate.py:260-267,291,
 //           evaluate_ensembled_models.py:281,300, evaluateCleanATModels.py:109,121,124
-#include <cuda.h>
-
 #include <cstdlib>
 
-#include "common.cuh"
+#include "umma_common.cuh"
 
 namespace dali {
 
 namespace {
 
-constexpr int UM = 128;        // UMMA M (TMEM lanes) per instruction
-constexpr int BN = 256;        // UMMA N (TMEM columns per accumulator)
-constexpr int BK = 32;         // K elements per pipeline slot
+using namespace umma;
 constexpr int kThreads = 192;
-constexpr int EPI_LD = 33;
-constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
-constexpr uint64_t kWatchdogCycles = 4000000000ull;  // ~2 s: trap instead of hanging the box
 
 // MH = number of 128-row UMMA halves per CTA tile.
 //   MH = 1: 128 x 256 tile, 4 slots of 48 KiB, two accumulators (epilogue overlaps the next tile)
@@ -57,130 +50,7 @@ struct Cfg {
   static constexpr int kSmemBytes = kSlots * kSlotBytes + EPI_BYTES + 256 + 1024;
 };
 
-enum Mode { kTf32 = 0, kTf32x3 = 1, kTf32c = 2 };
 
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > kWatchdogCycles) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar,
-                                            int32_t x, int32_t y) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap *map, uint32_t bar,
-                                                 int32_t x, int32_t y, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
-      "[%0], [%1, {%2, %3}], [%4], %5;"
-      ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar), "l"(policy)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-               ::"r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                            uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                            uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
-        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
-        "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major operand tiles (cute::UMMA::SmemDescriptor): start address [0,14) (>>4), LBO [16,30) = 1
-// (unused for swizzled K-major), SBO [32,46) = bytes between 8-row groups (>>4), descriptor
-// version [46,48) = 1 (sm_100), layout type [61,64): 2 = SWIZZLE_128B (fp32 tiles, rows of 128 B,
-// SBO 1024), 4 = SWIZZLE_64B (bf16 tiles, rows of 64 B, SBO 512).
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
-  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) |
-         (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
-  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (32ull << 32) |
-         (1ull << 46) | (4ull << 61);
-}
-
-// cute::UMMA::InstrDescriptor: fp32 accumulate (bit 4), A/B format [7,10)/[10,13)
-// (2 = TF32, 1 = BF16), both K-major, N>>3 at [17,23), M>>4 at [24,29).
-constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) |
-                                (uint32_t(UM >> 4) << 24);
-constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) |
-                                (uint32_t(UM >> 4) << 24);
-
-__device__ __forceinline__ float epilogue(float acc, int metric, float qs, float gs) {
-  switch (metric) {
-    case DALI_METRIC_COSINE: return 1.0f - acc;
-    case DALI_METRIC_SQEUCLIDEAN: return fmaf(-2.0f, acc, qs + gs);
-    case DALI_METRIC_EUCLIDEAN: return sqrtf(fmaxf(fmaf(-2.0f, acc, qs + gs), 1e-30f));
-    default: return acc;
-  }
-}
 
 struct UmmaParams {
   int64_t Q, G;
@@ -316,8 +186,8 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int k = 0; k < BK / 8; ++k)  // 32 bytes of K per tf32 MMA inside the 128 B atom
 #pragma unroll
               for (int h = 0; h < MH; ++h)
-                tc_mma_tf32(tmem_d + h * BN, make_desc_sw128(a0 + h * (UM * 128) + k * 32),
-                            make_desc_sw128(b0 + k * 32), kIdescTf32, (kb | k) ? 1u : 0u);
+                tc_mma_tf32<1>(tmem_d + h * BN, make_desc_sw128(a0 + h * (UM * 128) + k * 32),
+                            make_desc_sw128(b0 + k * 32), idesc_tf32(UM), (kb | k) ? 1u : 0u);
             tc_commit(empty_bar(slot));  // frees the slot when these MMAs retire
             advance();
             if (MODE == kTf32c) {
@@ -329,10 +199,10 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int k = 0; k < BK / 16; ++k) {  // 32 bytes of K per bf16 MMA inside the 64 B atom
 #pragma unroll
                 for (int h = 0; h < MH; ++h) {
-                  tc_mma_bf16(tmem_d + h * BN, make_desc_sw64(alo + h * (UM * 64) + k * 32),
-                              make_desc_sw64(bhi + k * 32), kIdescBf16, 1u);
-                  tc_mma_bf16(tmem_d + h * BN, make_desc_sw64(ahi + h * (UM * 64) + k * 32),
-                              make_desc_sw64(blo + k * 32), kIdescBf16, 1u);
+                  tc_mma_bf16<1>(tmem_d + h * BN, make_desc_sw64(alo + h * (UM * 64) + k * 32),
+                              make_desc_sw64(bhi + k * 32), idesc_bf16(UM), 1u);
+                  tc_mma_bf16<1>(tmem_d + h * BN, make_desc_sw64(ahi + h * (UM * 64) + k * 32),
+                              make_desc_sw64(blo + k * 32), idesc_bf16(UM), 1u);
                 }
               }
               tc_commit(empty_bar(slot));
@@ -349,12 +219,12 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
               for (int h = 0; h < MH; ++h) {
                 const uint32_t ho = h * (UM * 128) + k * 32;
-                tc_mma_tf32(tmem_d + h * BN, make_desc_sw128(a1 + ho), make_desc_sw128(b0 + k * 32),
-                            kIdescTf32, (kb | k) ? 1u : 0u);                      // lo * hi
-                tc_mma_tf32(tmem_d + h * BN, make_desc_sw128(a0 + ho), make_desc_sw128(b1 + k * 32),
-                            kIdescTf32, 1u);                                       // hi * lo
-                tc_mma_tf32(tmem_d + h * BN, make_desc_sw128(a0 + ho), make_desc_sw128(b0 + k * 32),
-                            kIdescTf32, 1u);                                       // hi * hi
+                tc_mma_tf32<1>(tmem_d + h * BN, make_desc_sw128(a1 + ho), make_desc_sw128(b0 + k * 32),
+                            idesc_tf32(UM), (kb | k) ? 1u : 0u);                      // lo * hi
+                tc_mma_tf32<1>(tmem_d + h * BN, make_desc_sw128(a0 + ho), make_desc_sw128(b1 + k * 32),
+                            idesc_tf32(UM), 1u);                                       // hi * lo
+                tc_mma_tf32<1>(tmem_d + h * BN, make_desc_sw128(a0 + ho), make_desc_sw128(b0 + k * 32),
+                            idesc_tf32(UM), 1u);                                       // hi * hi
               }
             }
             tc_commit(empty_bar(slot_hi));
@@ -399,7 +269,7 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int64_t r = row0 + rr;
             if (r < p.Q && col_ok) {
               const float qs = p.qsq ? __ldg(p.qsq + r) : 0.f;
-              const float val = epilogue(stg[rr * EPI_LD + lane], p.metric, qs, gs);
+              const float val = metric_epilogue(stg[rr * EPI_LD + lane], p.metric, qs, gs);
               if (p.stream_out) __stcs(p.out + r * p.ld + col, val); else p.out[r * p.ld + col] = val;
             }
           }
@@ -421,37 +291,6 @@ distmat_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
-                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
-                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// 2-D K-major operand map: dims {Dp, rows}, box {BK, box_rows}; fp32 tiles use the 128-byte
-// swizzle (BK * 4 = 128 B), bf16 tiles the 64-byte swizzle (BK * 2 = 64 B).
-int make_map(dali_ctx *ctx, CUtensorMap *map, const void *base, int64_t rows, int64_t Dp,
-             int box_rows, bool bf16) {
-  if (!ctx->encode_tiled) {
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
-      return set_err(ctx, DALI_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-    ctx->encode_tiled = fn;
-  }
-  const int esz = bf16 ? 2 : 4;
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(Dp), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(Dp) * esz};
-  cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
-      map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-      const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-      bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return set_err(ctx, DALI_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
-  return DALI_OK;
-}
 
 template <int MODE, int MH>
 int launch_t(dali_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmA16,
@@ -478,7 +317,7 @@ int launch_t(dali_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, cons
 // q32/g32: [npl32][rows_pad][Dp] fp32 planes (plane 0 = TF32-rounded operand, plane 1 = residual,
 // TF32X3 only); q16/g16: [2][rows_pad][Dp] bf16 planes (hi16, lo16; TF32C only).
 // rows_pad multiples of 256, Dp multiple of 32.  mode: DALI_PREC_TF32 / TF32X3 / TF32C.
-int launch_distmat_umma(dali_ctx *ctx, const float *q32, const float *g32, const void *q16,
+int launch_distmat_umma1(dali_ctx *ctx, const float *q32, const float *g32, const void *q16,
                         const void *g16, int64_t Q, int64_t G, int64_t Dp, int64_t q_rows_pad,
                         int64_t g_rows_pad, int64_t g_row0, int precision, int metric,
                         const float *qsq, const float *gsq, float *out, int64_t ld) {

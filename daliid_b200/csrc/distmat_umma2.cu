@@ -1,0 +1,543 @@
+// Q x G x D distance contraction on CTA pairs (tcgen05 cta_group::2), the default tensor-core
+// path (SURVEY 8a rows a2/a2', a7 fused; precisions DALI_PREC_TF32, TF32X3, TF32C).
+//
+//   out[i,j] = epilogue( sum_k A[i,k] * B[j,k] )        A = prepared queries, B = gallery
+//
+// Why pairs: with one CTA per 128 x 256 tile every k-block moves 48 KiB of fp32 operands
+// through L2 -> shared memory -> tensor core for 0.38 us of TF32 MMA time: 125 GB/s per SM in
+// each direction, which is the shared-memory port (128 B/clk) and ~15 TB/s of L2 fabric chip
+// wide; round 1 measured the tensor pipe 72-76 % active because of it.  Two CTAs of one TPC
+// computing a 256 x 256 tile together each stage only HALF of the gallery tile (the MMA reads
+// both halves), so operand traffic per FLOP drops by a third and the B-side shared-memory
+// reads by half.
+//
+// Structure (persistent, one CTA pair per TPC, 192 threads per CTA):
+//   warp 0    TMA producer (both CTAs): its 128 query rows + its 128 gallery rows of the k-block
+//             into a ring of six 32 KiB slots; transaction bytes of BOTH CTAs are reported to the
+//             leader's `full` barrier (cp.async.bulk.tensor ... .cta_group::2)
+//   warp 1    allocates TMEM (both CTAs, 512 columns = two 128x256 fp32 accumulators each); in the
+//             leader CTA one lane issues tcgen05.mma.cta_group::2 (M=256, N=256) and releases
+//             slots / publishes accumulators with multicast tcgen05.commit to both CTAs
+//   warps 2-5 epilogue (both CTAs, each drains its own 128 accumulator rows), overlapped with
+//             the next tile's MMAs through the second accumulator:
+//               kStore   metric -> transpose through shared memory -> coalesced row stores
+//               kFilter  metric -> compare with the row's running k-th best distance -> append
+//                        the rare survivors to the row's candidate list (fused top-k, the
+//                        distance matrix is never written: BASELINE config 5)
+//
+// replaces  1.0 - torch.mm(q, g.T)   validateModels.py:47, evaluate.py:260-267,291,
+//           evaluate_ensembled_models.py:281,300, evaluateCleanATModels.py:109,121,124
+//           torch.argsort(distmat, dim=1)[:, :20]   validateModels.py:93 (kFilter)
+#include <cstdlib>
+
+#include "umma_common.cuh"
+
+namespace dali {
+
+int launch_distmat_umma1(dali_ctx *ctx, const float *q32, const float *g32, const void *q16,
+                         const void *g16, int64_t Q, int64_t G, int64_t Dp, int64_t q_rows_pad,
+                         int64_t g_rows_pad, int64_t g_row0, int precision, int metric,
+                         const float *qsq, const float *gsq, float *out, int64_t ld);
+
+namespace {
+
+using namespace umma;
+
+constexpr int kThreads = 192;
+constexpr int PM = 2 * UM;                 // rows of a pair tile
+constexpr int HB = BN / 2;                 // gallery rows staged by each CTA
+constexpr int A_BYTES = UM * BK * 4;       // 16 KiB fp32 (rows of 128 B, SWIZZLE_128B)
+constexpr int B_BYTES = HB * BK * 4;       // 16 KiB
+constexpr int A16_BYTES = UM * BK * 2;     // 8 KiB bf16 (rows of 64 B, SWIZZLE_64B)
+constexpr int B16_BYTES = HB * BK * 2;     // 8 KiB
+constexpr int kSlotBytes = A_BYTES + B_BYTES;  // 32 KiB == 2*A16 + 2*B16
+constexpr int kSlots = 6;
+constexpr int kBarBytes = 256;
+constexpr int kSmemBytes = kSlots * kSlotBytes + EPI_BYTES + kBarBytes + 1024;
+static_assert(8 * (2 * kSlots + 4) + 8 <= kBarBytes, "barrier block too small");
+
+enum Epi { kStore = 0, kFilter = 1 };
+
+struct Umma2Params {
+  int64_t Q, G;
+  int num_m_pairs, num_n_tiles, num_kb;
+  int32_t a_plane_rows, b_plane_rows;  // row offset of plane 1 inside the tensor maps
+  int32_t b_row0;                      // first gallery row of this slab inside the B planes
+  int metric;
+  const float *qsq, *gsq;
+  // kStore
+  float *out;
+  int64_t ld;
+  // kFilter
+  const float *thr;     // [Q] running k-th best distance of the row (+inf / -inf: accept all)
+  int32_t *cand_cnt;    // [Q] entries appended to the row's list
+  uint64_t *cand;       // [Q][cap] composites (order key << 32 | gallery id)
+  int cap;
+  int largest;
+  int direct;           // 1: every column j is written to slot j of the list (first chunk)
+  int32_t id_base;      // gallery id of column 0
+  int debug;            // DALI_DEBUG_EPI (profiling experiments only)
+};
+
+// ---- kFilter epilogue: 32 accumulator columns of one query row -------------------------------
+struct FilterRow {
+  float thr, qs, alpha, beta;
+  uint32_t flip;
+  uint64_t *list;
+  int32_t *cnt;
+  int cap;
+  bool row_ok;
+};
+
+// v[j] for a run-time j without spilling the accumulator registers: a 5-level select tree.
+__device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int j) {
+  uint32_t a[16], b[8], c[4], d[2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) d[i] = (j & 8) ? c[2 * i + 1] : c[2 * i];
+  return (j & 16) ? d[1] : d[0];
+}
+
+// KIND 0: d = alpha * acc + beta (cosine: 1 - acc, dot: acc); 1: |q|^2 + |g|^2 - 2 acc; 2: its
+// square root (the expressions of umma::metric_epilogue, bit for bit).  SEL 0: keep d <= thr,
+// 1: keep d >= thr, 2: keep every column (first chunk, column j goes to slot j).  NaN always
+// passes, as it sorts last / first like everywhere else.
+// The hot loop is branch free (FFMA, FSETP, predicated OR into a survivor mask): survivors are
+// about one element in a thousand, and a branch per element paced the whole kernel (measured:
+// 11.8 ms against 4.9 ms of MMA time at 16k x 262k, D = 512).
+template <int KIND, int SEL>
+__device__ __forceinline__ void filter_cols(const uint32_t (&v)[32], const FilterRow &fr,
+                                            const float *__restrict__ gs, int lim, uint32_t id0,
+                                            int slot0) {
+  auto dist_of = [&](uint32_t bits, int j) {
+    const float acc = __uint_as_float(bits);
+    float d;
+    if (KIND == 0) {
+      d = fmaf(acc, fr.alpha, fr.beta);
+    } else {
+      d = fmaf(-2.0f, acc, fr.qs + __ldg(gs + (j < lim ? j : 0)));
+      if (KIND == 2) d = sqrtf(fmaxf(d, 1e-30f));
+    }
+    return d;
+  };
+  if (SEL == 2) {
+    if (!fr.row_ok) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < lim) fr.list[slot0 + j] = composite(dist_key(dist_of(v[j], j)) ^ fr.flip, id0 + j);
+    return;
+  }
+  uint32_t mask = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float d = dist_of(v[j], j);
+    const bool pass = SEL == 1 ? !(d < fr.thr) : !(d > fr.thr);
+    mask |= pass ? (1u << j) : 0u;
+  }
+  if (lim < 32) mask &= (1u << lim) - 1u;
+  if (!fr.row_ok) mask = 0;
+  while (mask) {  // rare, divergent
+    const int j = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const float d = dist_of(pick32(v, j), j);
+    const int pos = atomicAdd(fr.cnt, 1);
+    if (pos < fr.cap) fr.list[pos] = composite(dist_key(d) ^ fr.flip, id0 + j);
+  }
+  // the next tcgen05.ld is .sync.aligned: lanes that took the loop above must have rejoined
+  // (without this the lanes with no survivor ran ahead and the load landed in registers the
+  // others were still reading)
+  __syncwarp();
+}
+
+template <int MODE, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmA16,
+                     const __grid_constant__ CUtensorMap tmB16, const Umma2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  // the dynamic window starts at the same offset in both CTAs, so this rounding is identical
+  // in the pair (the MMA applies the leader's operand offsets to the peer's shared memory)
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                              ~uintptr_t(1023));
+  float *epi = reinterpret_cast<float *>(smem + kSlots * kSlotBytes);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kSlots * kSlotBytes + EPI_BYTES);
+  // bars: [0,S) full (leader's are used), [S,2S) empty, [2S,2S+2) tmem_full,
+  //       [2S+2,2S+4) tmem_empty (leader's are used), then the TMEM base pointer
+  uint32_t *tmem_ptr_s = reinterpret_cast<uint32_t *>(bars + 2 * kSlots + 4);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kSlots + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kSlots + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kSlots + 2 + s); };
+  auto slot_addr = [&](int s) { return smem_u32(smem + s * kSlotBytes); };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs)
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int num_tiles = p.num_m_pairs * p.num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (MODE == kTf32c) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA16) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB16) : "memory");
+    }
+    for (int s = 0; s < kSlots; ++s) {
+      mbar_init(full_bar(s), 1);   // the leader's arrive.expect_tx
+      mbar_init(empty_bar(s), 1);  // one multicast commit
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);   // one multicast commit
+      mbar_init(tempty_bar(s), 8);  // four epilogue warps in each CTA of the pair
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;"
+                 ::"r"(smem_u32(tmem_ptr_s))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs are initialised before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() { if (++slot == kSlots) { slot = 0; phase ^= 1u; } };
+      const uint32_t full0 = mapa_u32(full_bar(0), 0);  // the leader's full barriers
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        const int m = t % p.num_m_pairs, n = t / p.num_m_pairs;
+        const int arow = m * PM + static_cast<int>(rank) * UM;
+        const int brow = p.b_row0 + n * BN + static_cast<int>(rank) * HB;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(empty_bar(slot), phase ^ 1u);
+          if (rank == 0) mbar_expect_tx(full_bar(slot), 2 * kSlotBytes);
+          const uint32_t fb = full0 + 8u * slot;
+          tma_load_2d_pair(slot_addr(slot), &tmA, fb, kb * BK, arow);
+          tma_load_2d_pair(slot_addr(slot) + A_BYTES, &tmB, fb, kb * BK, brow);
+          advance();
+          if (MODE == kTf32x3) {  // residual planes (fp32, TF32-rounded)
+            mbar_wait(empty_bar(slot), phase ^ 1u);
+            if (rank == 0) mbar_expect_tx(full_bar(slot), 2 * kSlotBytes);
+            const uint32_t fb1 = full0 + 8u * slot;
+            tma_load_2d_pair(slot_addr(slot), &tmA, fb1, kb * BK, p.a_plane_rows + arow);
+            tma_load_2d_pair(slot_addr(slot) + A_BYTES, &tmB, fb1, kb * BK, p.b_plane_rows + brow);
+            advance();
+          } else if (MODE == kTf32c) {  // bf16 hi and residual planes
+            mbar_wait(empty_bar(slot), phase ^ 1u);
+            if (rank == 0) mbar_expect_tx(full_bar(slot), 2 * kSlotBytes);
+            const uint32_t fb1 = full0 + 8u * slot;
+            const uint32_t sb = slot_addr(slot);
+            tma_load_2d_pair(sb, &tmA16, fb1, kb * BK, arow);
+            tma_load_2d_pair(sb + A16_BYTES, &tmA16, fb1, kb * BK, p.a_plane_rows + arow);
+            tma_load_2d_pair(sb + 2 * A16_BYTES, &tmB16, fb1, kb * BK, brow);
+            tma_load_2d_pair(sb + 2 * A16_BYTES + B16_BYTES, &tmB16, fb1, kb * BK,
+                             p.b_plane_rows + brow);
+            advance();
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t kIdT = idesc_tf32(PM), kIdB = idesc_bf16(PM);
+      int slot = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() { if (++slot == kSlots) { slot = 0; phase ^= 1u; } };
+      int it = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+        const int as = it & 1;
+        // both CTAs' epilogues drained this accumulator
+        mbar_wait_cluster(tempty_bar(as), ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(full_bar(slot), phase);
+          tc_fence_after();
+          const uint32_t a0 = slot_addr(slot), b0 = a0 + A_BYTES;
+          if (MODE == kTf32 || MODE == kTf32c) {
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k)  // 32 bytes of K per tf32 MMA inside the 128 B atom
+              tc_mma_tf32<2>(tmem_d, make_desc_sw128(a0 + k * 32), make_desc_sw128(b0 + k * 32),
+                             kIdT, (kb | k) ? 1u : 0u);
+            tc_commit_pair(empty_bar(slot), 3);  // frees the slot in both CTAs
+            advance();
+            if (MODE == kTf32c) {
+              mbar_wait(full_bar(slot), phase);
+              tc_fence_after();
+              const uint32_t ahi = slot_addr(slot), alo = ahi + A16_BYTES;
+              const uint32_t bhi = ahi + 2 * A16_BYTES, blo = bhi + B16_BYTES;
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {  // 32 bytes of K per bf16 MMA inside the 64 B atom
+                tc_mma_bf16<2>(tmem_d, make_desc_sw64(alo + k * 32), make_desc_sw64(bhi + k * 32),
+                               kIdB, 1u);
+                tc_mma_bf16<2>(tmem_d, make_desc_sw64(ahi + k * 32), make_desc_sw64(blo + k * 32),
+                               kIdB, 1u);
+              }
+              tc_commit_pair(empty_bar(slot), 3);
+              advance();
+            }
+          } else {  // kTf32x3: both slots are needed by the cross terms
+            const int slot_hi = slot;
+            advance();
+            mbar_wait(full_bar(slot), phase);
+            tc_fence_after();
+            const uint32_t a1 = slot_addr(slot), b1 = a1 + A_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {
+              tc_mma_tf32<2>(tmem_d, make_desc_sw128(a1 + k * 32), make_desc_sw128(b0 + k * 32),
+                             kIdT, (kb | k) ? 1u : 0u);                           // lo * hi
+              tc_mma_tf32<2>(tmem_d, make_desc_sw128(a0 + k * 32), make_desc_sw128(b1 + k * 32),
+                             kIdT, 1u);                                            // hi * lo
+              tc_mma_tf32<2>(tmem_d, make_desc_sw128(a0 + k * 32), make_desc_sw128(b0 + k * 32),
+                             kIdT, 1u);                                            // hi * hi
+            }
+            tc_commit_pair(empty_bar(slot_hi), 3);
+            tc_commit_pair(empty_bar(slot), 3);
+            advance();
+          }
+        }
+        tc_commit_pair(tfull_bar(as), 3);  // accumulator complete, both CTAs
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (both CTAs) =====================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
+    float *stg = epi + (warp - 2) * 32 * EPI_LD;
+    int it = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+      const int m = t % p.num_m_pairs, n = t / p.num_m_pairs;
+      const int as = it & 1;
+      mbar_wait(tfull_bar(as), (it >> 1) & 1u);
+      tc_fence_after();
+      const int64_t colt = static_cast<int64_t>(n) * BN;
+      const int64_t row0 = static_cast<int64_t>(m) * PM + rank * UM + quarter * 32;
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                             static_cast<uint32_t>(as * BN);
+      if (row0 < p.Q) {  // otherwise this warp's rows are padding (warp-uniform)
+        if (EPI == kStore) {
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) {
+            if (colt + c * 32 >= p.G) break;
+            uint32_t v[32];
+            tc_ld_32x32(tbase + c * 32, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) stg[lane * EPI_LD + j] = __uint_as_float(v[j]);
+            __syncwarp();
+            const int64_t col = colt + c * 32 + lane;
+            const bool col_ok = col < p.G;
+            const float gs = (p.gsq && col_ok) ? __ldg(p.gsq + col) : 0.f;
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) {
+              const int64_t r = row0 + rr;
+              if (r < p.Q && col_ok) {
+                const float qs = p.qsq ? __ldg(p.qsq + r) : 0.f;
+                p.out[r * p.ld + col] = metric_epilogue(stg[rr * EPI_LD + lane], p.metric, qs, gs);
+              }
+            }
+            __syncwarp();
+          }
+        } else {
+          // one thread per query row: its 256 distances of this tile against the row's
+          // running threshold; the survivors (about k ln(G/k) per row over the whole
+          // gallery) go to the row's candidate list
+          const int64_t r = row0 + lane;
+          FilterRow fr;
+          fr.row_ok = r < p.Q;
+          fr.thr = fr.row_ok ? __ldg(p.thr + r) : 0.f;
+          fr.qs = (p.qsq && fr.row_ok) ? __ldg(p.qsq + r) : 0.f;
+          fr.alpha = p.metric == DALI_METRIC_COSINE ? -1.0f : 1.0f;
+          fr.beta = p.metric == DALI_METRIC_COSINE ? 1.0f : 0.0f;
+          fr.flip = p.largest ? 0xFFFFFFFFu : 0u;
+          fr.list = p.cand + (fr.row_ok ? r : 0) * p.cap;
+          fr.cnt = p.cand_cnt + (fr.row_ok ? r : 0);
+          fr.cap = p.cap;
+          const int kind = p.metric == DALI_METRIC_SQEUCLIDEAN ? 1 : p.metric == DALI_METRIC_EUCLIDEAN ? 2 : 0;
+          const int sel = p.direct ? 2 : (p.largest ? 1 : 0);
+          const int variant = kind * 3 + sel;  // warp-uniform
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) {
+            const int64_t col0 = colt + c * 32;
+            if (col0 >= p.G) break;
+            if (p.debug & 1) break;
+            uint32_t v[32];
+            tc_ld_32x32(tbase + c * 32, v);
+            tc_wait_ld();
+            if (p.debug & 2) {  // loads only
+              asm volatile("" ::"r"(v[0]), "r"(v[7]), "r"(v[15]), "r"(v[23]), "r"(v[31]));
+              continue;
+            }
+            if (p.debug & 4) {  // loads + compares, no append path
+              int npass = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                npass += !(fmaf(__uint_as_float(v[j]), fr.alpha, fr.beta) > fr.thr) ? 1 : 0;
+              if (npass == 77) p.cand_cnt[0] = 1;
+              continue;
+            }
+            const int lim = p.G - col0 < 32 ? static_cast<int>(p.G - col0) : 32;
+            const float *gs = p.gsq ? p.gsq + col0 : nullptr;
+            const uint32_t id0 = static_cast<uint32_t>(p.id_base + col0);
+            const int slot0 = static_cast<int>(col0);
+            switch (variant) {
+              case 0: filter_cols<0, 0>(v, fr, gs, lim, id0, slot0); break;
+              case 1: filter_cols<0, 1>(v, fr, gs, lim, id0, slot0); break;
+              case 2: filter_cols<0, 2>(v, fr, gs, lim, id0, slot0); break;
+              case 3: filter_cols<1, 0>(v, fr, gs, lim, id0, slot0); break;
+              case 4: filter_cols<1, 1>(v, fr, gs, lim, id0, slot0); break;
+              case 5: filter_cols<1, 2>(v, fr, gs, lim, id0, slot0); break;
+              case 6: filter_cols<2, 0>(v, fr, gs, lim, id0, slot0); break;
+              case 7: filter_cols<2, 1>(v, fr, gs, lim, id0, slot0); break;
+              default: filter_cols<2, 2>(v, fr, gs, lim, id0, slot0); break;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_bar(as), 0);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs are done with TMEM and with each other's barriers
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base)
+                 : "memory");
+  }
+}
+
+template <int MODE, int EPI>
+int launch_t(dali_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmA16,
+             const CUtensorMap &tmB16, const Umma2Params &p) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DALI_CUDA_OK(ctx, cudaFuncSetAttribute(distmat_umma2_kernel<MODE, EPI>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = p.num_m_pairs * p.num_n_tiles;
+  const int max_pairs = ctx->num_sms / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  KTimer t(ctx, DALI_K_DISTMAT);
+  distmat_umma2_kernel<MODE, EPI><<<2 * pairs, kThreads, kSmemBytes, ctx->stream>>>(tmA, tmB, tmA16,
+                                                                                   tmB16, p);
+  DALI_CUDA_OK(ctx, cudaGetLastError());
+  return DALI_OK;
+}
+
+template <int EPI>
+int launch_prec(dali_ctx *ctx, int precision, const CUtensorMap &tmA, const CUtensorMap &tmB,
+                const CUtensorMap &tmA16, const CUtensorMap &tmB16, const Umma2Params &p) {
+  switch (precision) {
+    case DALI_PREC_TF32: return launch_t<kTf32, EPI>(ctx, tmA, tmB, tmA16, tmB16, p);
+    case DALI_PREC_TF32X3: return launch_t<kTf32x3, EPI>(ctx, tmA, tmB, tmA16, tmB16, p);
+    case DALI_PREC_TF32C: return launch_t<kTf32c, EPI>(ctx, tmA, tmB, tmA16, tmB16, p);
+    default: return set_err(ctx, DALI_ERR_INVALID, "not a tensor-core precision");
+  }
+}
+
+int setup(dali_ctx *ctx, const float *q32, const float *g32, const void *q16, const void *g16,
+          int64_t Q, int64_t G, int64_t Dp, int64_t q_rows_pad, int64_t g_rows_pad, int64_t g_row0,
+          int precision, int metric, const float *qsq, const float *gsq, CUtensorMap *tmA,
+          CUtensorMap *tmB, CUtensorMap *tmA16, CUtensorMap *tmB16, Umma2Params *p) {
+  const int npl32 = precision == DALI_PREC_TF32X3 ? 2 : 1;
+  if (Dp % BK != 0 || q_rows_pad % PM != 0 || g_rows_pad % BN != 0 || g_row0 % BN != 0)
+    return set_err(ctx, DALI_ERR_INVALID, "umma operands must be padded (rows 256, D 32)");
+  if (q_rows_pad * 2 > INT32_MAX || g_rows_pad * 2 > INT32_MAX)
+    return set_err(ctx, DALI_ERR_UNSUPPORTED, "operand too tall for one tensor map");
+  int rc = make_map(ctx, tmA, q32, q_rows_pad * npl32, Dp, UM, false);
+  if (rc) return rc;
+  rc = make_map(ctx, tmB, g32, g_rows_pad * npl32, Dp, HB, false);
+  if (rc) return rc;
+  if (precision == DALI_PREC_TF32C) {
+    rc = make_map(ctx, tmA16, q16, q_rows_pad * 2, Dp, UM, true);
+    if (rc) return rc;
+    rc = make_map(ctx, tmB16, g16, g_rows_pad * 2, Dp, HB, true);
+    if (rc) return rc;
+  } else {
+    *tmA16 = *tmA;
+    *tmB16 = *tmB;
+  }
+  *p = Umma2Params{};
+  p->Q = Q; p->G = G;
+  p->num_m_pairs = static_cast<int>((Q + PM - 1) / PM);
+  p->num_n_tiles = static_cast<int>((G + BN - 1) / BN);
+  p->num_kb = static_cast<int>(Dp / BK);
+  p->a_plane_rows = static_cast<int32_t>(q_rows_pad);
+  p->b_plane_rows = static_cast<int32_t>(g_rows_pad);
+  p->b_row0 = static_cast<int32_t>(g_row0);
+  p->metric = metric; p->qsq = qsq; p->gsq = gsq;
+  if (static_cast<int64_t>(p->num_m_pairs) * p->num_n_tiles > INT32_MAX)
+    return set_err(ctx, DALI_ERR_UNSUPPORTED, "too many tiles (chunk the queries)");
+  return DALI_OK;
+}
+
+}  // namespace
+
+// q32/g32: [npl32][rows_pad][Dp] fp32 planes (plane 0 = TF32-rounded operand, plane 1 = residual,
+// TF32X3 only); q16/g16: [2][rows_pad][Dp] bf16 planes (hi16, lo16; TF32C only).
+// rows_pad multiples of 256, Dp multiple of 32.  mode: DALI_PREC_TF32 / TF32X3 / TF32C.
+// DALI_UMMA_2CTA=0 selects the one-CTA-per-tile kernel of distmat_umma.cu (cross-check).
+int launch_distmat_umma(dali_ctx *ctx, const float *q32, const float *g32, const void *q16,
+                        const void *g16, int64_t Q, int64_t G, int64_t Dp, int64_t q_rows_pad,
+                        int64_t g_rows_pad, int64_t g_row0, int precision, int metric,
+                        const float *qsq, const float *gsq, float *out, int64_t ld) {
+  if (Q == 0 || G == 0) return DALI_OK;
+  static const char *env = getenv("DALI_UMMA_2CTA");
+  if (env && atoi(env) == 0)
+    return launch_distmat_umma1(ctx, q32, g32, q16, g16, Q, G, Dp, q_rows_pad, g_rows_pad, g_row0,
+                                precision, metric, qsq, gsq, out, ld);
+  CUtensorMap tmA, tmB, tmA16, tmB16;
+  Umma2Params p;
+  int rc = setup(ctx, q32, g32, q16, g16, Q, G, Dp, q_rows_pad, g_rows_pad, g_row0, precision, metric,
+                 qsq, gsq, &tmA, &tmB, &tmA16, &tmB16, &p);
+  if (rc) return rc;
+  p.out = out; p.ld = ld;
+  return launch_prec<kStore>(ctx, precision, tmA, tmB, tmA16, tmB16, p);
+}
+
+// Fused distance + top-k candidate filter: columns [0, G) of the slab starting at gallery row
+// g_row0 are compared with thr[Q]; survivors are appended to cand[Q][cap] (cand_cnt[Q] counts
+// every survivor, also those beyond cap: the caller detects overflow).  direct != 0 requires
+// G <= cap and writes column j to slot j without counting.
+int launch_distmat_filter_umma(dali_ctx *ctx, const float *q32, const float *g32, const void *q16,
+                               const void *g16, int64_t Q, int64_t G, int64_t Dp,
+                               int64_t q_rows_pad, int64_t g_rows_pad, int64_t g_row0,
+                               int precision, int metric, const float *qsq, const float *gsq,
+                               const float *thr, int32_t *cand_cnt, uint64_t *cand, int cap,
+                               int largest, int direct, int32_t id_base) {
+  if (Q == 0 || G == 0) return DALI_OK;
+  if (direct && G > cap) return set_err(ctx, DALI_ERR_INVALID, "direct filter chunk wider than cap");
+  CUtensorMap tmA, tmB, tmA16, tmB16;
+  Umma2Params p;
+  int rc = setup(ctx, q32, g32, q16, g16, Q, G, Dp, q_rows_pad, g_rows_pad, g_row0, precision, metric,
+                 qsq, gsq, &tmA, &tmB, &tmA16, &tmB16, &p);
+  if (rc) return rc;
+  p.thr = thr; p.cand_cnt = cand_cnt; p.cand = cand; p.cap = cap;
+  p.largest = largest; p.direct = direct; p.id_base = id_base;
+  static const char *dbg = getenv("DALI_DEBUG_EPI");
+  p.debug = dbg ? atoi(dbg) : 0;
+  return launch_prec<kFilter>(ctx, precision, tmA, tmB, tmA16, tmB16, p);
+}
+
+}  // namespace dali

@@ -32,7 +32,7 @@ __device__ void bitonic_sort(uint64_t *cand, int n) {
   for (int size = 2; size <= n; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       __syncthreads();
-      for (int i = threadIdx.x; i < (n >> 1); i += kTopkThreads) {
+      for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
         const int pos = 2 * i - (i & (stride - 1));
         const bool asc = (pos & size) == 0;
         const uint64_t a = cand[pos], b = cand[pos + stride];
@@ -143,7 +143,65 @@ topk_kernel(const float *__restrict__ dist, int64_t G, int64_t ld, int k, int la
   }
 }
 
+// Fused top-k (distmat_umma2.cu, kFilter epilogue): after every gallery chunk the row's candidate
+// list [kept best so far | survivors of the chunk] is sorted, cut back to the k best, and the
+// row's threshold becomes its k-th best distance.  cnt[row] > cap means the chunk produced more
+// survivors than the list holds: the overflow flag tells the host to redo the call unfused.
+constexpr int kCompactThreads = 128;
+constexpr int kCompactCap = 1024;
+
+__global__ void __launch_bounds__(kCompactThreads)
+topk_compact_kernel(uint64_t *__restrict__ cand, int32_t *__restrict__ cnt, float *__restrict__ thr,
+                    int cap, int k, int largest, int fixed_cnt, int32_t *__restrict__ overflow,
+                    float *__restrict__ d_out, int32_t *__restrict__ i_out) {
+  __shared__ uint64_t s[kCompactCap];
+  const int64_t q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const uint32_t flip = largest ? 0xFFFFFFFFu : 0u;
+  int n = fixed_cnt >= 0 ? fixed_cnt : cnt[q];
+  if (n > cap) {
+    if (tid == 0) atomicOr(overflow, 1);
+    n = cap;
+  }
+  uint64_t *list = cand + q * cap;
+  const int np2 = next_pow2(n);
+  for (int i = tid; i < np2; i += kCompactThreads) s[i] = i < n ? list[i] : ~0ull;
+  bitonic_sort(s, np2);
+  const int m = n < k ? n : k;
+  for (int i = tid; i < m; i += kCompactThreads) list[i] = s[i];
+  if (tid == 0) {
+    cnt[q] = m;
+    thr[q] = n >= k ? key_to_dist(static_cast<uint32_t>(s[k - 1] >> 32) ^ flip)
+                    : (largest ? -INFINITY : INFINITY);
+  }
+  if (d_out) {
+    for (int i = tid; i < k; i += kCompactThreads) {
+      float dv = largest ? -INFINITY : INFINITY;
+      int32_t iv = -1;
+      if (i < m) {
+        dv = key_to_dist(static_cast<uint32_t>(s[i] >> 32) ^ flip);
+        iv = static_cast<int32_t>(static_cast<uint32_t>(s[i]));
+      }
+      d_out[q * k + i] = dv;
+      i_out[q * k + i] = iv;
+    }
+  }
+}
+
 }  // namespace
+
+int launch_topk_compact(dali_ctx *ctx, uint64_t *cand, int32_t *cand_cnt, float *thr, int64_t Q,
+                        int cap, int k, int largest, int fixed_cnt, int32_t *overflow, float *d_out,
+                        int32_t *i_out) {
+  if (Q == 0) return DALI_OK;
+  if (cap > kCompactCap || k > cap)
+    return set_err(ctx, DALI_ERR_INVALID, "top-k compaction: cap <= 1024 and k <= cap");
+  KTimer t(ctx, DALI_K_TOPK);
+  topk_compact_kernel<<<static_cast<unsigned>(Q), kCompactThreads, 0, ctx->stream>>>(
+      cand, cand_cnt, thr, cap, k, largest, fixed_cnt, overflow, d_out, i_out);
+  DALI_CUDA_OK(ctx, cudaGetLastError());
+  return DALI_OK;
+}
 
 int launch_topk(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t ld, int k,
                 int largest, const int32_t *col_ids, int32_t id_base, float *d_out,

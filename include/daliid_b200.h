@@ -96,6 +96,9 @@ int dali_ctx_timing_reset(dali_ctx *ctx);
 int dali_ctx_timing_read(dali_ctx *ctx, int which, int *launches, float *total_ms);
 /* Number of this library's kernel launches issued by the context since creation. */
 int64_t dali_ctx_launch_count(dali_ctx *ctx);
+/* Number of fused calls (dali_topk_features_f32) that overflowed their candidate lists and were
+ * redone through the materialised distance matrix (same result, slower). */
+int64_t dali_ctx_fallback_count(dali_ctx *ctx);
 
 /* ---- a1: row L2 normalisation -------------------------------------------- */
 /* out[i,:] = x[i,:] / ||x[i,:]||  (no eps: a zero row yields NaN, as the reference does)

@@ -54,9 +54,14 @@ def main():
         qf = torch.randn(Q, D, generator=g, device="cuda")
         gf = torch.randn(G, D, generator=g, device="cuda")
         for prec in ("tf32c", "tf32"):
+            ctx.timing_enable(True); ctx.timing_reset()
+            n_fb = ctx.fallback_count()
             ms, (v, i) = timeit(lambda: metrics.topk_features(qf, gf, k=20, precision=prec), n=2, warm=1)
+            kt = {k: (v[0], round(v[1], 3)) for k, v in ctx.timing_read().items() if v[0]}
+            ctx.timing_enable(False)
             print(f"faceid {Q}x{G} D={D} {prec}: {ms:.1f} ms, {Q * G / ms / 1e6:.2f} Gpairs/s, "
-                  f"{2 * Q * G * D / ms / 1e9:.0f} TFLOP/s", flush=True)
+                  f"{2 * Q * G * D / ms / 1e9:.0f} TFLOP/s, fallbacks {ctx.fallback_count() - n_fb}, "
+                  f"kernels (launches, total ms): {kt}", flush=True)
 
 
 if __name__ == "__main__":

@@ -193,3 +193,73 @@ def test_topk_features_fused():
     v, i = metrics.topk_features(qf, gf, k=20, precision="tf32x3", g_base=1000)
     ev, ei = metrics.topk_identify(d, k=20)
     assert torch.equal(v, ev) and torch.equal(i, ei + 1000)
+
+
+@pytest.mark.parametrize("precision", ["tf32c", "tf32x3", "tf32"])
+@pytest.mark.parametrize("metric,largest", [("cosine", False), ("sqeuclidean", False), ("dot", True)])
+def test_topk_features_fused_multi_chunk(precision, metric, largest):
+    """Fused distance + top-k (several gallery chunks, ragged last tile) equals top-k of the
+    materialised matrix of the same precision: same kernel arithmetic, so bit-identical."""
+    from daliid_b200 import metrics
+    g = torch.Generator().manual_seed(12)
+    Q, G, D = 300, 7777, 96
+    qf = torch.randn(Q, D, generator=g).cuda()
+    gf = torch.randn(G, D, generator=g).cuda()
+    gf[100] = gf[5000]                      # exact duplicates: ties broken by gallery index
+    gf[7000] = gf[5000]
+    d = metrics.compute_distance_matrix(qf, gf, metric, precision)
+    from daliid_b200 import _lib
+    n_fb = _lib.get_ctx(0).fallback_count()
+    for k in (1, 20, 128):
+        v, i = metrics.topk_features(qf, gf, k=k, metric=metric, precision=precision,
+                                     largest=largest, g_base=7)
+        ev, ei = metrics.topk_identify(d, k=k, largest=largest)
+        assert torch.equal(i, ei + 7), (precision, metric, k)
+        assert torch.equal(v, ev)
+    assert _lib.get_ctx(0).fallback_count() == n_fb  # the fused path itself produced these
+
+
+def test_topk_features_fused_overflow_falls_back():
+    """Gallery ordered so that every later item is closer to every query than all earlier ones:
+    each chunk overflows the candidate lists and the call must redo itself unfused."""
+    from daliid_b200 import metrics
+    g = torch.Generator().manual_seed(3)
+    Q, G, D = 64, 6000, 64
+    u = torch.nn.functional.normalize(torch.randn(1, D, generator=g), dim=1)
+    v = torch.nn.functional.normalize(torch.randn(G, D, generator=g), dim=1)
+    v = torch.nn.functional.normalize(v - (v @ u.T) * u, dim=1)
+    theta = torch.linspace(1.5, 0.05, G)[:, None]
+    gf = (torch.cos(theta) * u + torch.sin(theta) * v).cuda()
+    qf = (u + 1e-3 * torch.randn(Q, D, generator=g)).cuda()
+    d = metrics.compute_distance_matrix(qf, gf, "cosine", "tf32c")
+    from daliid_b200 import _lib
+    n_fb = _lib.get_ctx(0).fallback_count()
+    vv, ii = metrics.topk_features(qf, gf, k=20, precision="tf32c")
+    assert _lib.get_ctx(0).fallback_count() == n_fb + 1
+    ev, ei = metrics.topk_identify(d, k=20)
+    assert torch.equal(ii, ei) and torch.equal(vv, ev)
+    assert int(ii.min()) > G - 200          # the best items really are the last ones
+
+
+def test_two_cta_kernel_equals_one_cta_kernel():
+    """The CTA-pair contraction and the one-CTA-per-tile kernel accumulate every element in
+    the same k order: bit-identical matrices (run in a subprocess with DALI_UMMA_2CTA=0)."""
+    import subprocess
+    import sys
+    code = (
+        "import torch, sys, numpy as np\n"
+        "from daliid_b200 import metrics, synth\n"
+        "qf, gf, *_ = synth.make_config('small', device='cuda')\n"
+        "for p in ('tf32', 'tf32x3', 'tf32c'):\n"
+        "    d = metrics.compute_distance_matrix(qf, gf, 'cosine', p)\n"
+        "    np.save(sys.argv[1] + p + '.npy', d.cpu().numpy())\n")
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        for flag in ("0", "1"):
+            env = dict(os.environ, DALI_UMMA_2CTA=flag)
+            subprocess.check_call([sys.executable, "-c", code, os.path.join(td, flag + "_")], env=env,
+                                  cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        for p in ("tf32", "tf32x3", "tf32c"):
+            a = np.load(os.path.join(td, "0_" + p + ".npy"))
+            b = np.load(os.path.join(td, "1_" + p + ".npy"))
+            assert np.array_equal(a, b), p
