@@ -316,11 +316,12 @@ def run_ours(args):
     achieved = flops_per_launch / (ms_dm / max(n_dm, 1) * 1e-3) / 1e12 if n_dm else None
     n_rc, ms_rc = ktimes["rank_count"]
     rank_gbs = (4.0 * Q * G) / (ms_rc / max(n_rc, 1) * 1e-3) / 1e9 if n_rc else None
-    roofline = {"bound": "tensor", "kernel": "distmat_umma_kernel" if prec != "fp32" else "distmat_simt_kernel",
+    roofline = {"bound": "tensor", "kernel": "distmat_umma2_kernel" if prec != "fp32" else "distmat_simt_kernel",
                 "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
                 "frac": (achieved / pk["bf16"]) if achieved else None, "traffic": None,
-                "peak_source": pk["source"] + " bf16 burst; TF32 MMAs run at half the bf16 rate: "
-                               "ceiling 1/2 for tf32, 1/4 for tf32c (1 TF32 + 2 bf16 passes), 1/6 for tf32x3",
+                "peak_source": pk["source"] + " bf16 burst; the fp32-class splits issue several tensor "
+                               "passes per algorithmic FLOP: ceiling of frac = 1/3 for f16x3 (three 16-bit "
+                               "passes), 1/2 for tf32, 1/4 for tf32c (1 TF32 + 2 bf16 passes), 1/6 for tf32x3",
                 "avg_launch_ms": ms_dm / max(n_dm, 1) if n_dm else None}
     roofline_rank = {"bound": "hbm", "kernel": "rank_count_kernel", "achieved": rank_gbs,
                      "peak": pk["hbm"], "unit": "GB/s", "frac": (rank_gbs / pk["hbm"]) if rank_gbs else None,
@@ -369,7 +370,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="tf32c", choices=["fp32", "tf32x3", "tf32c", "tf32"])
+    ap.add_argument("--precision", default="f16x3", choices=["fp32", "tf32x3", "tf32c", "tf32", "f16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="diagnostic per-phase host timing (stderr)")
     args = ap.parse_args()

@@ -295,10 +295,13 @@ static int alloc_operand(dali_ctx *ctx, int ws_planes, int ws_p16, int ws_sq, in
   out->rows_pad = round_up(std::max<int64_t>(n, 1), 256);
   out->npl = precision == DALI_PREC_TF32X3 ? 2 : 1;
   void *pl = nullptr;
-  int rc = ws_ensure(ctx, ws_planes, sizeof(float) * out->npl * out->rows_pad * out->Dp, &pl);
-  if (rc) return rc;
+  int rc = DALI_OK;
+  if (precision != DALI_PREC_F16X3) {  // F16X3 reads only the two 16-bit planes
+    rc = ws_ensure(ctx, ws_planes, sizeof(float) * out->npl * out->rows_pad * out->Dp, &pl);
+    if (rc) return rc;
+  }
   out->planes = static_cast<float *>(pl);
-  if (precision == DALI_PREC_TF32C) {
+  if (precision == DALI_PREC_TF32C || precision == DALI_PREC_F16X3) {
     void *t = nullptr;
     rc = ws_ensure(ctx, ws_p16, 2 * 2 * out->rows_pad * out->Dp, &t);
     if (rc) return rc;
@@ -319,9 +322,10 @@ static int prep_rows(dali_ctx *ctx, const Prepared &o, const float *xd, int64_t 
                      int64_t r0, int64_t n_valid, int64_t r1, int precision, int normalize) {
   char *p16 = static_cast<char *>(o.planes16);
   const int64_t off = r0 * o.Dp;
-  return launch_prep(ctx, xd, n_valid, D, ldx, o.planes + off,
+  return launch_prep(ctx, xd, n_valid, D, ldx, o.planes ? o.planes + off : nullptr,
                      o.npl == 2 ? o.planes + o.rows_pad * o.Dp + off : nullptr, o.Dp, o.Dp, r1 - r0,
-                     normalize, precision == DALI_PREC_FP32 ? 0 : 1, nullptr,
+                     normalize, precision == DALI_PREC_FP32 ? 0 : precision == DALI_PREC_F16X3 ? 2 : 1,
+                     nullptr,
                      o.sq ? o.sq + r0 : nullptr, p16 ? p16 + 2 * off : nullptr,
                      p16 ? p16 + 2 * (o.rows_pad * o.Dp + off) : nullptr);
 }
@@ -349,11 +353,14 @@ static int contract(dali_ctx *ctx, const Prepared &a, const Prepared &b, int64_t
                              b.rows_pad, g_row0, precision, metric, a.sq, gsq, out, ld);
 }
 
-static int check_metric_prec(dali_ctx *ctx, int metric, int precision) {
+static int check_metric_prec(dali_ctx *ctx, int metric, int precision, int normalize) {
   if (metric < DALI_METRIC_COSINE || metric > DALI_METRIC_DOT)
     return set_err(ctx, DALI_ERR_INVALID, "unknown metric");
-  if (precision < DALI_PREC_FP32 || precision > DALI_PREC_TF32C)
+  if (precision < DALI_PREC_FP32 || precision > DALI_PREC_F16X3)
     return set_err(ctx, DALI_ERR_INVALID, "unknown precision");
+  if (precision == DALI_PREC_F16X3 && !normalize)
+    return set_err(ctx, DALI_ERR_UNSUPPORTED,
+                   "DALI_PREC_F16X3 needs unit rows (normalize != 0); use DALI_PREC_TF32C");
   return DALI_OK;
 }
 
@@ -602,7 +609,7 @@ int dali_distmat_f32(dali_ctx *ctx, const float *q, int64_t Q, const float *g, i
   if (rc) return rc;
   if (Q < 0 || G < 0 || D <= 0 || ld < G || !out || (!q && Q) || (!g && G))
     return set_err(ctx, DALI_ERR_INVALID, "distmat: bad shape or null pointer");
-  rc = check_metric_prec(ctx, metric, precision);
+  rc = check_metric_prec(ctx, metric, precision, normalize);
   if (rc) return rc;
   if (Q == 0 || G == 0) return DALI_OK;
   const bool out_dev = is_device_ptr(out);
@@ -924,7 +931,7 @@ int dali_eval_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float
   if (Q < 0 || G < 0 || D <= 0 || (!q && Q) || (!g && G) || !cmc || !mAP || max_rank < 1 ||
       (distmat_opt && ld_opt < G))
     return set_err(ctx, DALI_ERR_INVALID, "eval_features: bad shape or null pointer");
-  rc = check_metric_prec(ctx, metric, precision);
+  rc = check_metric_prec(ctx, metric, precision, normalize);
   if (rc) return rc;
   if (metric == DALI_METRIC_DOT)
     return set_err(ctx, DALI_ERR_INVALID, "eval_features ranks distances; DOT is a similarity");
@@ -1115,7 +1122,7 @@ int dali_topk_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float
   if (rc) return rc;
   if (Q < 0 || G < 0 || D <= 0 || (!q && Q) || (!g && G) || !d_out || !i_out || k < 1 || k > 128)
     return set_err(ctx, DALI_ERR_INVALID, "topk_features: bad arguments");
-  rc = check_metric_prec(ctx, metric, precision);
+  rc = check_metric_prec(ctx, metric, precision, normalize);
   if (rc) return rc;
   if (Q == 0) return DALI_OK;
   static const char *env_fused = getenv("DALI_TOPK_FUSED");

@@ -77,11 +77,12 @@ struct Umma2Params {
   int direct;           // 1: every column j is written to slot j of the list (first chunk)
   int32_t id_base;      // gallery id of column 0
   int debug;            // DALI_DEBUG_EPI (profiling experiments only)
+  float acc_scale;      // 2^-24 for kF16x3 (operands carry a factor 2^12 each), else 1
 };
 
 // ---- kFilter epilogue: 32 accumulator columns of one query row -------------------------------
 struct FilterRow {
-  float thr, qs, alpha, beta;
+  float thr, qs, alpha, beta, scale;  // alpha already carries the accumulator scale
   uint32_t flip;
   uint64_t *list;
   int32_t *cnt;
@@ -120,7 +121,7 @@ __device__ __forceinline__ void filter_cols(const uint32_t (&v)[32], const Filte
     if (KIND == 0) {
       d = fmaf(acc, fr.alpha, fr.beta);
     } else {
-      d = fmaf(-2.0f, acc, fr.qs + __ldg(gs + (j < lim ? j : 0)));
+      d = fmaf(-2.0f, acc * fr.scale, fr.qs + __ldg(gs + (j < lim ? j : 0)));
       if (KIND == 2) d = sqrtf(fmaxf(d, 1e-30f));
     }
     return d;
@@ -184,9 +185,11 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int num_tiles = p.num_m_pairs * p.num_n_tiles;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    if (MODE == kTf32c) {
+    if (MODE != kF16x3) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (MODE == kTf32c || MODE == kF16x3) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA16) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB16) : "memory");
     }
@@ -224,6 +227,19 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int arow = m * PM + static_cast<int>(rank) * UM;
         const int brow = p.b_row0 + n * BN + static_cast<int>(rank) * HB;
         for (int kb = 0; kb < p.num_kb; ++kb) {
+          if (MODE == kF16x3) {  // one slot: fp16 hi and residual planes of both operands
+            mbar_wait(empty_bar(slot), phase ^ 1u);
+            if (rank == 0) mbar_expect_tx(full_bar(slot), 2 * kSlotBytes);
+            const uint32_t fbh = full0 + 8u * slot;
+            const uint32_t sb = slot_addr(slot);
+            tma_load_2d_pair(sb, &tmA16, fbh, kb * BK, arow);
+            tma_load_2d_pair(sb + A16_BYTES, &tmA16, fbh, kb * BK, p.a_plane_rows + arow);
+            tma_load_2d_pair(sb + 2 * A16_BYTES, &tmB16, fbh, kb * BK, brow);
+            tma_load_2d_pair(sb + 2 * A16_BYTES + B16_BYTES, &tmB16, fbh, kb * BK,
+                             p.b_plane_rows + brow);
+            advance();
+            continue;
+          }
           mbar_wait(empty_bar(slot), phase ^ 1u);
           if (rank == 0) mbar_expect_tx(full_bar(slot), 2 * kSlotBytes);
           const uint32_t fb = full0 + 8u * slot;
@@ -271,7 +287,22 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           mbar_wait(full_bar(slot), phase);
           tc_fence_after();
           const uint32_t a0 = slot_addr(slot), b0 = a0 + A_BYTES;
-          if (MODE == kTf32 || MODE == kTf32c) {
+          if (MODE == kF16x3) {
+            constexpr uint32_t kIdH = idesc_f16(PM);
+            const uint32_t ahi = a0, alo = ahi + A16_BYTES;
+            const uint32_t bhi = ahi + 2 * A16_BYTES, blo = bhi + B16_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {  // 32 bytes of K per fp16 MMA inside the 64 B atom
+              tc_mma_bf16<2>(tmem_d, make_desc_sw64(alo + k * 32), make_desc_sw64(bhi + k * 32),
+                             kIdH, (kb | k) ? 1u : 0u);                            // lo * hi
+              tc_mma_bf16<2>(tmem_d, make_desc_sw64(ahi + k * 32), make_desc_sw64(blo + k * 32),
+                             kIdH, 1u);                                             // hi * lo
+              tc_mma_bf16<2>(tmem_d, make_desc_sw64(ahi + k * 32), make_desc_sw64(bhi + k * 32),
+                             kIdH, 1u);                                             // hi * hi
+            }
+            tc_commit_pair(empty_bar(slot), 3);
+            advance();
+          } else if (MODE == kTf32 || MODE == kTf32c) {
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k)  // 32 bytes of K per tf32 MMA inside the 128 B atom
               tc_mma_tf32<2>(tmem_d, make_desc_sw128(a0 + k * 32), make_desc_sw128(b0 + k * 32),
@@ -336,6 +367,7 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll 1
           for (int c = 0; c < BN / 32; ++c) {
             if (colt + c * 32 >= p.G) break;
+            if (p.debug & 1) break;
             uint32_t v[32];
             tc_ld_32x32(tbase + c * 32, v);
             tc_wait_ld();
@@ -350,7 +382,8 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               const int64_t r = row0 + rr;
               if (r < p.Q && col_ok) {
                 const float qs = p.qsq ? __ldg(p.qsq + r) : 0.f;
-                p.out[r * p.ld + col] = metric_epilogue(stg[rr * EPI_LD + lane], p.metric, qs, gs);
+                p.out[r * p.ld + col] =
+                    metric_epilogue(stg[rr * EPI_LD + lane] * p.acc_scale, p.metric, qs, gs);
               }
             }
             __syncwarp();
@@ -364,7 +397,8 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           fr.row_ok = r < p.Q;
           fr.thr = fr.row_ok ? __ldg(p.thr + r) : 0.f;
           fr.qs = (p.qsq && fr.row_ok) ? __ldg(p.qsq + r) : 0.f;
-          fr.alpha = p.metric == DALI_METRIC_COSINE ? -1.0f : 1.0f;
+          fr.scale = p.acc_scale;
+          fr.alpha = (p.metric == DALI_METRIC_COSINE ? -1.0f : 1.0f) * p.acc_scale;
           fr.beta = p.metric == DALI_METRIC_COSINE ? 1.0f : 0.0f;
           fr.flip = p.largest ? 0xFFFFFFFFu : 0u;
           fr.list = p.cand + (fr.row_ok ? r : 0) * p.cap;
@@ -452,6 +486,7 @@ int launch_prec(dali_ctx *ctx, int precision, const CUtensorMap &tmA, const CUte
     case DALI_PREC_TF32: return launch_t<kTf32, EPI>(ctx, tmA, tmB, tmA16, tmB16, p);
     case DALI_PREC_TF32X3: return launch_t<kTf32x3, EPI>(ctx, tmA, tmB, tmA16, tmB16, p);
     case DALI_PREC_TF32C: return launch_t<kTf32c, EPI>(ctx, tmA, tmB, tmA16, tmB16, p);
+    case DALI_PREC_F16X3: return launch_t<kF16x3, EPI>(ctx, tmA, tmB, tmA16, tmB16, p);
     default: return set_err(ctx, DALI_ERR_INVALID, "not a tensor-core precision");
   }
 }
@@ -465,15 +500,23 @@ int setup(dali_ctx *ctx, const float *q32, const float *g32, const void *q16, co
     return set_err(ctx, DALI_ERR_INVALID, "umma operands must be padded (rows 256, D 32)");
   if (q_rows_pad * 2 > INT32_MAX || g_rows_pad * 2 > INT32_MAX)
     return set_err(ctx, DALI_ERR_UNSUPPORTED, "operand too tall for one tensor map");
-  int rc = make_map(ctx, tmA, q32, q_rows_pad * npl32, Dp, UM, false);
-  if (rc) return rc;
-  rc = make_map(ctx, tmB, g32, g_rows_pad * npl32, Dp, HB, false);
-  if (rc) return rc;
-  if (precision == DALI_PREC_TF32C) {
-    rc = make_map(ctx, tmA16, q16, q_rows_pad * 2, Dp, UM, true);
+  const bool f16 = precision == DALI_PREC_F16X3;
+  int rc = DALI_OK;
+  if (!f16) {
+    rc = make_map(ctx, tmA, q32, q_rows_pad * npl32, Dp, UM, false);
     if (rc) return rc;
-    rc = make_map(ctx, tmB16, g16, g_rows_pad * 2, Dp, HB, true);
+    rc = make_map(ctx, tmB, g32, g_rows_pad * npl32, Dp, HB, false);
     if (rc) return rc;
+  }
+  if (precision == DALI_PREC_TF32C || f16) {
+    rc = make_map(ctx, tmA16, q16, q_rows_pad * 2, Dp, UM, true, f16);
+    if (rc) return rc;
+    rc = make_map(ctx, tmB16, g16, g_rows_pad * 2, Dp, HB, true, f16);
+    if (rc) return rc;
+    if (f16) {
+      *tmA = *tmA16;
+      *tmB = *tmB16;
+    }
   } else {
     *tmA16 = *tmA;
     *tmB16 = *tmB;
@@ -487,6 +530,7 @@ int setup(dali_ctx *ctx, const float *q32, const float *g32, const void *q16, co
   p->b_plane_rows = static_cast<int32_t>(g_rows_pad);
   p->b_row0 = static_cast<int32_t>(g_row0);
   p->metric = metric; p->qsq = qsq; p->gsq = gsq;
+  p->acc_scale = f16 ? 5.9604644775390625e-08f /* 2^-24 */ : 1.0f;
   if (static_cast<int64_t>(p->num_m_pairs) * p->num_n_tiles > INT32_MAX)
     return set_err(ctx, DALI_ERR_UNSUPPORTED, "too many tiles (chunk the queries)");
   return DALI_OK;
@@ -504,7 +548,7 @@ int launch_distmat_umma(dali_ctx *ctx, const float *q32, const float *g32, const
                         const float *qsq, const float *gsq, float *out, int64_t ld) {
   if (Q == 0 || G == 0) return DALI_OK;
   static const char *env = getenv("DALI_UMMA_2CTA");
-  if (env && atoi(env) == 0)
+  if (env && atoi(env) == 0 && precision != DALI_PREC_F16X3)
     return launch_distmat_umma1(ctx, q32, g32, q16, g16, Q, G, Dp, q_rows_pad, g_rows_pad, g_row0,
                                 precision, metric, qsq, gsq, out, ld);
   CUtensorMap tmA, tmB, tmA16, tmB16;
@@ -513,6 +557,8 @@ int launch_distmat_umma(dali_ctx *ctx, const float *q32, const float *g32, const
                  qsq, gsq, &tmA, &tmB, &tmA16, &tmB16, &p);
   if (rc) return rc;
   p.out = out; p.ld = ld;
+  static const char *dbg = getenv("DALI_DEBUG_EPI");
+  p.debug = dbg ? atoi(dbg) : 0;
   return launch_prec<kStore>(ctx, precision, tmA, tmB, tmA16, tmB16, p);
 }
 

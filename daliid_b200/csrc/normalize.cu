@@ -7,6 +7,7 @@
 //   evaluate_ensembled_models.py:278-279,297-298, evaluateCleanATModels.py:106-107,115-119,252-254
 // No eps, as in the reference: a zero row divides 0/0 and becomes NaN.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -42,7 +43,7 @@ struct PrepParams {
   float *plane1;  // nullable: residual plane
   int64_t ldo, d_pad, rows_pad;
   int do_normalize;
-  int round_mode;  // 0 keep fp32, 1 round plane0 to tf32
+  int round_mode;  // 0 keep fp32, 1 round plane0 to tf32, 2 fp16 hi/residual of 2^12 * x (no fp32 plane)
   float *norms;    // nullable: ||x|| of the input row
   float *sq;       // nullable: sum of squares of the OUTPUT row (fp32 values before tf32 rounding)
   __nv_bfloat16 *hi16;  // nullable: bf16 copy of plane0 (TF32C correction operand)
@@ -52,13 +53,13 @@ struct PrepParams {
 __global__ void __launch_bounds__(kPrepThreads) prep_rows_kernel(PrepParams p) {
   __shared__ float s_red[kPrepThreads / 32];
   const int64_t r = blockIdx.x;
-  float *o0 = p.plane0 + r * p.ldo;
+  float *o0 = p.plane0 ? p.plane0 + r * p.ldo : nullptr;
   float *o1 = p.plane1 ? p.plane1 + r * p.ldo : nullptr;
   __nv_bfloat16 *h16 = p.hi16 ? p.hi16 + r * p.ldo : nullptr;
   __nv_bfloat16 *l16 = p.lo16 ? p.lo16 + r * p.ldo : nullptr;
   if (r >= p.n) {  // padding rows: zeros
     for (int64_t c = threadIdx.x; c < p.d_pad; c += kPrepThreads) {
-      o0[c] = 0.f;
+      if (o0) o0[c] = 0.f;
       if (o1) o1[c] = 0.f;
       if (h16) { h16[c] = __float2bfloat16_rn(0.f); l16[c] = __float2bfloat16_rn(0.f); }
     }
@@ -83,7 +84,14 @@ __global__ void __launch_bounds__(kPrepThreads) prep_rows_kernel(PrepParams p) {
       if (p.do_normalize) v = v / nrm;  // IEEE division, like the reference's x / norm
     }
     acc2 = fmaf(v, v, acc2);
-    if (p.round_mode) {
+    if (p.round_mode == 2) {
+      // unit rows: |v| <= 1, so 4096 v fits fp16 (max 65504) and a typical 1/sqrt(D) entry and
+      // its residual stay in the normal range; the contraction's epilogue multiplies by 2^-24
+      const float sv = v * 4096.0f;
+      const __half hi = __float2half_rn(sv);
+      reinterpret_cast<__half *>(h16)[c] = hi;
+      reinterpret_cast<__half *>(l16)[c] = __float2half_rn(sv - __half2float(hi));
+    } else if (p.round_mode) {
       const float hi = round_tf32(v);
       o0[c] = hi;
       if (o1) o1[c] = round_tf32(v - hi);

@@ -16,7 +16,7 @@ constexpr int EPI_LD = 33;
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
 constexpr uint64_t kWatchdogCycles = 4000000000ull;  // ~2 s: trap instead of hanging the box
 
-enum Mode { kTf32 = 0, kTf32x3 = 1, kTf32c = 2 };
+enum Mode { kTf32 = 0, kTf32x3 = 1, kTf32c = 2, kF16x3 = 3 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -206,13 +206,17 @@ __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
 }
 
 // cute::UMMA::InstrDescriptor: fp32 accumulate (bit 4), A/B format [7,10)/[10,13)
-// (2 = TF32, 1 = BF16), both K-major, N>>3 at [17,23), M>>4 at [24,29).  M is the whole
+// (2 = TF32, 1 = BF16, 0 = F16), both K-major, N>>3 at [17,23), M>>4 at [24,29).  M is the whole
 // instruction's M: 128 for cta_group::1, 256 for a CTA pair.
 __host__ __device__ constexpr uint32_t idesc_tf32(int m) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(m >> 4) << 24);
 }
 __host__ __device__ constexpr uint32_t idesc_bf16(int m) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(m >> 4) << 24);
+}
+
+__host__ __device__ constexpr uint32_t idesc_f16(int m) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(m >> 4) << 24);
 }
 
 __device__ __forceinline__ float metric_epilogue(float acc, int metric, float qs, float gs) {
@@ -232,7 +236,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 // 2-D K-major operand map: dims {Dp, rows}, box {BK, box_rows}; fp32 tiles use the 128-byte
 // swizzle (BK * 4 = 128 B), bf16 tiles the 64-byte swizzle (BK * 2 = 64 B).
 inline int make_map(dali_ctx *ctx, CUtensorMap *map, const void *base, int64_t rows, int64_t Dp,
-                    int box_rows, bool bf16) {
+                    int box_rows, bool bf16, bool fp16 = false) {
   if (!ctx->encode_tiled) {
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -247,7 +251,7 @@ inline int make_map(dali_ctx *ctx, CUtensorMap *map, const void *base, int64_t r
   cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
-      map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+      map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
       const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
       bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

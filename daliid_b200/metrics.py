@@ -44,7 +44,16 @@ __all__ = [
     "evaluate_features",
 ]
 
-DEFAULT_PRECISION = "tf32c"  # fp32-class result on the tensor pipe (TF32 + bf16 corrections)
+DEFAULT_PRECISION = "auto"  # fp32-class result on the tensor pipe, see _precision()
+
+
+def _precision(precision, normalize):
+    """"auto" = the fastest fp32-class tensor-core arithmetic the operands allow: the fp16 hi/lo
+    split (f16x3) for unit rows -- the reference's live cosine path -- and TF32 + bf16
+    corrections (tf32c) for un-normalised features."""
+    if precision == "auto":
+        precision = "f16x3" if normalize else "tf32c"
+    return _enum(PRECISIONS, precision, "precision")
 
 
 def canonicalize_labels(q, g):
@@ -195,7 +204,7 @@ def compute_distance_matrix(input1, input2, metric="cosine", precision=DEFAULT_P
     ctx.attach_torch_stream()
     if Q and G:
         ctx.check(ctx.lib.dali_distmat_f32(ctx.h, c_vp(a.ptr), Q, c_vp(b.ptr), G, D, m,
-                                           _enum(PRECISIONS, precision, "precision"),
+                                           _precision(precision, normalize),
                                            1 if normalize else 0, c_vp(optr), max(ld, 1)))
     return out
 
@@ -286,7 +295,7 @@ def topk_features(qf, gf, k=20, metric="cosine", precision=DEFAULT_PRECISION, no
     if Q:
         ctx.check(ctx.lib.dali_topk_features_f32(
             ctx.h, c_vp(a.ptr), Q, c_vp(b.ptr), b.shape[0], a.shape[1], m,
-            _enum(PRECISIONS, precision, "precision"), 1 if normalize else 0, int(k),
+            _precision(precision, normalize), 1 if normalize else 0, int(k),
             1 if largest else 0, int(g_base), c_vp(vptr), c_vp(iptr)))
     return vals, idx
 
@@ -326,7 +335,7 @@ def evaluate_features(qf, gf, q_pids, g_pids, q_camids, g_camids, metric="cosine
         dist, dptr = _alloc_out((Q, G), dev)
     rc = ctx.lib.dali_eval_features_f32(
         ctx.h, c_vp(a.ptr), Q, c_vp(b.ptr), G, D, p_i32(qp), p_i32(gp), p_i32(qc), p_i32(gc), m,
-        _enum(PRECISIONS, precision, "precision"), 1 if normalize else 0, int(max_rank),
+        _precision(precision, normalize), 1 if normalize else 0, int(max_rank),
         _enum(ACCUMS, accum, "accumulation mode"), cmc.ctypes.data_as(_lib.c_f32p),
         ctypes.byref(mAP), ap.ctypes.data_as(_lib.c_f64p), first.ctypes.data_as(_lib.c_i32p),
         ctypes.byref(nvalid), c_vp(dptr), G)

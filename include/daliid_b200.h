@@ -60,6 +60,10 @@ extern "C" {
 #define DALI_PREC_TF32 2   /* tcgen05 kind::tf32, single pass (fast; <= 0.01 pp mAP)         */
 #define DALI_PREC_TF32C 3  /* tcgen05: TF32 hi*hi + two bf16 correction MMAs (fp32 class,
                               error <= 2^-18 per product; 2 instead of 3 tensor passes)      */
+#define DALI_PREC_F16X3 4  /* tcgen05 kind::f16: rows scaled by 2^12 and split into fp16 hi + fp16
+                              residual (22 mantissa bits), hi*hi + hi*lo + lo*hi at the 16-bit
+                              rate (1.5 TF32 passes, half the operand bytes; fp32 class, error
+                              <= 2^-20 per product).  Needs unit rows: normalize != 0.        */
 
 /* accumulation semantics of the CMC/AP reduction */
 #define DALI_ACCUM_CY_F32 0 /* torchreid Cython path: C float, sequential in rank order */

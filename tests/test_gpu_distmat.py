@@ -70,7 +70,7 @@ def test_golden_distances(metric, precision):
 
 @pytest.mark.parametrize("Q,G,D", [(1, 1, 1), (5, 3, 7), (130, 257, 33), (128, 256, 32),
                                    (300, 1000, 768), (129, 513, 2048), (257, 300, 3840)])
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "tf32c"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "tf32c", "f16x3"])
 def test_random_shapes_cosine(Q, G, D, precision):
     from daliid_b200 import metrics
     g = torch.Generator().manual_seed(Q * 7 + G)
@@ -79,6 +79,46 @@ def test_random_shapes_cosine(Q, G, D, precision):
     ref = do.cosine_distmat(qf, gf).numpy()
     out = metrics.compute_distance_matrix(qf.cuda(), gf.cuda(), "cosine", precision)
     _close(out, ref)
+
+
+def test_f16x3_golden_and_stress():
+    """fp16 hi/lo split (rows scaled by 2^12): golden cosine matrix, unit-row squared Euclidean,
+    badly scaled rows (1e-6 .. 1e6, one dominant coordinate, many tiny ones), and the refusal of
+    un-normalised operands."""
+    from daliid_b200 import metrics, _lib
+    z = np.load(os.path.join(GOLDEN, "tiny.npz"))
+    out = metrics.compute_distance_matrix(z["qf"], z["gf"], "cosine", "f16x3")
+    _close(out, z["cosine"])
+    qn = torch.from_numpy(z["qn"])
+    gn = torch.from_numpy(z["gf"])
+    gn = gn / torch.norm(gn, dim=1, keepdim=True)
+    ref = (qn ** 2).sum(1)[:, None] + (gn ** 2).sum(1)[None, :] - 2.0 * qn @ gn.T
+    out = metrics.compute_distance_matrix(z["qf"], z["gf"], "sqeuclidean", "f16x3", normalize=True)
+    _close(out, ref.numpy())
+    g = torch.Generator().manual_seed(5)
+    qf = torch.randn(257, 2048, generator=g)
+    gf = torch.randn(700, 2048, generator=g)
+    qf[:64] *= 1e6
+    qf[64:128] *= 1e-6
+    gf[:100] *= 3e5
+    gf[100:200, 0] = 50.0          # one dominant coordinate, the rest ~1/50 of it
+    gf[200:300] *= torch.logspace(-6, 0, 2048)[None, :]   # six decades inside a row
+    ref = do.cosine_distmat(qf, gf).numpy()
+    out = metrics.compute_distance_matrix(qf.cuda(), gf.cuda(), "cosine", "f16x3")
+    _close(out, ref)
+    # Exact duplicates (q.g = 1): the tensor core truncates its fp32 accumulator after every
+    # MMA, a bias of about half an ulp of the running sum per instruction that only shows when
+    # the sum is large.  3*D/16 instructions per element: within 1e-5 at D = 768 (the ViT
+    # shape); at D = 2048 the documented bound is 3*D/16 * 2^-24 = 2.3e-5 (DESIGN.md 4.1).
+    for D, tol in ((768, 1e-5), (2048, 2.3e-5)):
+        a = torch.randn(64, D, generator=g)
+        b = torch.cat([a[:32], torch.randn(100, D, generator=g)])
+        ref = do.cosine_distmat(a, b).numpy()
+        for prec in ("f16x3", "tf32c"):
+            out = metrics.compute_distance_matrix(a.cuda(), b.cuda(), "cosine", prec)
+            _close(out, ref, tol)
+    with pytest.raises(_lib.DaliError):
+        metrics.compute_distance_matrix(z["qf"], z["gf"], "sqeuclidean", "f16x3")
 
 
 def test_tf32_single_pass_quality():
@@ -102,7 +142,7 @@ def test_exact_path_is_tile_position_independent():
     g = torch.Generator().manual_seed(3)
     qf = torch.randn(200, 384, generator=g).cuda()
     gf = torch.randn(1500, 384, generator=g).cuda()
-    for precision in ("fp32", "tf32x3", "tf32c", "tf32"):
+    for precision in ("fp32", "tf32x3", "tf32c", "tf32", "f16x3"):
         full = metrics.compute_distance_matrix(qf, gf, "cosine", precision)
         part = metrics.compute_distance_matrix(qf, gf[700:1333].contiguous(), "cosine", precision)
         assert torch.equal(full[:, 700:1333], part), precision
@@ -113,7 +153,7 @@ def test_evaluate_features_end_to_end():
     rounding of the oracle fed the reference's CPU matrix."""
     from daliid_b200 import metrics, synth
     qf, gf, qp, gp, qc, gc = synth.make_config("small")
-    for precision in ("fp32", "tf32x3", "tf32c"):
+    for precision in ("fp32", "tf32x3", "tf32c", "f16x3", "auto"):
         cmc, mAP, dist, det = metrics.evaluate_features(qf, gf, qp, gp, qc, gc, precision=precision,
                                                         return_distmat=True, return_details=True)
         e = ro.eval_market1501_cy_f32(dist, qp, gp, qc, gc, return_details=True)
@@ -195,8 +235,10 @@ def test_topk_features_fused():
     assert torch.equal(v, ev) and torch.equal(i, ei + 1000)
 
 
-@pytest.mark.parametrize("precision", ["tf32c", "tf32x3", "tf32"])
-@pytest.mark.parametrize("metric,largest", [("cosine", False), ("sqeuclidean", False), ("dot", True)])
+@pytest.mark.parametrize("precision,metric,largest", [
+    ("f16x3", "cosine", False), ("tf32c", "cosine", False), ("tf32x3", "cosine", False),
+    ("tf32", "cosine", False), ("tf32c", "sqeuclidean", False), ("tf32", "euclidean", False),
+    ("tf32c", "dot", True), ("tf32", "dot", True), ("f16x3", "cosine", True)])
 def test_topk_features_fused_multi_chunk(precision, metric, largest):
     """Fused distance + top-k (several gallery chunks, ragged last tile) equals top-k of the
     materialised matrix of the same precision: same kernel arithmetic, so bit-identical."""
