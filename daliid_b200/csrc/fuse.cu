@@ -5,6 +5,8 @@
 //                                      evaluateCleanATModels.py:127
 // weighted  w_m[i,j] = max(wq_m[i], wg_m[j]);  (w0*d0 + w1*d1 + ..)/(w0 + w1 + ..)
 //                                      evaluateCleanATModels.py:154-157,193-196,230-233
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace dali {
@@ -91,6 +93,56 @@ __global__ void __launch_bounds__(256) fuse_kernel(FuseParams p) {
   }
 }
 
+// Contiguous matrices (ld == G, what numpy / torch hand over): the Q x G elements are one flat
+// array, so 128-bit accesses work for any G (15913 is odd); the (row, column) of an element is
+// only needed for the weighted form.
+__global__ void __launch_bounds__(256) fuse_flat_kernel(FuseParams p) {
+  const int64_t total = p.Q * p.G;
+  const int64_t nvec = (total + 3) >> 2;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t e0 = i << 2;
+    int64_t q = 0, col = e0;
+    if (p.weighted) {
+      q = e0 / p.G;
+      col = e0 - q * p.G;
+    }
+    float xs[kMaxFuse][4];
+    const bool full = e0 + 3 < total;
+#pragma unroll
+    for (int m = 0; m < kMaxFuse; ++m) {
+      if (m < p.n) {
+        if (full) {
+          const float4 x = __ldcs(reinterpret_cast<const float4 *>(p.d[m] + e0));
+          xs[m][0] = x.x; xs[m][1] = x.y; xs[m][2] = x.z; xs[m][3] = x.w;
+        } else {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) xs[m][t] = e0 + t < total ? __ldg(p.d[m] + e0 + t) : 0.f;
+        }
+      }
+    }
+    float o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float v[kMaxFuse], wqv[kMaxFuse];
+#pragma unroll
+      for (int m = 0; m < kMaxFuse; ++m) {
+        v[m] = (m < p.n) ? xs[m][t] : 0.f;
+        wqv[m] = (p.weighted && m < p.n && e0 + t < total) ? __ldg(p.wq[m] + q) : 0.f;
+      }
+      o[t] = (e0 + t < total) ? fuse_one(p, v, wqv, col) : 0.f;
+      if (++col == p.G) { col = 0; ++q; }
+    }
+    if (full) {
+      *reinterpret_cast<float4 *>(p.out + e0) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (e0 + t < total) p.out[e0 + t] = o[t];
+    }
+  }
+}
+
 }  // namespace
 
 // All pointers are DEVICE pointers here (capi.cu stages host operands first).
@@ -107,6 +159,17 @@ int launch_fuse(dali_ctx *ctx, const float *const *d, int n, const float *const 
     if (m < n && (reinterpret_cast<uintptr_t>(d[m]) & 15)) aligned = false;
   }
   p.out = out; p.n = n; p.weighted = (wq && wg) ? 1 : 0; p.Q = Q; p.G = G; p.ld = ld;
+  bool base_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  for (int m = 0; m < n; ++m) base_aligned = base_aligned && (reinterpret_cast<uintptr_t>(d[m]) & 15) == 0;
+  if ((ld == G || Q == 1) && base_aligned) {
+    KTimer t(ctx, DALI_K_FUSE);
+    const int64_t nvec = (Q * G + 3) / 4;
+    const int64_t want = (nvec + 255) / 256;
+    const int blocks = static_cast<int>(std::min<int64_t>(want, 8ll * ctx->num_sms));
+    fuse_flat_kernel<<<blocks, 256, 0, ctx->stream>>>(p);
+    DALI_CUDA_OK(ctx, cudaGetLastError());
+    return DALI_OK;
+  }
   if (Q > 65535 * 1ll) {
     // grid.y limit: process in row bands
     return set_err(ctx, DALI_ERR_UNSUPPORTED, "fusion of more than 65535 rows: call per band");

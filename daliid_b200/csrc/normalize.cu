@@ -109,6 +109,91 @@ __global__ void __launch_bounds__(kPrepThreads) prep_rows_kernel(PrepParams p) {
   }
 }
 
+// Single-pass variant for rows of at most 4096 elements with 16-byte aligned rows (every
+// BASELINE shape): the row is read once with 128-bit loads and kept in registers between the
+// norm reduction and the plane writes; 16-bit planes are written 8 bytes at a time.
+constexpr int kVecCache = 4;  // float4 per thread: 256 threads * 4 * 4 = 4096 elements
+
+__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  return make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi));
+}
+__device__ __forceinline__ uint2 pack_f16x4(__half a, __half b, __half c, __half d) {
+  const __half2 lo = __halves2half2(a, b), hi = __halves2half2(c, d);
+  return make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi));
+}
+
+__global__ void __launch_bounds__(kPrepThreads) prep_rows_vec_kernel(PrepParams p) {
+  __shared__ float s_red[kPrepThreads / 32];
+  const int64_t r = blockIdx.x;
+  float4 *o0 = p.plane0 ? reinterpret_cast<float4 *>(p.plane0 + r * p.ldo) : nullptr;
+  float4 *o1 = p.plane1 ? reinterpret_cast<float4 *>(p.plane1 + r * p.ldo) : nullptr;
+  uint2 *h16 = p.hi16 ? reinterpret_cast<uint2 *>(p.hi16 + r * p.ldo) : nullptr;
+  uint2 *l16 = p.lo16 ? reinterpret_cast<uint2 *>(p.lo16 + r * p.ldo) : nullptr;
+  const int nv_pad = static_cast<int>(p.d_pad >> 2);
+  if (r >= p.n) {  // padding rows: zeros
+    for (int c = threadIdx.x; c < nv_pad; c += kPrepThreads) {
+      if (o0) o0[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (o1) o1[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (h16) { h16[c] = make_uint2(0u, 0u); l16[c] = make_uint2(0u, 0u); }
+    }
+    return;
+  }
+  const float4 *xr = reinterpret_cast<const float4 *>(p.x + r * p.ldx);
+  const int nv = static_cast<int>(p.d >> 2);
+  float4 cache[kVecCache];
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVecCache; ++i) {
+    const int c = threadIdx.x + i * kPrepThreads;
+    cache[i] = c < nv ? __ldg(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    acc = fmaf(cache[i].x, cache[i].x, acc);
+    acc = fmaf(cache[i].y, cache[i].y, acc);
+    acc = fmaf(cache[i].z, cache[i].z, acc);
+    acc = fmaf(cache[i].w, cache[i].w, acc);
+  }
+  float nrm = 1.f;
+  if (p.do_normalize || p.norms) {
+    nrm = sqrtf(block_sum(acc, s_red));
+    if (p.norms && threadIdx.x == 0) p.norms[r] = nrm;
+  }
+  float acc2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVecCache; ++i) {
+    const int c = threadIdx.x + i * kPrepThreads;
+    if (c >= nv_pad) break;
+    float4 v = cache[i];  // zeros beyond d
+    if (p.do_normalize && c < nv) {  // IEEE division, like the reference's x / norm
+      v.x = v.x / nrm; v.y = v.y / nrm; v.z = v.z / nrm; v.w = v.w / nrm;
+    }
+    acc2 = fmaf(v.x, v.x, acc2); acc2 = fmaf(v.y, v.y, acc2);
+    acc2 = fmaf(v.z, v.z, acc2); acc2 = fmaf(v.w, v.w, acc2);
+    if (p.round_mode == 2) {
+      const float sx = v.x * 4096.0f, sy = v.y * 4096.0f, sz = v.z * 4096.0f, sw = v.w * 4096.0f;
+      const __half hx = __float2half_rn(sx), hy = __float2half_rn(sy), hz = __float2half_rn(sz),
+                   hw = __float2half_rn(sw);
+      h16[c] = pack_f16x4(hx, hy, hz, hw);
+      l16[c] = pack_f16x4(__float2half_rn(sx - __half2float(hx)), __float2half_rn(sy - __half2float(hy)),
+                          __float2half_rn(sz - __half2float(hz)), __float2half_rn(sw - __half2float(hw)));
+    } else if (p.round_mode) {
+      const float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+      o0[c] = hi;
+      if (o1) o1[c] = make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y),
+                                  round_tf32(v.z - hi.z), round_tf32(v.w - hi.w));
+      if (h16) {
+        h16[c] = pack_bf16x4(hi.x, hi.y, hi.z, hi.w);
+        l16[c] = pack_bf16x4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+      }
+    } else {
+      o0[c] = v;
+    }
+  }
+  if (p.sq) {
+    const float t = block_sum(acc2, s_red);
+    if (threadIdx.x == 0) p.sq[r] = t;
+  }
+}
+
 }  // namespace
 
 int launch_prep(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx, float *plane0,
@@ -118,7 +203,15 @@ int launch_prep(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx
   PrepParams p{x, n, d, ldx, plane0, plane1, ldo, d_pad, rows_pad, do_normalize, round_mode, norms, sq,
                static_cast<__nv_bfloat16 *>(hi16), static_cast<__nv_bfloat16 *>(lo16)};
   KTimer t(ctx, DALI_K_NORMALIZE);
-  prep_rows_kernel<<<static_cast<unsigned>(rows_pad), kPrepThreads, 0, ctx->stream>>>(p);
+  const bool vec = d % 4 == 0 && d_pad <= 4 * kPrepThreads * kVecCache && ldx % 4 == 0 && ldo % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(plane0) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(plane1) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(hi16) & 7) == 0 && (reinterpret_cast<uintptr_t>(lo16) & 7) == 0;
+  if (vec)
+    prep_rows_vec_kernel<<<static_cast<unsigned>(rows_pad), kPrepThreads, 0, ctx->stream>>>(p);
+  else
+    prep_rows_kernel<<<static_cast<unsigned>(rows_pad), kPrepThreads, 0, ctx->stream>>>(p);
   DALI_CUDA_OK(ctx, cudaGetLastError());
   return DALI_OK;
 }

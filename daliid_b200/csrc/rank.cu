@@ -202,11 +202,12 @@ rank_count_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int64_
 //      (+ exact 64-bit compares only inside a threshold-holding bin) and bumps a PRIVATE 16-bit
 //      counter cnt[b][thread] in shared memory: no atomics, at most 2-way bank conflicts;
 //   4. counters are reduced per bucket; count_below(T[i]) = sum_{b <= i} hist[b].
-constexpr int kV2Threads = 256;
 constexpr int kV2Chunk = 254;  // thresholds per pass; buckets 0..n fit 8 bits
 
 
-template <int LOG2NB>
+// kV2Threads = 256 for few thresholds; 128 when a query has many positives (DeepChange: ~120),
+// where zeroing and reducing n x threads private counters is a large share of the CTA's work.
+template <int LOG2NB, int kV2Threads>
 __global__ void __launch_bounds__(kV2Threads)
 rank_count_v2_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int64_t Gs,
                      const int64_t *__restrict__ off, const int32_t *__restrict__ nvalid,
@@ -218,8 +219,8 @@ rank_count_v2_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
   uint64_t *T = Tu + 256;                                          // [256] sorted
   uint32_t *hist = reinterpret_cast<uint32_t *>(T + 256);          // [256]
   uint16_t *orig = reinterpret_cast<uint16_t *>(hist + 256);       // [256]
-  uint16_t *lut = orig + 256;                                      // [NB]
-  uint16_t *cnt = lut + NB;                                        // [(n) * 256] private counters
+  uint16_t *lut = orig + 256;                                      // [NB + 8], entry NB = "above all"
+  uint16_t *cnt = lut + NB + 8;                                    // [n * kV2Threads] private counters
 
   const int64_t q = blockIdx.x;
   const int chunk = blockIdx.y;
@@ -230,14 +231,15 @@ rank_count_v2_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
   const int tid = threadIdx.x;
 
   // 1. sort the thresholds by counting (composites are distinct: gallery ids differ)
-  if (tid < n) Tu[tid] = composite(__ldg(keys + o + tid), static_cast<uint32_t>(__ldg(gid + o + tid)));
+  for (int t = tid; t < n; t += kV2Threads)
+    Tu[t] = composite(__ldg(keys + o + t), static_cast<uint32_t>(__ldg(gid + o + t)));
   __syncthreads();
-  if (tid < n) {
-    const uint64_t c = Tu[tid];
+  for (int t = tid; t < n; t += kV2Threads) {
+    const uint64_t c = Tu[t];
     int pos = 0;
     for (int u = 0; u < n; ++u) pos += (Tu[u] < c) ? 1 : 0;
     T[pos] = c;
-    orig[pos] = static_cast<uint16_t>(tid);
+    orig[pos] = static_cast<uint16_t>(t);
   }
   __syncthreads();
   const uint32_t klo = static_cast<uint32_t>(T[0] >> 32);
@@ -262,6 +264,7 @@ rank_count_v2_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
       while (i < n && static_cast<int>((static_cast<uint32_t>(T[i] >> 32) - klo) >> sh) == b) ++i;
       lut[b] = static_cast<uint16_t>(base | ((i - base) << 8));
     }
+    if (tid == 0) lut[NB] = static_cast<uint16_t>(n);  // keys beyond the table: above every threshold
   }
   // 3. zero the private counters (bucket n = "above every threshold" is never counted)
   {
@@ -282,7 +285,7 @@ rank_count_v2_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
   auto visit = [&](float d, uint32_t g) {
     const uint32_t key = dist_key(d);
     const uint32_t dk = max(key, klo) - klo;
-    const uint32_t bin = min(dk >> sh, static_cast<uint32_t>(NB - 1));
+    const uint32_t bin = min(dk >> sh, static_cast<uint32_t>(NB));  // NB: far above every threshold
     const uint32_t e = lut[bin];
     uint32_t b = e & 0xFFu;
     const uint32_t ni = e >> 8;
@@ -322,19 +325,25 @@ rank_count_v2_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
   {
     const int w = tid >> 5, l = tid & 31;
     for (int b = w; b < n; b += kV2Threads / 32) {
-      const uint4 x = *reinterpret_cast<const uint4 *>(cnt + b * kV2Threads + l * 8);
-      uint32_t sum = (x.x & 0xFFFFu) + (x.x >> 16) + (x.y & 0xFFFFu) + (x.y >> 16) +
-                     (x.z & 0xFFFFu) + (x.z >> 16) + (x.w & 0xFFFFu) + (x.w >> 16);
+      uint32_t sum;
+      if (kV2Threads == 256) {
+        const uint4 x = *reinterpret_cast<const uint4 *>(cnt + b * kV2Threads + l * 8);
+        sum = (x.x & 0xFFFFu) + (x.x >> 16) + (x.y & 0xFFFFu) + (x.y >> 16) +
+              (x.z & 0xFFFFu) + (x.z >> 16) + (x.w & 0xFFFFu) + (x.w >> 16);
+      } else {
+        const uint2 x = *reinterpret_cast<const uint2 *>(cnt + b * kV2Threads + l * 4);
+        sum = (x.x & 0xFFFFu) + (x.x >> 16) + (x.y & 0xFFFFu) + (x.y >> 16);
+      }
       sum = __reduce_add_sync(0xffffffffu, sum);
       if (l == 0) hist[b] = sum;
     }
   }
   __syncthreads();
   // 6. count_below(T[i]) = sum_{b <= i} hist[b]; scatter back to plan order
-  if (tid < n) {
+  for (int t = tid; t < n; t += kV2Threads) {
     uint32_t below = 0;
-    for (int b = 0; b <= tid; ++b) below += hist[b];
-    int32_t *dst = counts + o + orig[tid];
+    for (int b = 0; b <= t; ++b) below += hist[b];
+    int32_t *dst = counts + o + orig[t];
     if (nsplit > 1) {
       if (below) atomicAdd(dst, static_cast<int32_t>(below));
     } else {
@@ -424,8 +433,25 @@ int launch_rank_gather(dali_ctx *ctx, const dali_rank_plan *plan, const float *d
   return DALI_OK;
 }
 
-static size_t v2_smem_bytes(int log2nb, int nbuckets) {
-  return 256 * 8 * 2 + 256 * 4 + 256 * 2 + (size_t(1) << log2nb) * 2 + size_t(nbuckets) * kV2Threads * 2;
+static size_t v2_smem_bytes(int log2nb, int nbuckets, int threads) {
+  return 256 * 8 * 2 + 256 * 4 + 256 * 2 + ((size_t(1) << log2nb) + 8) * 2 + size_t(nbuckets) * threads * 2;
+}
+
+template <int LOG2NB, int THREADS>
+static int launch_v2(dali_ctx *ctx, dim3 grid, size_t smem, const dali_rank_plan *plan, const float *dist,
+                     int64_t ld, int64_t g0, int64_t Gs, const uint32_t *keys, int32_t *counts,
+                     int nsplit) {
+  static size_t attr = 0;
+  if (smem > attr) {
+    const size_t want = std::max<size_t>(smem, 48 * 1024);
+    DALI_CUDA_OK(ctx, cudaFuncSetAttribute(rank_count_v2_kernel<LOG2NB, THREADS>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(want)));
+    attr = want;
+  }
+  rank_count_v2_kernel<LOG2NB, THREADS><<<grid, THREADS, smem, ctx->stream>>>(
+      dist, ld, g0, Gs, plan->d_off, plan->d_nv, plan->d_gid, keys, counts, nsplit);
+  return DALI_OK;
 }
 
 int launch_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist, int64_t ld,
@@ -438,10 +464,10 @@ int launch_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *di
   const int nchunk = (plan->max_nv + per_cta - 1) / per_cta;
   if (nchunk > 65535) return set_err(ctx, DALI_ERR_UNSUPPORTED, "too many positives for one query");
   // enough CTAs for >= 4 per SM; never split a row below 4096 columns; a v2 CTA counts in
-  // 16-bit private counters, so it may see at most 65535 * 256 columns
+  // 16-bit private counters, so it may see at most 65535 * 128 columns
   int64_t want = (4ll * ctx->num_sms + plan->Q * nchunk - 1) / (plan->Q * nchunk);
   const int64_t max_split = (Gs + 4095) / 4096;
-  const int64_t min_split = (Gs + (8ll << 20) - 1) / (8ll << 20);
+  const int64_t min_split = (Gs + (4ll << 20) - 1) / (4ll << 20);
   int64_t ns = std::max<int64_t>(1, std::min(want, max_split));
   ns = std::max(ns, min_split);
   if (ns > 65535) return set_err(ctx, DALI_ERR_UNSUPPORTED, "slab too wide for one launch");
@@ -454,29 +480,14 @@ int launch_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *di
                                                               nsplit);
   } else {
     const int nb = std::min(plan->max_nv, kV2Chunk);
-    // finer table when many thresholds share the key range
-    const int log2nb = nb > 64 ? 12 : 11;
-    const size_t smem = v2_smem_bytes(log2nb, nb);
-    static size_t attr11 = 0, attr12 = 0;
-    if (log2nb == 11) {
-      if (smem > attr11) {
-        DALI_CUDA_OK(ctx, cudaFuncSetAttribute(rank_count_v2_kernel<11>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               static_cast<int>(std::max<size_t>(smem, 48 * 1024))));
-        attr11 = std::max<size_t>(smem, 48 * 1024);
-      }
-      rank_count_v2_kernel<11><<<grid, kV2Threads, smem, ctx->stream>>>(
-          dist, ld, g0, Gs, plan->d_off, plan->d_nv, plan->d_gid, keys, counts, nsplit);
+    // finer table and fewer private counter copies when a query has many thresholds
+    int rc;
+    if (nb > 64) {
+      rc = launch_v2<12, 128>(ctx, grid, v2_smem_bytes(12, nb, 128), plan, dist, ld, g0, Gs, keys, counts, nsplit);
     } else {
-      if (smem > attr12) {
-        DALI_CUDA_OK(ctx, cudaFuncSetAttribute(rank_count_v2_kernel<12>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               static_cast<int>(std::max<size_t>(smem, 48 * 1024))));
-        attr12 = std::max<size_t>(smem, 48 * 1024);
-      }
-      rank_count_v2_kernel<12><<<grid, kV2Threads, smem, ctx->stream>>>(
-          dist, ld, g0, Gs, plan->d_off, plan->d_nv, plan->d_gid, keys, counts, nsplit);
+      rc = launch_v2<11, 256>(ctx, grid, v2_smem_bytes(11, nb, 256), plan, dist, ld, g0, Gs, keys, counts, nsplit);
     }
+    if (rc) return rc;
   }
   DALI_CUDA_OK(ctx, cudaGetLastError());
   return DALI_OK;

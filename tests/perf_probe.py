@@ -30,7 +30,7 @@ def main():
     if what in ("market_vit", "deepchange", "market_resnet50"):
         qf, gf, qp, gp, qc, gc = synth.make_config(what, device="cuda")
         Q, G = qf.shape[0], gf.shape[0]
-        for prec in ("tf32c", "tf32", "fp32"):
+        for prec in ("f16x3", "tf32c", "tf32", "fp32"):
             if prec == "fp32" and what == "deepchange":
                 continue
             ctx.timing_enable(True); ctx.timing_reset()
@@ -53,7 +53,7 @@ def main():
         g = torch.Generator(device="cuda").manual_seed(12)
         qf = torch.randn(Q, D, generator=g, device="cuda")
         gf = torch.randn(G, D, generator=g, device="cuda")
-        for prec in ("tf32c", "tf32"):
+        for prec in ("f16x3", "tf32c", "tf32"):
             ctx.timing_enable(True); ctx.timing_reset()
             n_fb = ctx.fallback_count()
             ms, (v, i) = timeit(lambda: metrics.topk_features(qf, gf, k=20, precision=prec), n=2, warm=1)
