@@ -1086,9 +1086,11 @@ static int topk_features_fused(dali_ctx *ctx, const Prepared &b, const float *q,
     int64_t seen = 0;
     while (seen < G) {
       const bool first = seen == 0;
-      int64_t chunk = first ? std::min<int64_t>(G, kCapList)
+      // first chunk: every column becomes a candidate, so keep it as narrow as k allows (the
+      // compaction sorts it whole); later chunks start on a tile edge
+      const int64_t first_cols = std::min<int64_t>(kCapList, round_up(std::max<int64_t>(2 * k, 256), 256));
+      int64_t chunk = first ? std::min<int64_t>(G, first_cols)
                             : std::min<int64_t>(G - seen, std::max<int64_t>(256, growth * seen / 256 * 256));
-      if (first && chunk < G) chunk = chunk / 256 * 256;  // later chunks must start on a tile edge
       rc = launch_distmat_filter_umma(ctx, a.planes, b.planes, a.planes16, b.planes16, qc, chunk, a.Dp,
                                       a.rows_pad, b.rows_pad, seen, precision, metric, a.sq,
                                       b.sq ? b.sq + seen : nullptr, thr, cnt, cand, kCapList, largest,

@@ -28,6 +28,7 @@
 // replaces  1.0 - torch.mm(q, g.T)   validateModels.py:47, evaluate.py:260-267,291,
 //           evaluate_ensembled_models.py:281,300, evaluateCleanATModels.py:109,121,124
 //           torch.argsort(distmat, dim=1)[:, :20]   validateModels.py:93 (kFilter)
+#include <algorithm>
 #include <cstdlib>
 
 #include "umma_common.cuh"
@@ -53,7 +54,8 @@ constexpr int B16_BYTES = HB * BK * 2;     // 8 KiB
 constexpr int kSlotBytes = A_BYTES + B_BYTES;  // 32 KiB == 2*A16 + 2*B16
 constexpr int kSlots = 6;
 constexpr int kBarBytes = 256;
-constexpr int kSmemBytes = kSlots * kSlotBytes + EPI_BYTES + kBarBytes + 1024;
+constexpr int kStageBytes = 4 * 2 * 4096;  // four epilogue warps x two 32x32 fp32 store tiles
+constexpr int kSmemBytes = kSlots * kSlotBytes + kStageBytes + kBarBytes + 1024;
 static_assert(8 * (2 * kSlots + 4) + 8 <= kBarBytes, "barrier block too small");
 
 enum Epi { kStore = 0, kFilter = 1 };
@@ -61,6 +63,7 @@ enum Epi { kStore = 0, kFilter = 1 };
 struct Umma2Params {
   int64_t Q, G;
   int num_m_pairs, num_n_tiles, num_kb;
+  int nband;            // n-tiles per L2 band (1 = plain m-fastest order)
   int32_t a_plane_rows, b_plane_rows;  // row offset of plane 1 inside the tensor maps
   int32_t b_row0;                      // first gallery row of this slab inside the B planes
   int metric;
@@ -68,6 +71,7 @@ struct Umma2Params {
   // kStore
   float *out;
   int64_t ld;
+  int tma_out;          // 1: rows of `out` are 16-byte aligned, tiles leave through TMA stores
   // kFilter
   const float *thr;     // [Q] running k-th best distance of the row (+inf / -inf: accept all)
   int32_t *cand_cnt;    // [Q] entries appended to the row's list
@@ -79,6 +83,45 @@ struct Umma2Params {
   int debug;            // DALI_DEBUG_EPI (profiling experiments only)
   float acc_scale;      // 2^-24 for kF16x3 (operands carry a factor 2^12 each), else 1
 };
+
+// ---- kStore epilogue helpers -----------------------------------------------------------------
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float a) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int32_t x, int32_t y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(x), "r"(y)
+               : "memory");
+}
+
+// The metric on 32 accumulator columns of one query row, in registers (same expressions as the
+// filter epilogue and umma::metric_epilogue).  KIND 0: alpha * acc + beta (cosine, dot);
+// 1: |q|^2 + |g|^2 - 2 acc; 2: its square root.
+template <int KIND>
+__device__ __forceinline__ void apply_metric(uint32_t (&v)[32], float alpha, float beta, float scale,
+                                             float qs, const float *__restrict__ gs, int lim) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float acc = __uint_as_float(v[j]);
+    float d;
+    if (KIND == 0) {
+      d = fmaf(acc, alpha, beta);
+    } else {
+      d = fmaf(-2.0f, acc * scale, qs + __ldg(gs + (j < lim ? j : 0)));
+      if (KIND == 2) d = sqrtf(fmaxf(d, 1e-30f));
+    }
+    v[j] = __float_as_uint(d);
+  }
+}
 
 // ---- kFilter epilogue: 32 accumulator columns of one query row -------------------------------
 struct FilterRow {
@@ -159,14 +202,14 @@ template <int MODE, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmA16,
-                     const __grid_constant__ CUtensorMap tmB16, const Umma2Params p) {
+                     const __grid_constant__ CUtensorMap tmB16,
+                     const __grid_constant__ CUtensorMap tmOut, const Umma2Params p) {
   extern __shared__ uint8_t smem_raw[];
   // the dynamic window starts at the same offset in both CTAs, so this rounding is identical
   // in the pair (the MMA applies the leader's operand offsets to the peer's shared memory)
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~uintptr_t(1023));
-  float *epi = reinterpret_cast<float *>(smem + kSlots * kSlotBytes);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kSlots * kSlotBytes + EPI_BYTES);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kSlots * kSlotBytes + kStageBytes);
   // bars: [0,S) full (leader's are used), [S,2S) empty, [2S,2S+2) tmem_full,
   //       [2S+2,2S+4) tmem_empty (leader's are used), then the TMEM base pointer
   uint32_t *tmem_ptr_s = reinterpret_cast<uint32_t *>(bars + 2 * kSlots + 4);
@@ -183,6 +226,21 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
   const int num_tiles = p.num_m_pairs * p.num_n_tiles;
+  // Tile order.  Bands of `nband` gallery tiles: inside a band the tiles of one query pair-tile
+  // are consecutive, so the ~74 tiles in flight share a few query tiles and the band's gallery
+  // tiles stay in L2, while the query planes stream from HBM once per band.  nband = 1 is the
+  // m-fastest order (queries resident in L2, gallery streamed once) used when the query planes
+  // are small.
+  const int band_tiles = p.num_m_pairs * p.nband;
+  auto tile_mn = [&](int t, int &m, int &n) {
+    const int band = t / band_tiles;
+    const int r = t - band * band_tiles;
+    const int n0 = band * p.nband;
+    const int nb = min(p.nband, p.num_n_tiles - n0);
+    if (p.nband == 1) { m = r; n = n0; return; }
+    m = r / nb;
+    n = n0 + (r - m * nb);
+  };
 
   if (warp == 0 && lane == 0) {
     if (MODE != kF16x3) {
@@ -223,7 +281,8 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       auto advance = [&]() { if (++slot == kSlots) { slot = 0; phase ^= 1u; } };
       const uint32_t full0 = mapa_u32(full_bar(0), 0);  // the leader's full barriers
       for (int t = pair; t < num_tiles; t += num_pairs) {
-        const int m = t % p.num_m_pairs, n = t / p.num_m_pairs;
+        int m, n;
+        tile_mn(t, m, n);
         const int arow = m * PM + static_cast<int>(rank) * UM;
         const int brow = p.b_row0 + n * BN + static_cast<int>(rank) * HB;
         for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -351,10 +410,12 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   } else {
     // ===================== epilogue warps (both CTAs) =====================
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
-    float *stg = epi + (warp - 2) * 32 * EPI_LD;
+    const uint32_t stg_base = smem_u32(smem + kSlots * kSlotBytes) + static_cast<uint32_t>((warp - 2) * 8192);
+    uint32_t nstore = 0;
     int it = 0;
     for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
-      const int m = t % p.num_m_pairs, n = t / p.num_m_pairs;
+      int m, n;
+      tile_mn(t, m, n);
       const int as = it & 1;
       mbar_wait(tfull_bar(as), (it >> 1) & 1u);
       tc_fence_after();
@@ -364,29 +425,64 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                              static_cast<uint32_t>(as * BN);
       if (row0 < p.Q) {  // otherwise this warp's rows are padding (warp-uniform)
         if (EPI == kStore) {
+          // one thread per query row: metric in registers, then either
+          //   - the 32 x 32 block goes to a 128B-swizzled staging tile (conflict-free 16-byte
+          //     stores) and leaves through one TMA store (rows / columns beyond Q / G clipped by
+          //     the tensor map); two staging tiles per warp, so a store drains while the next
+          //     block is prepared; or
+          //   - (rows of `out` not 16-byte aligned) a padded transpose through the same staging
+          //     memory and coalesced 128-byte row stores.
+          const int64_t r_own = row0 + lane;
+          const float qs = (p.qsq && r_own < p.Q) ? __ldg(p.qsq + r_own) : 0.f;
+          const float alpha = (p.metric == DALI_METRIC_COSINE ? -1.0f : 1.0f) * p.acc_scale;
+          const float beta = p.metric == DALI_METRIC_COSINE ? 1.0f : 0.0f;
+          const int kind = p.metric == DALI_METRIC_SQEUCLIDEAN ? 1 : p.metric == DALI_METRIC_EUCLIDEAN ? 2 : 0;
 #pragma unroll 1
           for (int c = 0; c < BN / 32; ++c) {
-            if (colt + c * 32 >= p.G) break;
+            const int64_t col0 = colt + c * 32;
+            if (col0 >= p.G) break;
             if (p.debug & 1) break;
             uint32_t v[32];
             tc_ld_32x32(tbase + c * 32, v);
             tc_wait_ld();
+            const int lim = p.G - col0 < 32 ? static_cast<int>(p.G - col0) : 32;
+            const float *gs = p.gsq ? p.gsq + col0 : nullptr;
+            if (kind == 0) apply_metric<0>(v, alpha, beta, p.acc_scale, qs, gs, lim);
+            else if (kind == 1) apply_metric<1>(v, alpha, beta, p.acc_scale, qs, gs, lim);
+            else apply_metric<2>(v, alpha, beta, p.acc_scale, qs, gs, lim);
+            if (p.tma_out) {
+              const uint32_t buf = stg_base + static_cast<uint32_t>(((nstore++) & 1) * 4096);
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              __syncwarp();
+              const uint32_t rowaddr = buf + static_cast<uint32_t>(lane * 128);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) stg[lane * EPI_LD + j] = __uint_as_float(v[j]);
-            __syncwarp();
-            const int64_t col = colt + c * 32 + lane;
-            const bool col_ok = col < p.G;
-            const float gs = (p.gsq && col_ok) ? __ldg(p.gsq + col) : 0.f;
-#pragma unroll 4
-            for (int rr = 0; rr < 32; ++rr) {
-              const int64_t r = row0 + rr;
-              if (r < p.Q && col_ok) {
-                const float qs = p.qsq ? __ldg(p.qsq + r) : 0.f;
-                p.out[r * p.ld + col] =
-                    metric_epilogue(stg[rr * EPI_LD + lane] * p.acc_scale, p.metric, qs, gs);
+              for (int j = 0; j < 8; ++j)
+                sts128(rowaddr + static_cast<uint32_t>(((j ^ (lane & 7)) << 4)),
+                       __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmOut, buf, static_cast<int32_t>(col0), static_cast<int32_t>(row0));
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
               }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                sts32(stg_base + static_cast<uint32_t>((lane * EPI_LD + j) * 4), __uint_as_float(v[j]));
+              __syncwarp();
+              const int64_t col = col0 + lane;
+              float *dst = p.out + row0 * p.ld + col;
+              const int rows = p.Q - row0 < 32 ? static_cast<int>(p.Q - row0) : 32;
+              if (col < p.G) {
+#pragma unroll 8
+                for (int rr = 0; rr < 32; ++rr) {
+                  const float val = lds32(stg_base + static_cast<uint32_t>((rr * EPI_LD + lane) * 4));
+                  if (rr < rows) dst[rr * p.ld] = val;
+                }
+              }
+              __syncwarp();
             }
-            __syncwarp();
           }
         } else {
           // one thread per query row: its 256 distances of this tile against the row's
@@ -449,6 +545,7 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_bar(as), 0);
     }
+    if (EPI == kStore && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -462,7 +559,7 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
 template <int MODE, int EPI>
 int launch_t(dali_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmA16,
-             const CUtensorMap &tmB16, const Umma2Params &p) {
+             const CUtensorMap &tmB16, const CUtensorMap &tmOut, const Umma2Params &p) {
   static bool attr_set = false;
   if (!attr_set) {
     DALI_CUDA_OK(ctx, cudaFuncSetAttribute(distmat_umma2_kernel<MODE, EPI>,
@@ -474,21 +571,39 @@ int launch_t(dali_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, cons
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   KTimer t(ctx, DALI_K_DISTMAT);
   distmat_umma2_kernel<MODE, EPI><<<2 * pairs, kThreads, kSmemBytes, ctx->stream>>>(tmA, tmB, tmA16,
-                                                                                   tmB16, p);
+                                                                                   tmB16, tmOut, p);
   DALI_CUDA_OK(ctx, cudaGetLastError());
   return DALI_OK;
 }
 
 template <int EPI>
 int launch_prec(dali_ctx *ctx, int precision, const CUtensorMap &tmA, const CUtensorMap &tmB,
-                const CUtensorMap &tmA16, const CUtensorMap &tmB16, const Umma2Params &p) {
+                const CUtensorMap &tmA16, const CUtensorMap &tmB16, const CUtensorMap &tmOut,
+                const Umma2Params &p) {
   switch (precision) {
-    case DALI_PREC_TF32: return launch_t<kTf32, EPI>(ctx, tmA, tmB, tmA16, tmB16, p);
-    case DALI_PREC_TF32X3: return launch_t<kTf32x3, EPI>(ctx, tmA, tmB, tmA16, tmB16, p);
-    case DALI_PREC_TF32C: return launch_t<kTf32c, EPI>(ctx, tmA, tmB, tmA16, tmB16, p);
-    case DALI_PREC_F16X3: return launch_t<kF16x3, EPI>(ctx, tmA, tmB, tmA16, tmB16, p);
+    case DALI_PREC_TF32: return launch_t<kTf32, EPI>(ctx, tmA, tmB, tmA16, tmB16, tmOut, p);
+    case DALI_PREC_TF32X3: return launch_t<kTf32x3, EPI>(ctx, tmA, tmB, tmA16, tmB16, tmOut, p);
+    case DALI_PREC_TF32C: return launch_t<kTf32c, EPI>(ctx, tmA, tmB, tmA16, tmB16, tmOut, p);
+    case DALI_PREC_F16X3: return launch_t<kF16x3, EPI>(ctx, tmA, tmB, tmA16, tmB16, tmOut, p);
     default: return set_err(ctx, DALI_ERR_INVALID, "not a tensor-core precision");
   }
+}
+
+// Output map: fp32 [Q][G] with row pitch ld, 32 x 32 boxes in the 128-byte swizzle the epilogue
+// writes its staging tiles in.
+int make_out_map(dali_ctx *ctx, CUtensorMap *map, float *out, int64_t Q, int64_t G, int64_t ld) {
+  // ctx->encode_tiled was resolved by make_map() in setup()
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(G), static_cast<cuuint64_t>(Q)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_err(ctx, DALI_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed with CUresult " + std::to_string(r));
+  return DALI_OK;
 }
 
 int setup(dali_ctx *ctx, const float *q32, const float *g32, const void *q16, const void *g16,
@@ -531,6 +646,17 @@ int setup(dali_ctx *ctx, const float *q32, const float *g32, const void *q16, co
   p->b_row0 = static_cast<int32_t>(g_row0);
   p->metric = metric; p->qsq = qsq; p->gsq = gsq;
   p->acc_scale = f16 ? 5.9604644775390625e-08f /* 2^-24 */ : 1.0f;
+  {
+    // bytes of operand planes one tile row of 256 rows reads per pass over K
+    const int64_t bytes_per_row = Dp * (precision == DALI_PREC_TF32 ? 4 : precision == DALI_PREC_F16X3 ? 4 : 8);
+    const int64_t a_bytes = static_cast<int64_t>(p->num_m_pairs) * PM * bytes_per_row;
+    static const char *env_band = getenv("DALI_UMMA_NBAND");
+    int nband = 1;
+    if (a_bytes > (48ll << 20))
+      nband = static_cast<int>(std::max<int64_t>(1, (24ll << 20) / (BN * bytes_per_row)));
+    if (env_band) nband = atoi(env_band);
+    p->nband = std::max(1, std::min(nband, p->num_n_tiles));
+  }
   if (static_cast<int64_t>(p->num_m_pairs) * p->num_n_tiles > INT32_MAX)
     return set_err(ctx, DALI_ERR_UNSUPPORTED, "too many tiles (chunk the queries)");
   return DALI_OK;
@@ -559,7 +685,17 @@ int launch_distmat_umma(dali_ctx *ctx, const float *q32, const float *g32, const
   p.out = out; p.ld = ld;
   static const char *dbg = getenv("DALI_DEBUG_EPI");
   p.debug = dbg ? atoi(dbg) : 0;
-  return launch_prec<kStore>(ctx, precision, tmA, tmB, tmA16, tmB16, p);
+  // TMA stores need 16-byte aligned rows (always true for the library's own matrices, whose
+  // leading dimension is a multiple of 4; a caller's contiguous [Q, G] with odd G is not)
+  static const char *env_tma = getenv("DALI_UMMA_TMA_STORE");
+  CUtensorMap tmOut = tmA;
+  p.tma_out = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+              !(env_tma && atoi(env_tma) == 0) && Q <= INT32_MAX && G <= INT32_MAX;
+  if (p.tma_out) {
+    rc = make_out_map(ctx, &tmOut, out, Q, G, ld);
+    if (rc) return rc;
+  }
+  return launch_prec<kStore>(ctx, precision, tmA, tmB, tmA16, tmB16, tmOut, p);
 }
 
 // Fused distance + top-k candidate filter: columns [0, G) of the slab starting at gallery row
@@ -583,7 +719,7 @@ int launch_distmat_filter_umma(dali_ctx *ctx, const float *q32, const float *g32
   p.largest = largest; p.direct = direct; p.id_base = id_base;
   static const char *dbg = getenv("DALI_DEBUG_EPI");
   p.debug = dbg ? atoi(dbg) : 0;
-  return launch_prec<kFilter>(ctx, precision, tmA, tmB, tmA16, tmB16, p);
+  return launch_prec<kFilter>(ctx, precision, tmA, tmB, tmA16, tmB16, tmA, p);
 }
 
 }  // namespace dali

@@ -47,6 +47,21 @@ def main():
         d2 = d.clone()
         ms, _ = timeit(lambda: metrics.fuse_distmats([d, d2]))
         print(f"{what} fuse 2: {ms:.3f} ms -> {12 * Q * G / ms / 1e6:.0f} GB/s", flush=True)
+    elif what == "faceid_slab":
+        # BASELINE config 5 as one of 8 GPUs sees it: all 100k queries against a 125k gallery slab
+        Q, G, D = 100000, 125000, 512
+        g = torch.Generator(device="cuda").manual_seed(12)
+        qf = torch.randn(Q, D, generator=g, device="cuda")
+        gf = torch.randn(G, D, generator=g, device="cuda")
+        for prec in sys.argv[2:] or ("f16x3",):
+            ctx.timing_enable(True); ctx.timing_reset()
+            n_fb = ctx.fallback_count()
+            ms, (v, i) = timeit(lambda: metrics.topk_features(qf, gf, k=20, precision=prec), n=1, warm=1)
+            kt = {k: (v[0], round(v[1], 3)) for k, v in ctx.timing_read().items() if v[0]}
+            ctx.timing_enable(False)
+            print(f"faceid_slab {Q}x{G} D={D} {prec}: {ms:.1f} ms, {Q * G / ms / 1e6:.2f} Gpairs/s, "
+                  f"{2 * Q * G * D / ms / 1e9:.0f} TFLOP/s, fallbacks {ctx.fallback_count() - n_fb}, "
+                  f"kernels (launches, total ms): {kt}", flush=True)
     elif what == "faceid":
         # scaled-down BASELINE config 5 (100k x 1M, D=512): 16k x 262k here, k=20
         Q, G, D = 16384, 262144, 512

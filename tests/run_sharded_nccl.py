@@ -26,7 +26,7 @@ def main():
     for name in ("small", "market_vit"):
         qf, gf, qp, gp, qc, gc = synth.make_config(name, device=f"cuda:{local}")
         g0, gs = sharded.slab_bounds(gf.shape[0], world, rank)
-        for precision in ("tf32c", "fp32"):
+        for precision in ("auto", "tf32c", "fp32"):
             cmc, mAP, det = sharded.evaluate_features_sharded(
                 qf, gf[g0:g0 + gs].contiguous(), g0, qp, gp, qc, gc, precision=precision,
                 return_details=True)

@@ -284,24 +284,34 @@ def test_topk_features_fused_overflow_falls_back():
 
 
 def test_two_cta_kernel_equals_one_cta_kernel():
-    """The CTA-pair contraction and the one-CTA-per-tile kernel accumulate every element in
-    the same k order: bit-identical matrices (run in a subprocess with DALI_UMMA_2CTA=0)."""
+    """The CTA-pair contraction (plain and L2-banded tile order; TMA-store and transposing
+    epilogue) and the one-CTA-per-tile kernel accumulate every element in the same k order:
+    bit-identical matrices (subprocesses with DALI_UMMA_2CTA=0 / DALI_UMMA_NBAND=3 /
+    DALI_UMMA_TMA_STORE=0).  The 'small' gallery has 2100 rows: a multiple of 4, so the default
+    run stores through TMA."""
     import subprocess
     import sys
+    import tempfile
     code = (
         "import torch, sys, numpy as np\n"
         "from daliid_b200 import metrics, synth\n"
         "qf, gf, *_ = synth.make_config('small', device='cuda')\n"
-        "for p in ('tf32', 'tf32x3', 'tf32c'):\n"
+        "qf = torch.cat([qf, qf * 0.5 + 1.0, qf[:177] - 2.0])  # 777 queries: 4 pair tiles\n"
+        "for p in sys.argv[2:]:\n"
         "    d = metrics.compute_distance_matrix(qf, gf, 'cosine', p)\n"
         "    np.save(sys.argv[1] + p + '.npy', d.cpu().numpy())\n")
-    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    runs = {"one": (dict(DALI_UMMA_2CTA="0"), ("tf32", "tf32x3", "tf32c")),
+            "two": (dict(), ("tf32", "tf32x3", "tf32c", "f16x3")),
+            "band": (dict(DALI_UMMA_NBAND="3"), ("tf32", "tf32x3", "tf32c", "f16x3")),
+            "notma": (dict(DALI_UMMA_TMA_STORE="0"), ("tf32", "tf32x3", "tf32c", "f16x3"))}
     with tempfile.TemporaryDirectory() as td:
-        for flag in ("0", "1"):
-            env = dict(os.environ, DALI_UMMA_2CTA=flag)
-            subprocess.check_call([sys.executable, "-c", code, os.path.join(td, flag + "_")], env=env,
-                                  cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-        for p in ("tf32", "tf32x3", "tf32c"):
-            a = np.load(os.path.join(td, "0_" + p + ".npy"))
-            b = np.load(os.path.join(td, "1_" + p + ".npy"))
-            assert np.array_equal(a, b), p
+        for name, (env, precs) in runs.items():
+            subprocess.check_call([sys.executable, "-c", code, os.path.join(td, name + "_"), *precs],
+                                  env=dict(os.environ, **env), cwd=root)
+        for p in ("tf32", "tf32x3", "tf32c", "f16x3"):
+            b = np.load(os.path.join(td, "two_" + p + ".npy"))
+            assert np.array_equal(np.load(os.path.join(td, "band_" + p + ".npy")), b), p
+            assert np.array_equal(np.load(os.path.join(td, "notma_" + p + ".npy")), b), p
+            if p != "f16x3":
+                assert np.array_equal(np.load(os.path.join(td, "one_" + p + ".npy")), b), p
