@@ -191,7 +191,8 @@ static int finish_on_host(dali_ctx *ctx, const dali_rank_plan *plan, const int32
                           int32_t *first_rank_opt, int64_t *num_valid_opt) {
   const int64_t Q = plan->Q;
   const bool need_ranks = accum_mode == DALI_ACCUM_PY_F64;
-  const size_t b_ap = sizeof(float) * Q, b_first = sizeof(int32_t) * Q,
+  const int64_t Qp = std::max<int64_t>(Q, 1);  // layout of the device block (dali_rank_finalize)
+  const size_t b_ap = sizeof(float) * Qp, b_first = sizeof(int32_t) * Qp,
                b_cmc = sizeof(int32_t) * (max_rank + 1),
                b_ranks = need_ranks ? sizeof(int32_t) * plan->M : 0;
   int rc = pinned_ensure(ctx, b_ap + b_first + b_cmc + b_ranks + 64);
@@ -201,11 +202,8 @@ static int finish_on_host(dali_ctx *ctx, const dali_rank_plan *plan, const int32
   int32_t *h_first = reinterpret_cast<int32_t *>(h + b_ap);
   int32_t *h_cmc = reinterpret_cast<int32_t *>(h + b_ap + b_first);
   int32_t *h_ranks = reinterpret_cast<int32_t *>(h + b_ap + b_first + b_cmc);
-  if (Q) {
-    DALI_CUDA_OK(ctx, cudaMemcpyAsync(h_ap, d_ap, b_ap, cudaMemcpyDeviceToHost, ctx->stream));
-    DALI_CUDA_OK(ctx, cudaMemcpyAsync(h_first, d_first, b_first, cudaMemcpyDeviceToHost, ctx->stream));
-  }
-  DALI_CUDA_OK(ctx, cudaMemcpyAsync(h_cmc, d_cmc, b_cmc, cudaMemcpyDeviceToHost, ctx->stream));
+  (void)d_first; (void)d_cmc;  // contiguous after d_ap
+  DALI_CUDA_OK(ctx, cudaMemcpyAsync(h_ap, d_ap, b_ap + b_first + b_cmc, cudaMemcpyDeviceToHost, ctx->stream));
   if (b_ranks)
     DALI_CUDA_OK(ctx, cudaMemcpyAsync(h_ranks, d_ranks, b_ranks, cudaMemcpyDeviceToHost, ctx->stream));
   DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -876,22 +874,21 @@ int dali_rank_finalize(dali_ctx *ctx, const dali_rank_plan *plan, const uint32_t
   if (accum_mode != DALI_ACCUM_CY_F32 && accum_mode != DALI_ACCUM_PY_F64)
     return set_err(ctx, DALI_ERR_INVALID, "unknown accumulation mode");
   if (max_rank > plan->G) max_rank = static_cast<int>(std::max<int64_t>(plan->G, 1));
-  void *ranks, *ap, *first, *cmcd;
+  // per-query AP | first-match rank | CMC histogram live in one block: one D2H copy fetches them
+  void *ranks, *blk;
   rc = ws_ensure(ctx, WS_RANKS, sizeof(int32_t) * std::max<int64_t>(plan->M, 1), &ranks);
   if (rc) return rc;
-  rc = ws_ensure(ctx, WS_AP, sizeof(float) * std::max<int64_t>(plan->Q, 1), &ap);
+  const int64_t Qp = std::max<int64_t>(plan->Q, 1);
+  rc = ws_ensure(ctx, WS_AP, sizeof(float) * Qp + sizeof(int32_t) * Qp + sizeof(int32_t) * (max_rank + 1), &blk);
   if (rc) return rc;
-  rc = ws_ensure(ctx, WS_FIRST, sizeof(int32_t) * std::max<int64_t>(plan->Q, 1), &first);
+  float *ap = static_cast<float *>(blk);
+  int32_t *first = reinterpret_cast<int32_t *>(ap + Qp);
+  int32_t *cmcd = first + Qp;
+  rc = launch_rank_finalize(ctx, plan, keys, counts, max_rank, static_cast<int32_t *>(ranks), ap, first,
+                            cmcd);
   if (rc) return rc;
-  rc = ws_ensure(ctx, WS_CMC, sizeof(int32_t) * (max_rank + 1), &cmcd);
-  if (rc) return rc;
-  rc = launch_rank_finalize(ctx, plan, keys, counts, max_rank, static_cast<int32_t *>(ranks),
-                            static_cast<float *>(ap), static_cast<int32_t *>(first),
-                            static_cast<int32_t *>(cmcd));
-  if (rc) return rc;
-  return finish_on_host(ctx, plan, static_cast<int32_t *>(ranks), static_cast<float *>(ap),
-                        static_cast<int32_t *>(first), static_cast<int32_t *>(cmcd), max_rank,
-                        accum_mode, cmc, mAP, ap_opt, first_rank_opt, num_valid_opt);
+  return finish_on_host(ctx, plan, static_cast<int32_t *>(ranks), ap, first, cmcd, max_rank, accum_mode,
+                        cmc, mAP, ap_opt, first_rank_opt, num_valid_opt);
 }
 
 // ---------------------------------------------------------------------------

@@ -63,6 +63,8 @@ def canonicalize_labels(q, g):
     passed as ``queries[:,1]``, ``gallery[:,1]`` (pid) and ``[:,2]`` (camid)."""
     q = np.asarray(q).reshape(-1)
     g = np.asarray(g).reshape(-1)
+    if q.dtype == np.int32 and g.dtype == np.int32:
+        return np.ascontiguousarray(q), np.ascontiguousarray(g)
     if q.dtype.kind in "iu" and g.dtype.kind in "iu" and q.size + g.size > 0:
         lo = min(q.min(initial=0), g.min(initial=0))
         hi = max(q.max(initial=0), g.max(initial=0))

@@ -112,3 +112,30 @@ def test_msmt17_validator_balanced_accuracy(capsys):
     tm = vids == top
     ref = np.mean([tm[vids == l].mean() for l in np.unique(vids)])
     assert acc == pytest.approx(ref, abs=1e-12)
+
+
+def test_device_feature_sink_equals_reference_loop():
+    """the device-resident sink returns exactly what the reference's host loop
+    (getFeatures.py:56-67: model(batch.cuda()).cpu() + torch.cat) returns, and feeds
+    validate()'s fused call without a host round trip."""
+    from torch.utils.data import DataLoader, TensorDataset
+    from daliid_b200 import getFeatures as gf_mod, metrics
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(1037, 24, generator=g)
+    model = torch.nn.Sequential(torch.nn.Linear(24, 96), torch.nn.ReLU(), torch.nn.Linear(96, 40)).cuda()
+    loader = DataLoader(TensorDataset(x), batch_size=100)
+    dev = gf_mod.extract_features_to_device(loader, model, 0)
+    ref = []
+    model.eval()
+    with torch.no_grad():
+        for (batch,) in loader:
+            fvs = model(batch.cuda(0)).data.cpu()
+            ref = fvs if len(ref) == 0 else torch.cat((ref, fvs), 0)
+    assert dev.is_cuda and dev.shape == (1037, 40) and torch.equal(dev.cpu(), ref)
+    qp = np.arange(37, dtype=np.int32) % 9
+    gp = np.arange(1000, dtype=np.int32) % 9
+    qc = np.zeros(37, dtype=np.int32)
+    gc = np.ones(1000, dtype=np.int32)
+    a = metrics.evaluate_features(dev[:37].contiguous(), dev[37:].contiguous(), qp, gp, qc, gc)
+    b = metrics.evaluate_features(ref[:37].contiguous(), ref[37:].contiguous(), qp, gp, qc, gc)
+    assert np.array_equal(a[0], b[0]) and a[1] == b[1]
