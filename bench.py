@@ -93,18 +93,27 @@ class ClockSampler:
 
 
 def make_workload(name, rank, world, device):
-    """Queries are shared by every rank (same seed); each rank draws its own gallery slab."""
+    """Queries are shared by every rank (same seed); each rank draws its own gallery slab.
+
+    Weak scaling: the gallery grows by one Market-sized slab per GPU and its identity space
+    grows with it (n_ids x world identities, as a larger gallery has more people, not more
+    images per person), so a query keeps ~21 same-identity gallery items whatever the number
+    of slabs and the per-GPU work is fixed.  Queries carry identities of the first n_ids."""
     from daliid_b200 import synth
     cfg = dict(synth.CONFIGS[name])
     Q, G, D = cfg["Q"], cfg["G"], cfg["D"]
-    q_pid, _, q_cam, _ = synth.make_labels(Q, G, cfg["n_ids"], cfg["n_cams"], seed=12)
+    n_ids = cfg["n_ids"]
+    q_pid, _, q_cam, _ = synth.make_labels(Q, G, n_ids, cfg["n_cams"], seed=12)
     gen = torch.Generator().manual_seed(12)
-    centers = torch.randn(cfg["n_ids"], D, generator=gen)
+    centers = torch.randn(n_ids, D, generator=gen)
     qf = centers[torch.from_numpy(q_pid).long()] + cfg["sigma"] * torch.randn(Q, D, generator=gen)
+    if world > 1:  # identities that only exist in the (larger) gallery
+        gen2 = torch.Generator().manual_seed(13)
+        centers = torch.cat([centers, torch.randn(n_ids * (world - 1), D, generator=gen2)])
     slabs = []
     for r in range(world):
         g = torch.Generator().manual_seed(1000 + r)
-        pid = torch.randint(0, cfg["n_ids"], (G,), generator=g)
+        pid = torch.randint(0, n_ids * world, (G,), generator=g)
         cam = torch.randint(0, cfg["n_cams"], (G,), generator=g)
         slabs.append((pid.numpy().astype(np.int32), cam.numpy().astype(np.int32)))
     g = torch.Generator().manual_seed(2000 + rank)
@@ -168,6 +177,41 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------
+def measure_c5(dev, rank, world, dist):
+    """BASELINE config 5 beside the headline: 100k queries x 125k gallery rows PER GPU (1M at 8
+    GPUs), D=512, fused distance + top-20 (the Q x G matrix is never written), per-slab top-k
+    all-gathered and merged.  Device-resident synthetic features, 3 timed evaluations."""
+    from daliid_b200 import sharded
+    Q, Gs, D, k = 100000, 125000, 512, 20
+    gq = torch.Generator(device=dev).manual_seed(12)
+    qf = torch.randn(Q, D, generator=gq, device=dev)
+    gg = torch.Generator(device=dev).manual_seed(1000 + rank)
+    gf = torch.randn(Gs, D, generator=gg, device=dev)
+    for _ in range(2):
+        sharded.topk_features_sharded(qf, gf, rank * Gs, k=k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 3
+    e0.record()
+    for _ in range(n):
+        v, i = sharded.topk_features_sharded(qf, gf, rank * Gs, k=k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    del qf, gf
+    tf = 2.0 * Q * Gs * D / (ms * 1e-3) / 1e12
+    return {"workload": f"Q={Q} x G={Gs}/GPU (global {Gs * world}) x D={D}, fused distance + top-{k}, f16x3",
+            "ms_per_eval": ms, "pairs_per_s": Q * Gs * world / (ms * 1e-3), "tflops_per_gpu": tf,
+            "frac_of_bf16_peak": tf / peaks()["bf16"], "frac_ceiling": 1.0 / 3.0,
+            "scaling": "weak (one 125k slab per GPU)"}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from daliid_b200 import _lib, metrics, sharded
@@ -305,6 +349,10 @@ def run_ours(args):
                   ", ".join(f"{k}={v[0] * 100:.3f}/{v[1] * 100:.3f}" for k, v in acc.items()),
                   file=sys.stderr, flush=True)
 
+    c5 = None
+    if not args.no_c5:
+        c5 = measure_c5(dev, rank, world, dist)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -335,6 +383,8 @@ def run_ours(args):
         "data": "synthetic (seed 12, class centres + gaussian noise; no datasets offline)",
         "config": {"workload": f"{WORKLOAD}: Q={Q} x G={G}/GPU x D={D}, cosine, precision={prec}",
                    "global_gallery": G * world, "parallelism": f"gallery-sharded x{world}",
+                   "weak_scaling": "one Market-sized slab per GPU; gallery identities = 751 x n_gpus "
+                                   "(positives per query constant)",
                    "l2": "inputs larger than L2 (features 158 MB + operand planes 315 MB + distmat "
                          "214 MB per step vs 126 MB L2); no explicit flush"},
         "clocks": clocks,
@@ -347,6 +397,8 @@ def run_ours(args):
         "kernel_ms_per_step": {k: v[1] / args.steps for k, v in ktimes.items() if v[0]},
         "mAP": mAP, "rank1": float(cmc[0]),
     }
+    if c5:
+        line["c5_faceid_1toN"] = c5
     if world == 1 and not args.no_cpu_baseline:
         from oracle import c_oracle
         c_oracle.build()
@@ -372,6 +424,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="f16x3", choices=["fp32", "tf32x3", "tf32c", "tf32", "f16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the config-5 (1:N top-k) side measurement")
     ap.add_argument("--breakdown", action="store_true", help="diagnostic per-phase host timing (stderr)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -167,7 +167,7 @@ def normalize(x, return_norms=False):
 
 
 def compute_distance_matrix(input1, input2, metric="cosine", precision=DEFAULT_PRECISION,
-                            normalize=None, out=None, device=None):
+                            normalize=None, out=None, device=None, padded=False):
     """``[Q,G]`` fp32 distance matrix between feature rows.
 
     ``metric``: ``cosine`` (``1 - q.g`` on L2-normalised rows), ``sqeuclidean`` (what
@@ -176,7 +176,10 @@ def compute_distance_matrix(input1, input2, metric="cosine", precision=DEFAULT_P
     The result lives where the inputs live (CUDA tensor in, CUDA tensor out) unless ``out``
     (a contiguous float32 CUDA tensor or numpy array) or ``device`` (a CUDA ordinal: host
     features are streamed to the GPU in chunks overlapped with compute, the matrix stays
-    there) says otherwise."""
+    there) says otherwise.  ``padded=True`` (CUDA results only) returns a ``[Q,G]`` view of a
+    matrix whose rows are padded to a multiple of 4 floats: 16-byte aligned rows let the
+    contraction store its tiles through TMA (the reference's contiguous layout with an odd G,
+    e.g. 15913, cannot)."""
     a = as_matrix(input1, np.float32, "input1")
     b = as_matrix(input2, np.float32, "input2")
     if a.shape[1] != b.shape[1]:
@@ -200,8 +203,13 @@ def compute_distance_matrix(input1, input2, metric="cosine", precision=DEFAULT_P
     else:
         if dev is None and device is not None:
             dev = int(device)
-        out, optr = _alloc_out((Q, G), dev)
-        ld = G
+        if padded and dev is not None and G % 4:
+            ld = (G + 3) // 4 * 4
+            buf, optr = _alloc_out((Q, ld), dev)
+            out = buf[:, :G]
+        else:
+            out, optr = _alloc_out((Q, G), dev)
+            ld = G
     ctx = get_ctx(dev)
     ctx.attach_torch_stream()
     if Q and G:

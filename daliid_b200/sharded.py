@@ -42,7 +42,7 @@ class CudaOps:
         # host features are streamed in (chunked H2D overlapped with compute); the slab
         # matrix always stays on this rank's GPU
         return metrics.compute_distance_matrix(qf, gf_slab, metric, precision, normalize,
-                                               device=self.ctx.device)
+                                               device=self.ctx.device, padded=True)
 
     def plan(self, q_pid, g_pid, q_cam, g_cam):
         self.ctx.attach_torch_stream()
