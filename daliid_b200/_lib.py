@@ -61,6 +61,8 @@ _SIGNATURES = {
     "dali_ctx_timing_read": (ci, [c_vp, ci, ctypes.POINTER(ci), c_f32p]),
     "dali_ctx_launch_count": (i64, [c_vp]),
     "dali_ctx_fallback_count": (i64, [c_vp]),
+    "dali_ctx_plan_cache_enable": (ci, [c_vp, ci]),
+    "dali_ctx_plan_cache_hits": (i64, [c_vp]),
     "dali_normalize_f32": (ci, [c_vp, c_vp, i64, i64, i64, c_vp, i64, c_vp]),
     "dali_distmat_f32": (ci, [c_vp, c_vp, i64, c_vp, i64, i64, ci, ci, ci, c_vp, i64]),
     "dali_fuse_f32": (ci, [c_vp, ctypes.POINTER(c_vp), ci, ctypes.POINTER(c_vp),
@@ -165,6 +167,12 @@ class Context:
 
     def fallback_count(self):
         return int(self.lib.dali_ctx_fallback_count(self.h))
+
+    def plan_cache_enable(self, on=True):
+        self.check(self.lib.dali_ctx_plan_cache_enable(self.h, 1 if on else 0))
+
+    def plan_cache_hits(self):
+        return int(self.lib.dali_ctx_plan_cache_hits(self.h))
 
 
 _tls = threading.local()

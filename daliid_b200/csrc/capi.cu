@@ -447,6 +447,11 @@ void dali_ctx_destroy(dali_ctx *ctx) {
     cudaEventDestroy(pe.second.second);
   }
   for (auto e : ctx->t_pool) cudaEventDestroy(e);
+  if (ctx->cached_plan) {
+    dali_rank_plan *c = ctx->cached_plan;
+    ctx->cached_plan = nullptr;
+    dali_rank_plan_destroy(c);
+  }
   for (auto &b : ctx->ws)
     if (b.p) cudaFree(b.p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -496,6 +501,17 @@ int dali_ctx_timing_read(dali_ctx *ctx, int which, int *launches, float *total_m
 
 int64_t dali_ctx_launch_count(dali_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int64_t dali_ctx_fallback_count(dali_ctx *ctx) { return ctx ? ctx->fallbacks : 0; }
+int64_t dali_ctx_plan_cache_hits(dali_ctx *ctx) { return ctx ? ctx->plan_cache_hits : 0; }
+int dali_ctx_plan_cache_enable(dali_ctx *ctx, int on) {
+  if (!ctx) return DALI_ERR_INVALID;
+  ctx->plan_cache = on != 0;
+  if (!on && ctx->cached_plan) {
+    dali_rank_plan *c = ctx->cached_plan;
+    ctx->cached_plan = nullptr;
+    dali_rank_plan_destroy(c);
+  }
+  return DALI_OK;
+}
 
 // ---------------------------------------------------------------------------
 int dali_normalize_f32(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx, float *out,
@@ -711,6 +727,22 @@ int dali_rank_plan_create(dali_ctx *ctx, const int32_t *q_pid, const int32_t *g_
     return set_err(ctx, DALI_ERR_INVALID, "rank plan: bad arguments");
   if (G > INT32_MAX || Q > INT32_MAX) return set_err(ctx, DALI_ERR_UNSUPPORTED, "Q or G exceeds 2^31");
   *out = nullptr;
+  static const char *env_cache = getenv("DALI_PLAN_CACHE");
+  const bool use_cache = ctx->plan_cache && !(env_cache && atoi(env_cache) == 0);
+  if (use_cache && ctx->cached_plan) {
+    dali_rank_plan *c = ctx->cached_plan;
+    if (c->Q == Q && c->G == G &&
+        (Q == 0 || (std::memcmp(c->labels.data(), q_pid, sizeof(int32_t) * Q) == 0 &&
+                    std::memcmp(c->labels.data() + Q + G, q_cam, sizeof(int32_t) * Q) == 0)) &&
+        (G == 0 || (std::memcmp(c->labels.data() + Q, g_pid, sizeof(int32_t) * G) == 0 &&
+                    std::memcmp(c->labels.data() + 2 * Q + G, g_cam, sizeof(int32_t) * G) == 0))) {
+      if (c->ready) DALI_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, c->ready, 0));
+      c->refs++;
+      ctx->plan_cache_hits++;
+      *out = c;
+      return DALI_OK;
+    }
+  }
   // ---- host part: gallery CSR by identity (counting sort) + per-query ranges -------------
   // identities are looked up through `start` (dense ids) or a sorted copy (sparse ids)
   int32_t pmin = 0, pmax = -1;
@@ -828,13 +860,32 @@ int dali_rank_plan_create(dali_ctx *ctx, const int32_t *q_pid, const int32_t *g_
     dali_rank_plan_destroy(p);
     return rc;
   }
+  if (use_cache) {  // keep it for the next call with the same labels
+    p->labels.resize(2 * (Q + G));
+    if (Q) {
+      std::memcpy(p->labels.data(), q_pid, sizeof(int32_t) * Q);
+      std::memcpy(p->labels.data() + Q + G, q_cam, sizeof(int32_t) * Q);
+    }
+    if (G) {
+      std::memcpy(p->labels.data() + Q, g_pid, sizeof(int32_t) * G);
+      std::memcpy(p->labels.data() + 2 * Q + G, g_cam, sizeof(int32_t) * G);
+    }
+    if (cudaEventCreateWithFlags(&p->ready, cudaEventDisableTiming) == cudaSuccess)
+      cudaEventRecord(p->ready, ctx->stream);
+    dali_rank_plan *old = ctx->cached_plan;
+    ctx->cached_plan = p;
+    p->refs++;
+    if (old) dali_rank_plan_destroy(old);
+  }
   *out = p;
   return DALI_OK;
 }
 
 void dali_rank_plan_destroy(dali_rank_plan *plan) {
   if (!plan) return;
+  if (--plan->refs > 0) return;
   if (plan->d_block) cudaFreeAsync(plan->d_block, plan->ctx->stream);
+  if (plan->ready) cudaEventDestroy(plan->ready);
   delete plan;
 }
 

@@ -81,6 +81,8 @@ enum WsSlot {
 
 }  // namespace dali
 
+struct dali_rank_plan;
+
 struct dali_ctx {
   int device = 0;
   int num_sms = 0;
@@ -103,6 +105,12 @@ struct dali_ctx {
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> t_pending;
   std::vector<cudaEvent_t> t_pool;
   float t_ms[DALI_K_COUNT_] = {0};
+  // rank-plan cache: the plan depends on the label arrays only, and evaluation code calls the
+  // path many times with the same query / gallery sets.  The last plan is kept and
+  // reused when the next call's labels compare equal byte for byte.
+  dali_rank_plan *cached_plan = nullptr;
+  bool plan_cache = true;
+  int64_t plan_cache_hits = 0;
   int64_t launches = 0;
   int64_t fallbacks = 0;  // fused calls that had to be redone through the materialised path
   // tensor-map encoder (driver entry point, resolved lazily)
@@ -111,6 +119,9 @@ struct dali_ctx {
 
 struct dali_rank_plan {
   dali_ctx *ctx = nullptr;
+  int refs = 1;                       // the creator, plus the context's cache while it holds it
+  std::vector<int32_t> labels;        // q_pid | g_pid | q_cam | g_cam as passed (cache key)
+  cudaEvent_t ready = nullptr;        // device image complete (expansion kernel done)
   int64_t Q = 0, G = 0, M = 0;
   int max_m = 0;   // largest number of matches (same identity) of one query
   int max_nv = 0;  // upper bound of the valid positives of one query (== max_m; the exact

@@ -103,6 +103,14 @@ int64_t dali_ctx_launch_count(dali_ctx *ctx);
 /* Number of fused calls (dali_topk_features_f32) that overflowed their candidate lists and were
  * redone through the materialised distance matrix (same result, slower). */
 int64_t dali_ctx_fallback_count(dali_ctx *ctx);
+/* Rank-plan cache.  The plan (gallery index by identity + per-query match lists) depends on the
+ * four label arrays only; evaluation code calls the path again and again with the same query and
+ * gallery sets (mainKIT.py:154-163 twice per epoch, evaluateCleanATModels.py 7 times per run).
+ * The context keeps the last plan and reuses it when the next call's labels are byte-for-byte
+ * equal (compared in full on every call).  Enabled by default; DALI_PLAN_CACHE=0 in the
+ * environment or dali_ctx_plan_cache_enable(ctx, 0) turn it off. */
+int dali_ctx_plan_cache_enable(dali_ctx *ctx, int on);
+int64_t dali_ctx_plan_cache_hits(dali_ctx *ctx);
 
 /* ---- a1: row L2 normalisation -------------------------------------------- */
 /* out[i,:] = x[i,:] / ||x[i,:]||  (no eps: a zero row yields NaN, as the reference does)

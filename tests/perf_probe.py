@@ -47,6 +47,27 @@ def main():
         d2 = d.clone()
         ms, _ = timeit(lambda: metrics.fuse_distmats([d, d2]))
         print(f"{what} fuse 2: {ms:.3f} ms -> {12 * Q * G / ms / 1e6:.0f} GB/s", flush=True)
+    elif what == "plan":
+        # host cost of the rank plan for an 8-slab global gallery (the sharded path builds it on
+        # every rank and every step)
+        import numpy as np
+        from daliid_b200 import sharded
+        ops = sharded.CudaOps(0)
+        for world in (1, 8):
+            G, Q = 15913 * world, 3368
+            rng = np.random.default_rng(0)
+            gp = rng.integers(0, 751 * world, G).astype(np.int32); gc = rng.integers(0, 6, G).astype(np.int32)
+            qp = rng.integers(0, 751, Q).astype(np.int32); qc = rng.integers(0, 6, Q).astype(np.int32)
+            for _ in range(3):
+                ops.plan_destroy(ops.plan(qp, gp, qc, gc))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(20):
+                pl = ops.plan(qp, gp, qc, gc)
+                ops.plan_destroy(pl)
+            t1 = time.perf_counter()
+            torch.cuda.synchronize()
+            print(f"plan create+destroy, G={G}: {(t1 - t0) / 20 * 1e3:.3f} ms host per call", flush=True)
     elif what == "faceid_slab":
         # BASELINE config 5 as one of 8 GPUs sees it: all 100k queries against a 125k gallery slab
         Q, G, D = 100000, 125000, 512

@@ -124,3 +124,38 @@ def test_sharded_building_blocks_equal_unsharded():
         ops.plan_destroy(plan)
         assert np.array_equal(cmc, e[0]) and mAP == e[1], world
         assert np.array_equal(det["first_rank"], e[3])
+
+
+def test_plan_cache_reuses_only_identical_labels():
+    """The context keeps the last rank plan and reuses it when the labels are byte-for-byte
+    equal; any change in any of the four arrays rebuilds it (results checked against the oracle
+    either way)."""
+    from daliid_b200 import _lib, metrics
+    rng = np.random.default_rng(4)
+    Q, G = 40, 500
+    d = rng.random((Q, G), dtype=np.float32)
+    qp = rng.integers(0, 7, Q).astype(np.int32); gp = rng.integers(0, 7, G).astype(np.int32)
+    qc = rng.integers(0, 3, Q).astype(np.int32); gc = rng.integers(0, 3, G).astype(np.int32)
+    ctx = _lib.get_ctx(0)
+    ctx.plan_cache_enable(True)
+    h0 = ctx.plan_cache_hits()
+    a = metrics.evaluate_rank(d, qp, gp, qc, gc)
+    b = metrics.evaluate_rank(d * 0.5 + 0.1, qp.copy(), gp.copy(), qc.copy(), gc.copy())
+    assert ctx.plan_cache_hits() == h0 + 1          # second call: same labels, other distances
+    e = ro.evaluate_rank(d, qp, gp, qc, gc)
+    assert np.array_equal(a[0], e[0]) and a[1] == e[1]
+    assert np.array_equal(b[0], e[0]) and b[1] == e[1]   # monotone map of d: same ranking
+    for arr in (qp, gp, qc, gc):                    # one changed label anywhere: rebuilt
+        old = arr[-1]
+        arr[-1] = old + 1
+        h = ctx.plan_cache_hits()
+        r = metrics.evaluate_rank(d, qp, gp, qc, gc)
+        assert ctx.plan_cache_hits() == h
+        e = ro.evaluate_rank(d, qp, gp, qc, gc)
+        assert np.array_equal(r[0], e[0]) and r[1] == e[1]
+        arr[-1] = old
+    ctx.plan_cache_enable(False)
+    h = ctx.plan_cache_hits()
+    metrics.evaluate_rank(d, qp, gp, qc, gc); metrics.evaluate_rank(d, qp, gp, qc, gc)
+    assert ctx.plan_cache_hits() == h
+    ctx.plan_cache_enable(True)
