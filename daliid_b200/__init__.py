@@ -7,10 +7,11 @@ kernels (``include/daliid_b200.h``).  See DESIGN.md and INTEGRATION.md.
 """
 from .metrics import (canonicalize_labels, compute_distance_matrix, evaluate_features,
                       evaluate_rank, evaluate_rank_detailed, fuse_distmats, normalize,
-                      topk_features, topk_identify)
+                      re_ranking, topk_features, topk_identify)
 
 __all__ = [
     "canonicalize_labels", "compute_distance_matrix", "evaluate_features", "evaluate_rank",
-    "evaluate_rank_detailed", "fuse_distmats", "normalize", "topk_features", "topk_identify",
+    "evaluate_rank_detailed", "fuse_distmats", "normalize", "re_ranking", "topk_features",
+    "topk_identify",
 ]
 __version__ = "0.1.0"

@@ -1070,6 +1070,39 @@ int dali_topk_f32(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_
 
 // a7 from features, materialised: the gallery is processed in one slab through an internal
 // [band, G] matrix per query band (bounded workspace); each band owns its rows.
+int dali_rerank_f32(dali_ctx *ctx, const float *qg, int64_t ld_qg, const float *qq, int64_t ld_qq,
+                    const float *gg, int64_t ld_gg, int64_t Q, int64_t G, int k1, int k2,
+                    double lambda_value, float *out, int64_t ld_out) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (Q < 0 || G < 0 || !out || (Q && G && (!qg || !qq || !gg)) || ld_qg < G || ld_qq < Q || ld_gg < G ||
+      ld_out < G)
+    return set_err(ctx, DALI_ERR_INVALID, "re_ranking: bad shape or null pointer");
+  if (Q == 0 || G == 0) return DALI_OK;
+  const float *dqg, *dqq, *dgg;
+  int64_t l1, l2, l3;
+  if ((rc = stage_in(ctx, WS_STAGE_A, qg, Q, G, ld_qg, &dqg, &l1))) return rc;
+  if ((rc = stage_in(ctx, WS_STAGE_B, qq, Q, Q, ld_qq, &dqq, &l2))) return rc;
+  if ((rc = stage_in(ctx, WS_STAGE_C, gg, G, G, ld_gg, &dgg, &l3))) return rc;
+  const bool odev = is_device_ptr(out);
+  float *od = out;
+  int64_t ldo = ld_out;
+  if (!odev) {
+    void *t;
+    ldo = G;
+    if ((rc = ws_ensure(ctx, WS_DIST, sizeof(float) * Q * G, &t))) return rc;
+    od = static_cast<float *>(t);
+  }
+  rc = launch_rerank(ctx, dqg, l1, dqq, l2, dgg, l3, Q, G, k1, k2, lambda_value, od, ldo);
+  if (rc) return rc;
+  if (!odev) {
+    DALI_CUDA_OK(ctx, cudaMemcpy2DAsync(out, sizeof(float) * ld_out, od, sizeof(float) * ldo, sizeof(float) * G,
+                                        Q, cudaMemcpyDeviceToHost, ctx->stream));
+    DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return DALI_OK;
+}
+
 static int topk_features_unfused(dali_ctx *ctx, const Prepared &b, const float *q, int64_t Q, int64_t G,
                                  int64_t D, int metric, int precision, int normalize, int k,
                                  int largest, int32_t g_base, float *d_out, int32_t *i_out) {

@@ -76,6 +76,13 @@ enum WsSlot {
   WS_CAND_CNT,  // [Q] int32
   WS_THR,       // [Q] fp32 running k-th best distance
   WS_FLAG,      // overflow flag
+  WS_RR_OD,     // re-ranking: normalised squared [N,N] matrix
+  WS_RR_MISC,
+  WS_RR_RANK,
+  WS_RR_V0,
+  WS_RR_V,
+  WS_RR_CSC,
+  WS_RR_TEMP,
   WS_COUNT_
 };
 
@@ -201,6 +208,10 @@ int launch_topk(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t 
 int launch_topk_compact(dali_ctx *ctx, uint64_t *cand, int32_t *cand_cnt, float *thr, int64_t Q,
                         int cap, int k, int largest, int fixed_cnt, int32_t *overflow, float *d_out,
                         int32_t *i_out);
+// rerank.cu
+int launch_rerank(dali_ctx *ctx, const float *qg, int64_t ld_qg, const float *qq, int64_t ld_qq,
+                  const float *gg, int64_t ld_gg, int64_t Q, int64_t G, int k1, int k2, double lambda,
+                  float *out, int64_t ld_out);
 // fuse.cu
 int launch_fuse(dali_ctx *ctx, const float *const *d_ptrs_dev, int n, const float *const *wq_dev,
                 const float *const *wg_dev, float *out, int64_t Q, int64_t G, int64_t ld);

@@ -33,6 +33,7 @@ from . import _lib
 from ._lib import ACCUMS, METRICS, PRECISIONS, as_i32, as_matrix, c_vp, get_ctx, p_i32
 
 __all__ = [
+    "re_ranking",
     "canonicalize_labels",
     "evaluate_rank",
     "evaluate_rank_detailed",
@@ -308,6 +309,30 @@ def topk_features(qf, gf, k=20, metric="cosine", precision=DEFAULT_PRECISION, no
             _precision(precision, normalize), 1 if normalize else 0, int(k),
             1 if largest else 0, int(g_base), c_vp(vptr), c_vp(iptr)))
     return vals, idx
+
+
+def re_ranking(q_g_dist, q_q_dist, g_g_dist, k1=20, k2=6, lambda_value=0.3):
+    """k-reciprocal re-ranking with ``torchreid.utils.re_ranking``'s signature: the hook the
+    reference keeps commented out after every distance matrix (validateModels.py:49-53,
+    evaluate.py:294-298, evaluate_ensembled_models.py:284-288,303-307).
+
+    ``q_g_dist`` [Q,G], ``q_q_dist`` [Q,Q], ``g_g_dist`` [G,G]; returns the re-ranked ``[Q,G]``
+    float32 matrix where the inputs live (numpy in, numpy out; CUDA tensor in, CUDA tensor out)."""
+    a = as_matrix(q_g_dist, np.float32, "q_g_dist")
+    b = as_matrix(q_q_dist, np.float32, "q_q_dist")
+    c = as_matrix(g_g_dist, np.float32, "g_g_dist")
+    Q, G = a.shape
+    if b.shape != (Q, Q) or c.shape != (G, G):
+        raise ValueError("q_q_dist must be [Q,Q] and g_g_dist [G,G]")
+    if len({a.device, b.device, c.device}) != 1:
+        raise ValueError("the three matrices must live on the same device (or all on the host)")
+    ctx = _ctx_for(a, b, c)
+    out, optr = _alloc_out((Q, G), a.device)
+    if Q and G:
+        ctx.check(ctx.lib.dali_rerank_f32(ctx.h, c_vp(a.ptr), max(a.ld, 1), c_vp(b.ptr), max(b.ld, 1),
+                                          c_vp(c.ptr), max(c.ld, 1), Q, G, int(k1), int(k2),
+                                          float(lambda_value), c_vp(optr), max(G, 1)))
+    return out
 
 
 def evaluate_features(qf, gf, q_pids, g_pids, q_camids, g_camids, metric="cosine",

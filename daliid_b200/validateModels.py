@@ -50,6 +50,25 @@ class validateModels:
         queries_fvs = self.feature_extractor(queries, self.img_height, self.img_width, model, 500, self.gpu_index)
         gallery_fvs = self.feature_extractor(gallery, self.img_height, self.img_width, model, 500, self.gpu_index)
 
+        if getattr(self, "rerank", False):
+            # the reference's commented-out hook, live here (validateModels.py:49-53): torchreid's
+            # "euclidean" is the squared distance; features are L2-normalised first (41-42)
+            print('Applying person re-ranking ...')
+            qn = metrics.normalize(queries_fvs)
+            gn = metrics.normalize(gallery_fvs)
+            distmat = metrics.compute_distance_matrix(qn, gn, "cosine", precision=self.precision,
+                                                      normalize=True)
+            distmat_qq = metrics.compute_distance_matrix(qn, qn, "sqeuclidean", precision=self.precision,
+                                                         normalize=True)
+            distmat_gg = metrics.compute_distance_matrix(gn, gn, "sqeuclidean", precision=self.precision,
+                                                         normalize=True)
+            distmat = metrics.re_ranking(distmat, distmat_qq, distmat_gg)
+            del queries_fvs, gallery_fvs, distmat_qq, distmat_gg
+            cmc, mAP = self.calculateMetrics(distmat, queries, gallery)
+            if not isinstance(distmat, torch.Tensor):
+                distmat = torch.from_numpy(distmat)
+            return cmc, mAP, distmat
+
         # normalise -> 1 - q.g -> rank -> CMC/mAP, one library call (validateModels.py:41-69)
         print('Computing CMC and mAP ...')
         cmc, mAP, distmat = metrics.evaluate_features(

@@ -94,7 +94,8 @@ const char *dali_strerror(int code);
 #define DALI_K_TOPK 4
 #define DALI_K_FUSE 5
 #define DALI_K_RANK_GATHER 6
-#define DALI_K_COUNT_ 7
+#define DALI_K_RERANK 7
+#define DALI_K_COUNT_ 8
 int dali_ctx_timing_enable(dali_ctx *ctx, int on);
 int dali_ctx_timing_reset(dali_ctx *ctx);
 int dali_ctx_timing_read(dali_ctx *ctx, int which, int *launches, float *total_ms);
@@ -187,6 +188,17 @@ int dali_topk_f32(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_
 int dali_topk_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float *g, int64_t G,
                            int64_t D, int metric, int precision, int normalize, int k,
                            int largest, int32_t g_base, float *d_out, int32_t *i_out);
+
+/* ---- next row N1: k-reciprocal re-ranking ------------------------------------- */
+/* out[Q,G] = torchreid.utils.re_ranking(qg, qq, gg, k1, k2, lambda_value): the hook the
+ * reference keeps commented out at validateModels.py:49-53, evaluate.py:294-298,
+ * evaluate_ensembled_models.py:284-288,303-307 (flag: validateModels.py:28-31).
+ * qg [Q,G], qq [Q,Q], gg [G,G] fp32 with leading dimensions ld_*; all host or all device; out
+ * [Q,G] (ld_out), host or device.  1 <= k1 <= 28, 1 <= k2 <= min(8, k1+1).  Neighbour sets are
+ * exact (stable tie order); values agree with the numpy form to fp32 rounding. */
+int dali_rerank_f32(dali_ctx *ctx, const float *qg, int64_t ld_qg, const float *qq, int64_t ld_qq,
+                    const float *gg, int64_t ld_gg, int64_t Q, int64_t G, int k1, int k2,
+                    double lambda_value, float *out, int64_t ld_out);
 
 /* ---- (e) gallery-sharded building blocks ------------------------------------ */
 /* One process per GPU holds all Q queries and a contiguous gallery slab

@@ -47,6 +47,24 @@ def main():
         d2 = d.clone()
         ms, _ = timeit(lambda: metrics.fuse_distmats([d, d2]))
         print(f"{what} fuse 2: {ms:.3f} ms -> {12 * Q * G / ms / 1e6:.0f} GB/s", flush=True)
+    elif what == "rerank":
+        # SURVEY 8f N1 at the Market shape: qq / gg / qg from the contraction, then re-ranking
+        qf, gf, qp, gp, qc, gc = synth.make_config("market_vit", device="cuda")
+        Q, G = qf.shape[0], gf.shape[0]
+        qg = metrics.compute_distance_matrix(qf, gf, "cosine")
+        qq = metrics.compute_distance_matrix(qf, qf, "sqeuclidean", normalize=True)
+        gg = metrics.compute_distance_matrix(gf, gf, "sqeuclidean", normalize=True)
+        ctx.timing_enable(True); ctx.timing_reset()
+        ms, out = timeit(lambda: metrics.re_ranking(qg, qq, gg), n=3, warm=1)
+        kt = {k: (v[0], round(v[1], 3)) for k, v in ctx.timing_read().items() if v[0]}
+        ctx.timing_enable(False)
+        c0, m0 = metrics.evaluate_rank(qg, qp, gp, qc, gc)
+        c1, m1 = metrics.evaluate_rank(out, qp, gp, qc, gc)
+        print(f"rerank market_vit N={Q + G}: {ms:.2f} ms per call; kernels (launches, total ms): {kt}; "
+              f"mAP {m0:.4f} -> {m1:.4f}, R1 {c0[0]:.4f} -> {c1[0]:.4f}", flush=True)
+        ms, _ = timeit(lambda: (metrics.compute_distance_matrix(qf, qf, "sqeuclidean", normalize=True),
+                                metrics.compute_distance_matrix(gf, gf, "sqeuclidean", normalize=True)), n=3, warm=1)
+        print(f"qq + gg distance matrices: {ms:.2f} ms", flush=True)
     elif what == "plan":
         # host cost of the rank plan for an 8-slab global gallery (the sharded path builds it on
         # every rank and every step)

@@ -159,3 +159,38 @@ def test_plan_cache_reuses_only_identical_labels():
     metrics.evaluate_rank(d, qp, gp, qc, gc); metrics.evaluate_rank(d, qp, gp, qc, gc)
     assert ctx.plan_cache_hits() == h
     ctx.plan_cache_enable(True)
+
+
+@pytest.mark.parametrize("Q,G,k1,k2,lam", [(23, 90, 8, 3, 0.3), (64, 700, 20, 6, 0.3), (40, 333, 28, 1, 0.5),
+                                           (5, 40, 4, 2, 0.0)])
+def test_re_ranking_matches_oracle(Q, G, k1, k2, lam):
+    """k-reciprocal re-ranking (torchreid.utils.re_ranking's signature) against the
+    restated numpy form.  Neighbour sets are integer work (a wrong member would move a value by
+    ~1e-2); values agree to fp32 rounding -- exp() differs in the last ulp between numpy and CUDA."""
+    import torch
+    from daliid_b200 import metrics
+    from oracle import rerank_oracle as rr
+    g = torch.Generator().manual_seed(Q + G)
+    D = 24
+    cent = torch.randn(11, D, generator=g)
+    q = cent[torch.randint(0, 11, (Q,), generator=g)] + 0.6 * torch.randn(Q, D, generator=g)
+    x = cent[torch.randint(0, 11, (G,), generator=g)] + 0.6 * torch.randn(G, D, generator=g)
+    x[7] = x[3]  # exact duplicates: ties in the neighbour lists
+    q = q / q.norm(dim=1, keepdim=True)
+    x = x / x.norm(dim=1, keepdim=True)
+    sq = lambda a, b: ((a * a).sum(1)[:, None] + (b * b).sum(1)[None, :] - 2.0 * a @ b.T)
+    qg, qq, gg = (1.0 - q @ x.T), sq(q, q), sq(x, x)
+    exp = rr.re_ranking(qg.numpy(), qq.numpy(), gg.numpy(), k1, k2, lam)
+    out = metrics.re_ranking(qg.numpy(), qq.numpy(), gg.numpy(), k1, k2, lam)
+    assert out.dtype == np.float32 and out.shape == (Q, G)
+    assert np.abs(out - exp).max() <= 2e-6
+    out_d = metrics.re_ranking(qg.cuda(), qq.cuda(), gg.cuda(), k1, k2, lam)
+    assert out_d.is_cuda and np.array_equal(out_d.cpu().numpy(), out)
+    if lam == 0.0:
+        return
+    # the re-ranked matrix feeds the evaluator like any other
+    qp = np.arange(Q, dtype=np.int32) % 11
+    gp = np.arange(G, dtype=np.int32) % 11
+    a = metrics.evaluate_rank(out, qp, gp, np.zeros(Q, np.int32), np.ones(G, np.int32))
+    b = ro.evaluate_rank(out, qp, gp, np.zeros(Q, np.int32), np.ones(G, np.int32))
+    assert np.array_equal(a[0], b[0]) and a[1] == b[1]

@@ -130,3 +130,36 @@ def test_briar_hits_match_reference_callsite():
     ref = _meta()["callsites"]["validateBRIAR.calculateMetrics"]
     assert hits == pytest.approx(ref["cmc"], abs=0)
     assert np.array_equal(top.astype(np.int32), np.load(os.path.join(GOLDEN, "tiny_top20.npy")))
+
+
+def _rerank_case(Q=23, G=90, D=16, seed=0):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    cent = torch.randn(9, D, generator=g)
+    q = cent[torch.randint(0, 9, (Q,), generator=g)] + 0.7 * torch.randn(Q, D, generator=g)
+    x = cent[torch.randint(0, 9, (G,), generator=g)] + 0.7 * torch.randn(G, D, generator=g)
+    q = q / q.norm(dim=1, keepdim=True)
+    x = x / x.norm(dim=1, keepdim=True)
+    sq = lambda a, b: ((a * a).sum(1)[:, None] + (b * b).sum(1)[None, :] - 2.0 * a @ b.T).numpy()
+    return (1.0 - q @ x.T).numpy(), sq(q, q), sq(x, x)
+
+
+def test_rerank_oracle_invariants():
+    """The restated k-reciprocal re-ranking (oracle/rerank_oracle.py) is pinned by its own
+    invariants: rows of V sum to one, Jaccard self-distance of a query is 0, lambda = 1 returns the
+    normalised squared input, gallery permutations permute the result."""
+    from oracle import rerank_oracle as rr
+    qg, qq, gg = _rerank_case()
+    Q, G = qg.shape
+    det = rr.re_ranking_details(qg, qq, gg, k1=8, k2=3, lambda_value=0.3)
+    assert det["final"].shape == (Q, G) and det["final"].dtype == np.float32
+    np.testing.assert_allclose(det["V0"].sum(1), 1.0, rtol=1e-5)
+    np.testing.assert_allclose(det["V"].sum(1), 1.0, rtol=1e-5)
+    assert np.all(np.abs(det["jaccard"][np.arange(Q), np.arange(Q)]) < 1e-6)
+    lam1 = rr.re_ranking(qg, qq, gg, k1=8, k2=3, lambda_value=1.0)
+    np.testing.assert_array_equal(lam1, det["original"][:, Q:])
+    perm = np.random.default_rng(1).permutation(G)
+    p = rr.re_ranking(qg[:, perm], qq, gg[np.ix_(perm, perm)], k1=8, k2=3, lambda_value=0.3)
+    np.testing.assert_allclose(p, det["final"][:, perm], atol=2e-6)
+    k2_1 = rr.re_ranking_details(qg, qq, gg, k1=8, k2=1, lambda_value=0.3)
+    np.testing.assert_array_equal(k2_1["V"], k2_1["V0"])
