@@ -207,7 +207,7 @@ int launch_topk(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t 
                 int32_t *i_out);
 int launch_topk_compact(dali_ctx *ctx, uint64_t *cand, int32_t *cand_cnt, float *thr, int64_t Q,
                         int cap, int k, int largest, int fixed_cnt, int32_t *overflow, float *d_out,
-                        int32_t *i_out);
+                        int32_t *i_out, int32_t *row_flags = nullptr);
 // rerank.cu
 int launch_rerank(dali_ctx *ctx, const float *qg, int64_t ld_qg, const float *qq, int64_t ld_qq,
                   const float *gg, int64_t ld_gg, int64_t Q, int64_t G, int k1, int k2, double lambda,

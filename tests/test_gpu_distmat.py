@@ -206,6 +206,41 @@ def test_topk_matches_stable_argsort(k):
     assert np.array_equal(i2.cpu().numpy(), ro.stable_argsort(big)[:, :k].astype(np.int32))
 
 
+@pytest.mark.parametrize("largest", [False, True])
+def test_topk_streaming_long_rows(largest):
+    """Rows of >= 4096 columns take the streaming filter + compaction path; rows whose candidate
+    list overflows (here: values quantised to 9 levels, one row sorted so that every later column
+    is better, a row of NaN / inf) are redone on the device by the one-CTA-per-row kernel.  Equal
+    to the stable argsort prefix in all cases, odd leading dimension included."""
+    from daliid_b200 import metrics
+    rng = np.random.default_rng(21)
+    Q, G = 41, 30011
+    d = rng.random((Q, G)).astype(np.float32)
+    d[1] = np.round(d[1] * 8) / 8                       # massive ties
+    d[2] = np.sort(d[2])[::-1] if not largest else np.sort(d[2])   # every later column is better
+    d[3] = np.nan
+    d[4, ::3] = np.inf
+    d[5, ::5] = -np.inf
+    d[6, 100:200] = np.nan
+    d[7] = 0.25                                          # one value only
+    sign = -1.0 if largest else 1.0
+    dt = torch.from_numpy(d).cuda()
+    for k in (1, 20, 128):
+        v, i = metrics.topk_identify(dt, k=k, largest=largest)
+        if largest:
+            # torch.topk semantics: NaN counts as the largest value, ties by ascending index
+            key = np.where(np.isnan(d), np.inf, d)
+            order = np.argsort(-key, axis=1, kind="stable")[:, :k]
+        else:
+            order = ro.stable_argsort(d)[:, :k]
+        assert np.array_equal(i.cpu().numpy(), order.astype(np.int32)), (largest, k)
+        assert np.array_equal(v.cpu().numpy(), np.take_along_axis(d, order, 1), equal_nan=True)
+    # host matrix with an odd width (unaligned rows)
+    v, i = metrics.topk_identify(d[:, :30001].copy(), k=20, largest=largest)
+    e, ei = metrics.topk_identify(dt[:, :30001].contiguous(), k=20, largest=largest)
+    assert np.array_equal(i, ei.cpu().numpy()) and np.array_equal(v, e.cpu().numpy(), equal_nan=True)
+
+
 def test_topk_largest_short_rows_and_merge():
     from daliid_b200 import metrics
     rng = np.random.default_rng(9)
