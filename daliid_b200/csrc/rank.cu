@@ -214,12 +214,15 @@ __device__ __noinline__ uint32_t bucket_exact(const uint64_t *T, uint32_t base, 
 
 // kV2Threads = 256 for few thresholds; 128 when a query has many positives (DeepChange: ~120),
 // where zeroing and reducing n x threads private counters is a large share of the CTA's work.
-template <int LOG2NB, int kV2Threads>
+// BYTEC: 8-bit private counters (a thread must then see <= 255 elements: the launcher splits the
+// row accordingly), rows of counters skewed by 4 bytes so that lanes hitting different buckets
+// spread over the banks.  Halves the shared memory of a many-threshold CTA again.
+template <int LOG2NB, int kV2Threads, bool BYTEC>
 __global__ void __launch_bounds__(kV2Threads)
 rank_count_v2_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int64_t Gs,
                      const int64_t *__restrict__ off, const int32_t *__restrict__ nvalid,
                      const int32_t *__restrict__ gid, const uint32_t *__restrict__ keys,
-                     int32_t *__restrict__ counts, int nsplit) {
+                     int32_t *__restrict__ counts, int nsplit, int tchunk) {
   constexpr int NB = 1 << LOG2NB;
   extern __shared__ __align__(16) uint8_t smem_v2[];
   uint64_t *Tu = reinterpret_cast<uint64_t *>(smem_v2);            // [256] unsorted
@@ -228,13 +231,15 @@ rank_count_v2_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
   uint16_t *orig = reinterpret_cast<uint16_t *>(hist + 256);       // [256]
   uint16_t *lut = orig + 256;                                      // [NB + 8], entry NB = "above all"
   uint16_t *cnt = lut + NB + 8;                                    // [(n + 1) * kV2Threads] private counters
+  uint8_t *cnt8 = reinterpret_cast<uint8_t *>(cnt);                // BYTEC: [(n + 1) * (kV2Threads + 4)]
+  constexpr int RS8 = kV2Threads + 4;                              // skewed row stride in bytes
 
   const int64_t q = blockIdx.x;
   const int chunk = blockIdx.y;
   const int nv = nvalid[q];
-  if (chunk * kV2Chunk >= nv) return;  // uniform exit
-  const int n = min(kV2Chunk, nv - chunk * kV2Chunk);
-  const int64_t o = off[q] + static_cast<int64_t>(chunk) * kV2Chunk;
+  if (chunk * tchunk >= nv) return;  // uniform exit
+  const int n = min(tchunk, nv - chunk * tchunk);
+  const int64_t o = off[q] + static_cast<int64_t>(chunk) * tchunk;
   const int tid = threadIdx.x;
 
   // 1. sort the thresholds by counting (composites are distinct: gallery ids differ)
@@ -276,7 +281,8 @@ rank_count_v2_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
   // 3. zero the private counters (bucket n = "above every threshold" is never counted)
   {
     uint32_t *w = reinterpret_cast<uint32_t *>(cnt);
-    for (int i = tid; i < (n + 1) * (kV2Threads / 2); i += kV2Threads) w[i] = 0u;
+    const int words = BYTEC ? (n + 1) * (RS8 / 4) : (n + 1) * (kV2Threads / 2);
+    for (int i = tid; i < words; i += kV2Threads) w[i] = 0u;
   }
   __syncthreads();
 
@@ -302,7 +308,8 @@ rank_count_v2_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
     const uint32_t e = lut[min(dk >> sh, static_cast<uint32_t>(NB))];
     uint32_t b = e & 0xFFu;
     if (e >= 0x100u) b = bucket_exact(T, b, e >> 8, composite(key, g));  // rare
-    mycnt[b * kV2Threads] += 1;  // row n ("above every threshold") is never read
+    if (BYTEC) cnt8[b * RS8 + tid] += 1;
+    else mycnt[b * kV2Threads] += 1;  // row n ("above every threshold") is never read
   };
 
   const int mis = static_cast<int>((reinterpret_cast<uintptr_t>(row + c0) >> 2) & 3);
@@ -334,7 +341,13 @@ rank_count_v2_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
     const int w = tid >> 5, l = tid & 31;
     for (int b = w; b < n; b += kV2Threads / 32) {
       uint32_t sum;
-      if (kV2Threads == 256) {
+      if (BYTEC) {
+        sum = 0;
+        for (int e = l; e < kV2Threads / 4; e += 32) {
+          const uint32_t x = *reinterpret_cast<const uint32_t *>(cnt8 + b * RS8 + e * 4);
+          sum += (x & 0xFFu) + ((x >> 8) & 0xFFu) + ((x >> 16) & 0xFFu) + (x >> 24);
+        }
+      } else if (kV2Threads == 256) {
         const uint4 x = *reinterpret_cast<const uint4 *>(cnt + b * kV2Threads + l * 8);
         sum = (x.x & 0xFFFFu) + (x.x >> 16) + (x.y & 0xFFFFu) + (x.y >> 16) +
               (x.z & 0xFFFFu) + (x.z >> 16) + (x.w & 0xFFFFu) + (x.w >> 16);
@@ -441,24 +454,25 @@ int launch_rank_gather(dali_ctx *ctx, const dali_rank_plan *plan, const float *d
   return DALI_OK;
 }
 
-static size_t v2_smem_bytes(int log2nb, int nbuckets, int threads) {
-  return 256 * 8 * 2 + 256 * 4 + 256 * 2 + ((size_t(1) << log2nb) + 8) * 2 + size_t(nbuckets + 1) * threads * 2;
+static size_t v2_smem_bytes(int log2nb, int nbuckets, int threads, bool bytec = false) {
+  return 256 * 8 * 2 + 256 * 4 + 256 * 2 + ((size_t(1) << log2nb) + 8) * 2 +
+         (bytec ? size_t(nbuckets + 1) * (threads + 4) : size_t(nbuckets + 1) * threads * 2);
 }
 
-template <int LOG2NB, int THREADS>
+template <int LOG2NB, int THREADS, bool BYTEC = false>
 static int launch_v2(dali_ctx *ctx, dim3 grid, size_t smem, const dali_rank_plan *plan, const float *dist,
                      int64_t ld, int64_t g0, int64_t Gs, const uint32_t *keys, int32_t *counts,
-                     int nsplit) {
+                     int nsplit, int tchunk) {
   static size_t attr = 0;
   if (smem > attr) {
     const size_t want = std::max<size_t>(smem, 48 * 1024);
-    DALI_CUDA_OK(ctx, cudaFuncSetAttribute(rank_count_v2_kernel<LOG2NB, THREADS>,
+    DALI_CUDA_OK(ctx, cudaFuncSetAttribute(rank_count_v2_kernel<LOG2NB, THREADS, BYTEC>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(want)));
     attr = want;
   }
-  rank_count_v2_kernel<LOG2NB, THREADS><<<grid, THREADS, smem, ctx->stream>>>(
-      dist, ld, g0, Gs, plan->d_off, plan->d_nv, plan->d_gid, keys, counts, nsplit);
+  rank_count_v2_kernel<LOG2NB, THREADS, BYTEC><<<grid, THREADS, smem, ctx->stream>>>(
+      dist, ld, g0, Gs, plan->d_off, plan->d_nv, plan->d_gid, keys, counts, nsplit, tchunk);
   return DALI_OK;
 }
 
@@ -468,7 +482,14 @@ int launch_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *di
   DALI_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, sizeof(int32_t) * plan->M, ctx->stream));
   if (plan->max_nv == 0 || Gs == 0) return DALI_OK;
   static const bool use_v1 = getenv("DALI_RANK_V1") != nullptr;  // debugging cross-check only
-  const int per_cta = use_v1 ? kChunk : kV2Chunk;
+  static const char *env_c = getenv("DALI_RANK_CHUNK");
+  static const char *env_t = getenv("DALI_RANK_THREADS");
+  // thresholds per CTA: a query with many positives is split over several CTAs that each stream
+  // the row (re-reads hit L2) -- the private counters of one CTA (n x threads x 2 B) are what
+  // limits the number of resident warps
+  int tchunk = kV2Chunk;
+  if (env_c) tchunk = std::max(8, std::min(kV2Chunk, atoi(env_c)));
+  const int per_cta = use_v1 ? kChunk : tchunk;
   const int nchunk = (plan->max_nv + per_cta - 1) / per_cta;
   if (nchunk > 65535) return set_err(ctx, DALI_ERR_UNSUPPORTED, "too many positives for one query");
   // enough CTAs for >= 4 per SM; never split a row below 4096 columns; a v2 CTA counts in
@@ -478,6 +499,10 @@ int launch_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *di
   const int64_t min_split = (Gs + (4ll << 20) - 1) / (4ll << 20);
   int64_t ns = std::max<int64_t>(1, std::min(want, max_split));
   ns = std::max(ns, min_split);
+  // many thresholds per query: byte counters, so a thread may see at most 255 elements
+  static const char *env_b = getenv("DALI_RANK_BYTE");
+  const bool bytec = !use_v1 && std::min(plan->max_nv, tchunk) > 64 && !(env_b && atoi(env_b) == 0);
+  if (bytec) ns = std::max<int64_t>(ns, (Gs + 250ll * 128 - 1) / (250ll * 128));
   if (ns > 65535) return set_err(ctx, DALI_ERR_UNSUPPORTED, "slab too wide for one launch");
   const int nsplit = static_cast<int>(ns);
   dim3 grid(static_cast<unsigned>(plan->Q), nchunk, nsplit);
@@ -487,17 +512,19 @@ int launch_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *di
                                                               plan->d_nv, plan->d_gid, keys, counts,
                                                               nsplit);
   } else {
-    const int nb = std::min(plan->max_nv, kV2Chunk);
+    const int nb = std::min(plan->max_nv, tchunk);
     // finer table and fewer private counter copies when a query has many thresholds
     int rc;
-    static const char *env_t = getenv("DALI_RANK_THREADS");
     const int force = env_t ? atoi(env_t) : 0;
     if (force == 1128) {
-      rc = launch_v2<11, 128>(ctx, grid, v2_smem_bytes(11, nb, 128), plan, dist, ld, g0, Gs, keys, counts, nsplit);
-    } else if (nb > 64 || force == 128) {
-      rc = launch_v2<12, 128>(ctx, grid, v2_smem_bytes(12, nb, 128), plan, dist, ld, g0, Gs, keys, counts, nsplit);
+      rc = launch_v2<11, 128>(ctx, grid, v2_smem_bytes(11, nb, 128), plan, dist, ld, g0, Gs, keys, counts, nsplit, tchunk);
+    } else if (bytec && force == 0) {
+      rc = launch_v2<12, 128, true>(ctx, grid, v2_smem_bytes(12, nb, 128, true), plan, dist, ld, g0, Gs, keys, counts,
+                                    nsplit, tchunk);
+    } else if (force == 128 || (force == 0 && nb > 64)) {
+      rc = launch_v2<12, 128>(ctx, grid, v2_smem_bytes(12, nb, 128), plan, dist, ld, g0, Gs, keys, counts, nsplit, tchunk);
     } else {
-      rc = launch_v2<11, 256>(ctx, grid, v2_smem_bytes(11, nb, 256), plan, dist, ld, g0, Gs, keys, counts, nsplit);
+      rc = launch_v2<11, 256>(ctx, grid, v2_smem_bytes(11, nb, 256), plan, dist, ld, g0, Gs, keys, counts, nsplit, tchunk);
     }
     if (rc) return rc;
   }
