@@ -373,14 +373,20 @@ def run_ours(args):
     rank_gbs = (4.0 * Q * G) / (ms_rc / max(n_rc, 1) * 1e-3) / 1e9 if n_rc else None
     roofline = {"bound": "tensor", "kernel": "distmat_umma2_kernel" if prec != "fp32" else "distmat_simt_kernel",
                 "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
-                "frac": (achieved / pk["bf16"]) if achieved else None, "traffic": None,
+                "frac": (achieved / pk["bf16"]) if achieved else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this
+                # shape, ncu --set full (profiles/r01d_full.md: 234.8 MB + 188.5 MB); algorithmic
+                # minimum = 161 MB of fp16 operand planes + 214 MB of distance matrix
+                "traffic": 423.3e6 if (prec == "f16x3" and world == 1) else None,
+                "traffic_source": "profiles/r01d_full.md",
                 "peak_source": pk["source"] + " bf16 burst; the fp32-class splits issue several tensor "
                                "passes per algorithmic FLOP: ceiling of frac = 1/3 for f16x3 (three 16-bit "
                                "passes), 1/2 for tf32, 1/4 for tf32c (1 TF32 + 2 bf16 passes), 1/6 for tf32x3",
                 "avg_launch_ms": ms_dm / max(n_dm, 1) if n_dm else None}
     roofline_rank = {"bound": "hbm", "kernel": "rank_count_kernel", "achieved": rank_gbs,
                      "peak": pk["hbm"], "unit": "GB/s", "frac": (rank_gbs / pk["hbm"]) if rank_gbs else None,
-                     "traffic": None, "avg_launch_ms": ms_rc / max(n_rc, 1) if n_rc else None}
+                     "traffic": 218.7e6 if world == 1 else None,  # profiles/r01d_full.md: 215.1 + 3.5 MB
+                     "avg_launch_ms": ms_rc / max(n_rc, 1) if n_rc else None}
 
     line = {
         "metric": METRIC, "value": pairs_per_step * args.steps / (ms * 1e-3), "unit": UNIT,
