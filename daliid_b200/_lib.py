@@ -65,6 +65,13 @@ _SIGNATURES = {
     "dali_ctx_plan_cache_hits": (i64, [c_vp]),
     "dali_normalize_f32": (ci, [c_vp, c_vp, i64, i64, i64, c_vp, i64, c_vp]),
     "dali_distmat_f32": (ci, [c_vp, c_vp, i64, c_vp, i64, i64, ci, ci, ci, c_vp, i64]),
+    "dali_peer_create": (ci, [c_vp, ci, ci, i64, ctypes.POINTER(c_vp)]),
+    "dali_peer_ipc_handle": (ci, [c_vp, c_vp]),
+    "dali_peer_connect": (ci, [c_vp, c_vp]),
+    "dali_peer_destroy": (None, [c_vp]),
+    "dali_peer_capacity": (i64, [c_vp]),
+    "dali_peer_buffer": (c_vp, [c_vp, ci]),
+    "dali_peer_allreduce_i32": (ci, [c_vp, c_vp, ci, c_vp, i64]),
     "dali_rerank_f32": (ci, [c_vp, c_vp, i64, c_vp, i64, c_vp, i64, i64, i64, ci, ci, ctypes.c_double, c_vp, i64]),
     "dali_fuse_f32": (ci, [c_vp, ctypes.POINTER(c_vp), ci, ctypes.POINTER(c_vp),
                            ctypes.POINTER(c_vp), c_vp, i64, i64, i64]),

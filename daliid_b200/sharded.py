@@ -59,23 +59,31 @@ class CudaOps:
     def num_matches(self, plan):
         return int(self.ctx.lib.dali_rank_plan_num_matches(plan))
 
-    def gather_keys(self, plan, dist_slab, g0):
+    def gather_keys(self, plan, dist_slab, g0, out_ptr=None):
+        """Keys of the matches whose gallery item lies in this slab (0 elsewhere).  ``out_ptr``:
+        write into that device buffer (a peer-exchange buffer) instead of a fresh tensor."""
         self.ctx.attach_torch_stream()
         M = self.num_matches(plan)
-        keys = torch.zeros(max(M, 1), dtype=torch.int32, device=self.device)
+        keys = None
+        if out_ptr is None:
+            keys = torch.zeros(max(M, 1), dtype=torch.int32, device=self.device)
+            out_ptr = keys.data_ptr()
         Q, Gs = dist_slab.shape
         self.ctx.check(self.ctx.lib.dali_rank_gather_keys(
             self.ctx.h, plan, c_vp(dist_slab.data_ptr()), max(dist_slab.stride(0), Gs, 1) if Q else max(Gs, 1),
-            g0, Gs, c_vp(keys.data_ptr())))
+            g0, Gs, c_vp(out_ptr)))
         return keys
 
-    def count(self, plan, dist_slab, g0, keys):
+    def count(self, plan, dist_slab, g0, keys, out_ptr=None):
         self.ctx.attach_torch_stream()
-        counts = torch.zeros_like(keys)
+        counts = None
+        if out_ptr is None:
+            counts = torch.zeros_like(keys)
+            out_ptr = counts.data_ptr()
         Q, Gs = dist_slab.shape
         self.ctx.check(self.ctx.lib.dali_rank_count(
             self.ctx.h, plan, c_vp(dist_slab.data_ptr()), max(dist_slab.stride(0), Gs, 1) if Q else max(Gs, 1),
-            g0, Gs, c_vp(keys.data_ptr()), c_vp(counts.data_ptr())))
+            g0, Gs, c_vp(keys.data_ptr()), c_vp(out_ptr)))
         return counts
 
     def finalize(self, plan, keys, counts, Q, G, max_rank, accum):
@@ -111,6 +119,70 @@ def _all_reduce_sum(t, group):
     return t
 
 
+class PeerExchange:
+    """The two exchange steps over NVLink peer memory instead of NCCL (``csrc/peer.cu``).
+
+    Every rank allocates one block (two int32 buffers + flag words), the CUDA IPC handles are
+    exchanged once through ``torch.distributed`` (the plumbing), and from then on an exchange is ONE
+    kernel per rank: signal "my contribution is complete" into every peer's flag word, wait for
+    all peers, sum the peers' buffers with plain loads.  ``gather_keys`` / ``count`` write their
+    contribution straight into the block.  Collective: all ranks of the group make the same calls
+    in the same order.  Single node, world <= 8, CUDA only."""
+
+    def __init__(self, ops, capacity, group=None):
+        self.ops = ops
+        self.group = group
+        self.world, self.rank = _world(group)
+        self.h = c_vp()
+        ctx = ops.ctx
+        ctx.check(ctx.lib.dali_peer_create(ctx.h, self.rank, self.world, int(capacity), ctypes.byref(self.h)))
+        self.capacity = int(ctx.lib.dali_peer_capacity(self.h))
+        mine = ctypes.create_string_buffer(64)
+        ctx.check(ctx.lib.dali_peer_ipc_handle(self.h, mine))
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(mine.raw), group=group)
+            blob = ctypes.create_string_buffer(b"".join(handles), 64 * self.world)
+            ctx.check(ctx.lib.dali_peer_connect(self.h, blob))
+            dist.barrier(group=group)  # every rank has mapped every block before anyone signals
+        self.out = [torch.empty(self.capacity, dtype=torch.int32, device=ops.device) for _ in range(2)]
+
+    def buffer_ptr(self, which):
+        return self.ops.ctx.lib.dali_peer_buffer(self.h, which)
+
+    def allreduce(self, which, n):
+        """Sum over ranks of buffer ``which`` -> a device tensor of ``n`` int32."""
+        ctx = self.ops.ctx
+        ctx.attach_torch_stream()
+        out = self.out[which]
+        ctx.check(ctx.lib.dali_peer_allreduce_i32(ctx.h, self.h, which, c_vp(out.data_ptr()), int(n)))
+        return out[:max(int(n), 1)]
+
+    def close(self):
+        if self.h:
+            if self.world > 1:
+                torch.cuda.synchronize(self.ops.device)
+                dist.barrier(group=self.group)  # nobody unmaps while a peer may still read
+            self.ops.ctx.lib.dali_peer_destroy(self.h)
+            self.h = c_vp()
+
+
+_peer_cache = {}
+
+
+def peer_exchange(ops, need, group=None):
+    """Process-wide PeerExchange for this (device, group); re-created collectively when a larger
+    capacity is needed (``need`` = number of matches, identical on every rank)."""
+    key = (ops.ctx.device, id(group))
+    px = _peer_cache.get(key)
+    if px is None or px.capacity < need:
+        if px is not None:
+            px.close()
+        px = PeerExchange(ops, max(int(need * 1.25), 1 << 16), group)
+        _peer_cache[key] = px
+    return px
+
+
 def gather_gallery_labels(g_pid_slab, g_cam_slab, group=None):
     """All ranks learn the labels of the whole gallery (two int32 vectors; tiny) and the
     slab offsets.  Returns (g_pid_all, g_cam_all, g0_of_this_rank, sizes)."""
@@ -127,7 +199,7 @@ def gather_gallery_labels(g_pid_slab, g_cam_slab, group=None):
 
 
 def evaluate_rank_sharded(dist_slab, g0, q_pids, g_pids_all, q_camids, g_camids_all, max_rank=50,
-                          accum="cy_f32", group=None, ops=None, return_details=False):
+                          accum="cy_f32", group=None, ops=None, return_details=False, exchange="auto"):
     """CMC/mAP from a per-rank distance slab ``[Q, Gs]`` (columns = gallery ``g0 .. g0+Gs``).
     Labels are those of the whole gallery.  Every rank returns the same ``(cmc, mAP)``.
 
@@ -142,10 +214,22 @@ def evaluate_rank_sharded(dist_slab, g0, q_pids, g_pids_all, q_camids, g_camids_
     if G < max_rank:
         max_rank = G
         print("Note: number of gallery samples is quite small, got {}".format(G))
+    world, _ = _world(group)
+    use_peer = (exchange == "peer" or (exchange == "auto" and world > 1 and isinstance(ops, CudaOps)
+                                       and dist.get_backend(group) == "nccl"))
     plan = ops.plan(qp, gp, qc, gc)
     try:
-        keys = _all_reduce_sum(ops.gather_keys(plan, dist_slab, g0), group)
-        counts = _all_reduce_sum(ops.count(plan, dist_slab, g0, keys), group)
+        if use_peer:
+            # exchange steps as single kernels over NVLink peer memory (PeerExchange)
+            M = ops.num_matches(plan)
+            px = peer_exchange(ops, M, group)
+            ops.gather_keys(plan, dist_slab, g0, out_ptr=px.buffer_ptr(0))
+            keys = px.allreduce(0, M)
+            ops.count(plan, dist_slab, g0, keys, out_ptr=px.buffer_ptr(1))
+            counts = px.allreduce(1, M)
+        else:
+            keys = _all_reduce_sum(ops.gather_keys(plan, dist_slab, g0), group)
+            counts = _all_reduce_sum(ops.count(plan, dist_slab, g0, keys), group)
         cmc, mAP, details = ops.finalize(plan, keys, counts, Q, G, max_rank, accum)
     finally:
         ops.plan_destroy(plan)
@@ -155,7 +239,7 @@ def evaluate_rank_sharded(dist_slab, g0, q_pids, g_pids_all, q_camids, g_camids_
 def evaluate_features_sharded(qf, gf_slab, g0, q_pids, g_pids_all, q_camids, g_camids_all,
                               metric="cosine", precision=metrics.DEFAULT_PRECISION,
                               normalize=None, max_rank=50, accum="cy_f32", group=None, ops=None,
-                              return_details=False):
+                              return_details=False, exchange="auto"):
     """Features in (all queries + this rank's gallery slab), ``(cmc, mAP)`` out."""
     ops = ops or CudaOps(qf.device.index if getattr(qf, "is_cuda", False) else None)
     if normalize is None:
@@ -164,7 +248,7 @@ def evaluate_features_sharded(qf, gf_slab, g0, q_pids, g_pids_all, q_camids, g_c
     if not isinstance(dist_slab, torch.Tensor):
         dist_slab = torch.from_numpy(dist_slab)
     return evaluate_rank_sharded(dist_slab, g0, q_pids, g_pids_all, q_camids, g_camids_all,
-                                 max_rank, accum, group, ops, return_details)
+                                 max_rank, accum, group, ops, return_details, exchange)
 
 
 def topk_features_sharded(qf, gf_slab, g0, k=20, metric="cosine", precision=metrics.DEFAULT_PRECISION,

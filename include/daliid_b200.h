@@ -227,6 +227,29 @@ int dali_rank_finalize(dali_ctx *ctx, const dali_rank_plan *plan, const uint32_t
                        double *mAP, double *ap_opt, int32_t *first_rank_opt,
                        int64_t *num_valid_opt);
 
+/* ---- (e) exchange over NVLink peer memory --------------------------------------- */
+/* The two exchange steps above are sums of small int32 arrays (one word per match).  Instead of
+ * an NCCL all-reduce each (host launch + tens of microseconds on the device), every rank keeps its
+ * contribution in a block that the other ranks of the node map through CUDA IPC, and one kernel
+ * per exchange signals, waits and reduces with peer loads (daliid_b200/csrc/peer.cu).
+ *   dali_peer_create      allocate this rank's block: two buffers of `capacity` int32
+ *   dali_peer_ipc_handle  64-byte cudaIpcMemHandle of the block (exchange it with any transport,
+ *                         e.g. torch.distributed.all_gather_object)
+ *   dali_peer_connect     map the blocks of all ranks; handles = world x 64 bytes, rank order
+ *   dali_peer_buffer      DEVICE pointer of buffer `which` (0 / 1): pass it as keys_out of
+ *                         dali_rank_gather_keys or counts_out of dali_rank_count
+ *   dali_peer_allreduce_i32  out[i] = sum over ranks of buffer `which`[i], i < n.  Collective:
+ *                         every rank must call it the same number of times in the same order.
+ * One process per GPU, all GPUs on one node (NVLink / NVSwitch), world <= 8. */
+typedef struct dali_peer dali_peer;
+int dali_peer_create(dali_ctx *ctx, int rank, int world, int64_t capacity, dali_peer **out);
+int dali_peer_ipc_handle(dali_peer *peer, void *handle64);
+int dali_peer_connect(dali_peer *peer, const void *handles);
+void dali_peer_destroy(dali_peer *peer);
+int64_t dali_peer_capacity(const dali_peer *peer);
+void *dali_peer_buffer(dali_peer *peer, int which);
+int dali_peer_allreduce_i32(dali_ctx *ctx, dali_peer *peer, int which, int32_t *out, int64_t n);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -26,13 +26,13 @@ def main():
     for name in ("small", "market_vit"):
         qf, gf, qp, gp, qc, gc = synth.make_config(name, device=f"cuda:{local}")
         g0, gs = sharded.slab_bounds(gf.shape[0], world, rank)
-        for precision in ("auto", "tf32c", "fp32"):
+        for precision, exchange in (("auto", "peer"), ("auto", "nccl"), ("tf32c", "peer"), ("fp32", "auto")):
             cmc, mAP, det = sharded.evaluate_features_sharded(
                 qf, gf[g0:g0 + gs].contiguous(), g0, qp, gp, qc, gc, precision=precision,
-                return_details=True)
+                return_details=True, exchange=exchange)
             e_cmc, e_map, e_det = metrics.evaluate_features(qf, gf, qp, gp, qc, gc, precision=precision,
                                                             return_details=True)
-            assert np.array_equal(cmc, e_cmc) and mAP == e_map, (name, precision, mAP, e_map)
+            assert np.array_equal(cmc, e_cmc) and mAP == e_map, (name, precision, exchange, mAP, e_map)
             assert np.array_equal(det["first_rank"], e_det["first_rank"])
         v, i = sharded.topk_features_sharded(qf, gf[g0:g0 + gs].contiguous(), g0, k=20)
         ev, ei = metrics.topk_features(qf, gf, k=20)
