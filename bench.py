@@ -356,6 +356,19 @@ def run_ours(args):
                   ", ".join(f"{k}={v[0] * 100:.3f}/{v[1] * 100:.3f}" for k, v in acc.items()),
                   file=sys.stderr, flush=True)
 
+    # the other arithmetic modes of the contraction on the same workload (BASELINE config 1:
+    # "exact fp32 path vs TF32 tensor-core path"), a few steps each
+    modes = {}
+    if world == 1 and not args.no_modes:
+        for m in ("fp32", "tf32", "f16", "tf32c"):
+            def step_m(m=m):
+                return metrics.evaluate_features(qf_d, gf_d, wl["q_pid"], g_pid, wl["q_cam"], g_cam,
+                                                 metric="cosine", precision=m)
+            for _ in range(2):
+                step_m()
+            ms_m, (_, map_m) = timed(step_m, 5)
+            modes[m] = {"ms_per_step": ms_m / 5, "pairs_per_s": Q * G / (ms_m / 5 * 1e-3), "mAP": map_m}
+
     c5 = None
     if not args.no_c5:
         c5 = measure_c5(dev, rank, world, dist)
@@ -414,6 +427,8 @@ def run_ours(args):
         "kernel_ms_per_step": {k: v[1] / args.steps for k, v in ktimes.items() if v[0]},
         "mAP": mAP, "rank1": float(cmc[0]),
     }
+    if modes:
+        line["other_precisions"] = modes
     if c5:
         line["c5_faceid_1toN"] = c5
     if world == 1 and not args.no_cpu_baseline:
@@ -439,8 +454,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="f16x3", choices=["fp32", "tf32x3", "tf32c", "tf32", "f16x3"])
+    ap.add_argument("--precision", default="f16x3", choices=["fp32", "tf32x3", "tf32c", "tf32", "f16x3", "f16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-modes", action="store_true", help="skip the per-precision side measurements")
     ap.add_argument("--no-c5", action="store_true", help="skip the config-5 (1:N top-k) side measurement")
     ap.add_argument("--breakdown", action="store_true", help="diagnostic per-phase host timing (stderr)")
     args = ap.parse_args()

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libdaliid_b200.so")
 ABI_VERSION = 1
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_VALID_QUERY, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 METRICS = {"cosine": 0, "sqeuclidean": 1, "euclidean": 2, "dot": 3}
-PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2, "tf32c": 3, "f16x3": 4}
+PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2, "tf32c": 3, "f16x3": 4, "f16": 5}
 ACCUMS = {"cy_f32": 0, "py_f64": 1}
 K_NORMALIZE, K_DISTMAT, K_RANK_COUNT, K_RANK_FINALIZE, K_TOPK, K_FUSE, K_RANK_GATHER, K_RERANK = range(8)
 KERNEL_SLOTS = {"normalize": 0, "distmat": 1, "rank_count": 2, "rank_finalize": 3, "topk": 4,

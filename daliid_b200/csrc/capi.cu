@@ -294,12 +294,12 @@ static int alloc_operand(dali_ctx *ctx, int ws_planes, int ws_p16, int ws_sq, in
   out->npl = precision == DALI_PREC_TF32X3 ? 2 : 1;
   void *pl = nullptr;
   int rc = DALI_OK;
-  if (precision != DALI_PREC_F16X3) {  // F16X3 reads only the two 16-bit planes
+  if (precision != DALI_PREC_F16X3 && precision != DALI_PREC_F16) {  // the fp16 modes read only 16-bit planes
     rc = ws_ensure(ctx, ws_planes, sizeof(float) * out->npl * out->rows_pad * out->Dp, &pl);
     if (rc) return rc;
   }
   out->planes = static_cast<float *>(pl);
-  if (precision == DALI_PREC_TF32C || precision == DALI_PREC_F16X3) {
+  if (precision == DALI_PREC_TF32C || precision == DALI_PREC_F16X3 || precision == DALI_PREC_F16) {
     void *t = nullptr;
     rc = ws_ensure(ctx, ws_p16, 2 * 2 * out->rows_pad * out->Dp, &t);
     if (rc) return rc;
@@ -322,7 +322,8 @@ static int prep_rows(dali_ctx *ctx, const Prepared &o, const float *xd, int64_t 
   const int64_t off = r0 * o.Dp;
   return launch_prep(ctx, xd, n_valid, D, ldx, o.planes ? o.planes + off : nullptr,
                      o.npl == 2 ? o.planes + o.rows_pad * o.Dp + off : nullptr, o.Dp, o.Dp, r1 - r0,
-                     normalize, precision == DALI_PREC_FP32 ? 0 : precision == DALI_PREC_F16X3 ? 2 : 1,
+                     normalize,
+                     precision == DALI_PREC_FP32 ? 0 : (precision == DALI_PREC_F16X3 || precision == DALI_PREC_F16) ? 2 : 1,
                      nullptr,
                      o.sq ? o.sq + r0 : nullptr, p16 ? p16 + 2 * off : nullptr,
                      p16 ? p16 + 2 * (o.rows_pad * o.Dp + off) : nullptr);
@@ -354,11 +355,11 @@ static int contract(dali_ctx *ctx, const Prepared &a, const Prepared &b, int64_t
 static int check_metric_prec(dali_ctx *ctx, int metric, int precision, int normalize) {
   if (metric < DALI_METRIC_COSINE || metric > DALI_METRIC_DOT)
     return set_err(ctx, DALI_ERR_INVALID, "unknown metric");
-  if (precision < DALI_PREC_FP32 || precision > DALI_PREC_F16X3)
+  if (precision < DALI_PREC_FP32 || precision > DALI_PREC_F16)
     return set_err(ctx, DALI_ERR_INVALID, "unknown precision");
-  if (precision == DALI_PREC_F16X3 && !normalize)
+  if ((precision == DALI_PREC_F16X3 || precision == DALI_PREC_F16) && !normalize)
     return set_err(ctx, DALI_ERR_UNSUPPORTED,
-                   "DALI_PREC_F16X3 needs unit rows (normalize != 0); use DALI_PREC_TF32C");
+                   "DALI_PREC_F16X3 / DALI_PREC_F16 need unit rows (normalize != 0); use DALI_PREC_TF32C / TF32");
   return DALI_OK;
 }
 

@@ -243,11 +243,11 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   };
 
   if (warp == 0 && lane == 0) {
-    if (MODE != kF16x3) {
+    if (MODE != kF16x3 && MODE != kF16) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     }
-    if (MODE == kTf32c || MODE == kF16x3) {
+    if (MODE == kTf32c || MODE == kF16x3 || MODE == kF16) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA16) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB16) : "memory");
     }
@@ -286,16 +286,18 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int arow = m * PM + static_cast<int>(rank) * UM;
         const int brow = p.b_row0 + n * BN + static_cast<int>(rank) * HB;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          if (MODE == kF16x3) {  // one slot: fp16 hi and residual planes of both operands
+          if (MODE == kF16x3 || MODE == kF16) {  // one slot: fp16 hi (and residual) planes of both operands
             mbar_wait(empty_bar(slot), phase ^ 1u);
-            if (rank == 0) mbar_expect_tx(full_bar(slot), 2 * kSlotBytes);
+            if (rank == 0) mbar_expect_tx(full_bar(slot), MODE == kF16 ? kSlotBytes : 2 * kSlotBytes);
             const uint32_t fbh = full0 + 8u * slot;
             const uint32_t sb = slot_addr(slot);
             tma_load_2d_pair(sb, &tmA16, fbh, kb * BK, arow);
-            tma_load_2d_pair(sb + A16_BYTES, &tmA16, fbh, kb * BK, p.a_plane_rows + arow);
             tma_load_2d_pair(sb + 2 * A16_BYTES, &tmB16, fbh, kb * BK, brow);
-            tma_load_2d_pair(sb + 2 * A16_BYTES + B16_BYTES, &tmB16, fbh, kb * BK,
-                             p.b_plane_rows + brow);
+            if (MODE == kF16x3) {
+              tma_load_2d_pair(sb + A16_BYTES, &tmA16, fbh, kb * BK, p.a_plane_rows + arow);
+              tma_load_2d_pair(sb + 2 * A16_BYTES + B16_BYTES, &tmB16, fbh, kb * BK,
+                               p.b_plane_rows + brow);
+            }
             advance();
             continue;
           }
@@ -346,7 +348,16 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           mbar_wait(full_bar(slot), phase);
           tc_fence_after();
           const uint32_t a0 = slot_addr(slot), b0 = a0 + A_BYTES;
-          if (MODE == kF16x3) {
+          if (MODE == kF16) {
+            constexpr uint32_t kIdH = idesc_f16(PM);
+            const uint32_t ahi = a0, bhi = ahi + 2 * A16_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              tc_mma_bf16<2>(tmem_d, make_desc_sw64(ahi + k * 32), make_desc_sw64(bhi + k * 32),
+                             kIdH, (kb | k) ? 1u : 0u);                            // hi * hi
+            tc_commit_pair(empty_bar(slot), 3);
+            advance();
+          } else if (MODE == kF16x3) {
             constexpr uint32_t kIdH = idesc_f16(PM);
             const uint32_t ahi = a0, alo = ahi + A16_BYTES;
             const uint32_t bhi = ahi + 2 * A16_BYTES, blo = bhi + B16_BYTES;
@@ -585,6 +596,7 @@ int launch_prec(dali_ctx *ctx, int precision, const CUtensorMap &tmA, const CUte
     case DALI_PREC_TF32X3: return launch_t<kTf32x3, EPI>(ctx, tmA, tmB, tmA16, tmB16, tmOut, p);
     case DALI_PREC_TF32C: return launch_t<kTf32c, EPI>(ctx, tmA, tmB, tmA16, tmB16, tmOut, p);
     case DALI_PREC_F16X3: return launch_t<kF16x3, EPI>(ctx, tmA, tmB, tmA16, tmB16, tmOut, p);
+    case DALI_PREC_F16: return launch_t<kF16, EPI>(ctx, tmA, tmB, tmA16, tmB16, tmOut, p);
     default: return set_err(ctx, DALI_ERR_INVALID, "not a tensor-core precision");
   }
 }
@@ -615,7 +627,7 @@ int setup(dali_ctx *ctx, const float *q32, const float *g32, const void *q16, co
     return set_err(ctx, DALI_ERR_INVALID, "umma operands must be padded (rows 256, D 32)");
   if (q_rows_pad * 2 > INT32_MAX || g_rows_pad * 2 > INT32_MAX)
     return set_err(ctx, DALI_ERR_UNSUPPORTED, "operand too tall for one tensor map");
-  const bool f16 = precision == DALI_PREC_F16X3;
+  const bool f16 = precision == DALI_PREC_F16X3 || precision == DALI_PREC_F16;
   int rc = DALI_OK;
   if (!f16) {
     rc = make_map(ctx, tmA, q32, q_rows_pad * npl32, Dp, UM, false);
@@ -648,7 +660,7 @@ int setup(dali_ctx *ctx, const float *q32, const float *g32, const void *q16, co
   p->acc_scale = f16 ? 5.9604644775390625e-08f /* 2^-24 */ : 1.0f;
   {
     // bytes of operand planes one tile row of 256 rows reads per pass over K
-    const int64_t bytes_per_row = Dp * (precision == DALI_PREC_TF32 ? 4 : precision == DALI_PREC_F16X3 ? 4 : 8);
+    const int64_t bytes_per_row = Dp * (precision == DALI_PREC_F16 ? 2 : precision == DALI_PREC_TF32 ? 4 : precision == DALI_PREC_F16X3 ? 4 : 8);
     const int64_t a_bytes = static_cast<int64_t>(p->num_m_pairs) * PM * bytes_per_row;
     static const char *env_band = getenv("DALI_UMMA_NBAND");
     int nband = 1;
@@ -674,7 +686,7 @@ int launch_distmat_umma(dali_ctx *ctx, const float *q32, const float *g32, const
                         const float *qsq, const float *gsq, float *out, int64_t ld) {
   if (Q == 0 || G == 0) return DALI_OK;
   static const char *env = getenv("DALI_UMMA_2CTA");
-  if (env && atoi(env) == 0 && precision != DALI_PREC_F16X3)
+  if (env && atoi(env) == 0 && precision != DALI_PREC_F16X3 && precision != DALI_PREC_F16)
     return launch_distmat_umma1(ctx, q32, g32, q16, g16, Q, G, Dp, q_rows_pad, g_rows_pad, g_row0,
                                 precision, metric, qsq, gsq, out, ld);
   CUtensorMap tmA, tmB, tmA16, tmB16;

@@ -16,7 +16,7 @@ constexpr int EPI_LD = 33;
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
 constexpr uint64_t kWatchdogCycles = 4000000000ull;  // ~2 s: trap instead of hanging the box
 
-enum Mode { kTf32 = 0, kTf32x3 = 1, kTf32c = 2, kF16x3 = 3 };
+enum Mode { kTf32 = 0, kTf32x3 = 1, kTf32c = 2, kF16x3 = 3, kF16 = 4 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -64,6 +64,9 @@ extern "C" {
                               residual (22 mantissa bits), hi*hi + hi*lo + lo*hi at the 16-bit
                               rate (1.5 TF32 passes, half the operand bytes; fp32 class, error
                               <= 2^-20 per product).  Needs unit rows: normalize != 0.        */
+#define DALI_PREC_F16 5    /* tcgen05 kind::f16, single pass on the fp16 hi plane of F16X3: the
+                              same 11-bit mantissa as TF32 at twice its rate and half its operand
+                              bytes (fast; <= 0.01 pp mAP).  Needs unit rows: normalize != 0.   */
 
 /* accumulation semantics of the CMC/AP reduction */
 #define DALI_ACCUM_CY_F32 0 /* torchreid Cython path: C float, sequential in rank order */

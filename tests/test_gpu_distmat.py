@@ -128,11 +128,12 @@ def test_tf32_single_pass_quality():
     from daliid_b200 import metrics, synth
     qf, gf, qp, gp, qc, gc = synth.make_config("small", device="cuda")
     exact = metrics.compute_distance_matrix(qf, gf, "cosine", "fp32")
-    fast = metrics.compute_distance_matrix(qf, gf, "cosine", "tf32")
-    assert (exact - fast).abs().max().item() < 2e-3
     m_exact = metrics.evaluate_rank(exact, qp, gp, qc, gc)[1]
-    m_fast = metrics.evaluate_rank(fast, qp, gp, qc, gc)[1]
-    assert abs(m_exact - m_fast) * 100 <= 0.05
+    for prec in ("tf32", "f16"):  # both keep 11 mantissa bits of the unit rows
+        fast = metrics.compute_distance_matrix(qf, gf, "cosine", prec)
+        assert (exact - fast).abs().max().item() < 2e-3
+        m_fast = metrics.evaluate_rank(fast, qp, gp, qc, gc)[1]
+        assert abs(m_exact - m_fast) * 100 <= 0.05
 
 
 def test_exact_path_is_tile_position_independent():
@@ -142,7 +143,7 @@ def test_exact_path_is_tile_position_independent():
     g = torch.Generator().manual_seed(3)
     qf = torch.randn(200, 384, generator=g).cuda()
     gf = torch.randn(1500, 384, generator=g).cuda()
-    for precision in ("fp32", "tf32x3", "tf32c", "tf32", "f16x3"):
+    for precision in ("fp32", "tf32x3", "tf32c", "tf32", "f16x3", "f16"):
         full = metrics.compute_distance_matrix(qf, gf, "cosine", precision)
         part = metrics.compute_distance_matrix(qf, gf[700:1333].contiguous(), "cosine", precision)
         assert torch.equal(full[:, 700:1333], part), precision
@@ -273,7 +274,7 @@ def test_topk_features_fused():
 @pytest.mark.parametrize("precision,metric,largest", [
     ("f16x3", "cosine", False), ("tf32c", "cosine", False), ("tf32x3", "cosine", False),
     ("tf32", "cosine", False), ("tf32c", "sqeuclidean", False), ("tf32", "euclidean", False),
-    ("tf32c", "dot", True), ("tf32", "dot", True), ("f16x3", "cosine", True)])
+    ("tf32c", "dot", True), ("tf32", "dot", True), ("f16x3", "cosine", True), ("f16", "cosine", False)])
 def test_topk_features_fused_multi_chunk(precision, metric, largest):
     """Fused distance + top-k (several gallery chunks, ragged last tile) equals top-k of the
     materialised matrix of the same precision: same kernel arithmetic, so bit-identical."""

@@ -42,7 +42,7 @@ def test_market_tf32_within_001pp_and_under_50ms(market):
     from daliid_b200 import metrics
     qf, gf, qp, gp, qc, gc = market
     res = {}
-    for precision in ("fp32", "tf32x3", "tf32c", "tf32"):
+    for precision in ("fp32", "tf32x3", "tf32c", "tf32", "f16x3", "f16"):
         metrics.evaluate_features(qf, gf, qp, gp, qc, gc, precision=precision)  # warm-up
         torch.cuda.synchronize()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
@@ -55,9 +55,12 @@ def test_market_tf32_within_001pp_and_under_50ms(market):
     assert abs(res["tf32"][1] - res["fp32"][1]) * 100 <= 0.01
     assert abs(res["tf32x3"][1] - res["fp32"][1]) * 100 <= 0.01
     assert abs(res["tf32c"][1] - res["fp32"][1]) * 100 <= 0.01
+    assert abs(res["f16x3"][1] - res["fp32"][1]) * 100 <= 0.01
+    assert abs(res["f16"][1] - res["fp32"][1]) * 100 <= 0.01   # single fp16 pass: TF32's mantissa
     assert np.all(np.diff(res["tf32x3"][0]) >= 0)
     # BASELINE.json target: full Market-shaped eval in under 50 ms on one B200
     assert res["tf32x3_ms"] < 50.0, res["tf32x3_ms"]
+    assert res["f16x3_ms"] < 50.0 and res["fp32_ms"] < 50.0
 
 
 def test_market_sharded_equals_unsharded(market):
