@@ -194,3 +194,12 @@ def test_re_ranking_matches_oracle(Q, G, k1, k2, lam):
     a = metrics.evaluate_rank(out, qp, gp, np.zeros(Q, np.int32), np.ones(G, np.int32))
     b = ro.evaluate_rank(out, qp, gp, np.zeros(Q, np.int32), np.ones(G, np.int32))
     assert np.array_equal(a[0], b[0]) and a[1] == b[1]
+
+
+def test_re_ranking_golden():
+    from daliid_b200 import metrics
+    z = np.load(os.path.join(GOLDEN, "rerank.npz"))
+    for name in "abc":
+        k1, k2, lam = z["params_" + name]
+        out = metrics.re_ranking(z["qg"], z["qq"], z["gg"], int(k1), int(k2), float(lam))
+        assert np.abs(out - z["final_" + name]).max() <= 2e-6, name

@@ -163,3 +163,13 @@ def test_rerank_oracle_invariants():
     np.testing.assert_allclose(p, det["final"][:, perm], atol=2e-6)
     k2_1 = rr.re_ranking_details(qg, qq, gg, k1=8, k2=1, lambda_value=0.3)
     np.testing.assert_array_equal(k2_1["V"], k2_1["V0"])
+
+
+def test_rerank_oracle_matches_golden():
+    """Regression pin of the restated re-ranking against the committed vectors."""
+    from oracle import rerank_oracle as rr
+    z = np.load(os.path.join(GOLDEN, "rerank.npz"))
+    for name in "abc":
+        k1, k2, lam = z["params_" + name]
+        out = rr.re_ranking(z["qg"], z["qq"], z["gg"], int(k1), int(k2), float(lam))
+        np.testing.assert_allclose(out, z["final_" + name], rtol=0, atol=1e-7)
