@@ -28,7 +28,7 @@ __device__ __forceinline__ float epilogue(float acc, int metric, float qs, float
 }
 
 // A: [rows >= gridDim.y*BM, lda] zero padded, B likewise; K = Dp multiple of BK.
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 distmat_simt_kernel(const float *__restrict__ A, const float *__restrict__ B, int64_t lda,
                     int64_t ldb, int64_t Q, int64_t G, int64_t Dp, int metric,
                     const float *__restrict__ qsq, const float *__restrict__ gsq,
@@ -45,11 +45,14 @@ distmat_simt_kernel(const float *__restrict__ A, const float *__restrict__ B, in
   // compute mapping: 16 x 16 threads, each 2x2 blocks of 4x4
   const int ty = tid >> 4, tx = tid & 15;
 
-  float acc[8][8];
+  // accumulators as fp32 pairs: the inner product runs on packed FFMA2 (sm_100 fma.rn.f32x2),
+  // two IEEE fmaf per instruction -- half the issue slots and operand reads of scalar FFMA, the
+  // same bits (each half is an ordinary round-to-nearest fma in ascending k)
+  float2 acc[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
 
   float4 ra[2], rb[2];
   auto gload = [&](int64_t k0) {
@@ -84,11 +87,14 @@ distmat_simt_kernel(const float *__restrict__ A, const float *__restrict__ B, in
       const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[buf][k][tx * 4]);
       const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[buf][k][64 + tx * 4]);
       const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float2 b[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
+                           make_float2(b1.z, b1.w)};
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i) {
+        const float2 ai = make_float2(a[i], a[i]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(ai, b[j], acc[i][j]);
+      }
     }
     if (kb + 1 < nk) {
       sstore(buf ^ 1);
@@ -110,7 +116,8 @@ distmat_simt_kernel(const float *__restrict__ A, const float *__restrict__ B, in
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float gs = (gsq && c + j < G) ? __ldg(gsq + c + j) : 0.f;
-        v[j] = epilogue(acc[i][jb * 4 + j], metric, qs, gs);
+        const float2 pr = acc[i][jb * 2 + (j >> 1)];
+        v[j] = epilogue((j & 1) ? pr.y : pr.x, metric, qs, gs);
       }
       float *dst = out + r * ld + c;
       if (vec_ok && c + 3 < G) {

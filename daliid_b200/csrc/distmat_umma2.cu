@@ -80,7 +80,6 @@ struct Umma2Params {
   int largest;
   int direct;           // 1: every column j is written to slot j of the list (first chunk)
   int32_t id_base;      // gallery id of column 0
-  int debug;            // DALI_DEBUG_EPI (profiling experiments only)
   float acc_scale;      // 2^-24 for kF16x3 (operands carry a factor 2^12 each), else 1
 };
 
@@ -452,7 +451,6 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           for (int c = 0; c < BN / 32; ++c) {
             const int64_t col0 = colt + c * 32;
             if (col0 >= p.G) break;
-            if (p.debug & 1) break;
             uint32_t v[32];
             tc_ld_32x32(tbase + c * 32, v);
             tc_wait_ld();
@@ -518,22 +516,9 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           for (int c = 0; c < BN / 32; ++c) {
             const int64_t col0 = colt + c * 32;
             if (col0 >= p.G) break;
-            if (p.debug & 1) break;
             uint32_t v[32];
             tc_ld_32x32(tbase + c * 32, v);
             tc_wait_ld();
-            if (p.debug & 2) {  // loads only
-              asm volatile("" ::"r"(v[0]), "r"(v[7]), "r"(v[15]), "r"(v[23]), "r"(v[31]));
-              continue;
-            }
-            if (p.debug & 4) {  // loads + compares, no append path
-              int npass = 0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                npass += !(fmaf(__uint_as_float(v[j]), fr.alpha, fr.beta) > fr.thr) ? 1 : 0;
-              if (npass == 77) p.cand_cnt[0] = 1;
-              continue;
-            }
             const int lim = p.G - col0 < 32 ? static_cast<int>(p.G - col0) : 32;
             const float *gs = p.gsq ? p.gsq + col0 : nullptr;
             const uint32_t id0 = static_cast<uint32_t>(p.id_base + col0);
@@ -695,8 +680,6 @@ int launch_distmat_umma(dali_ctx *ctx, const float *q32, const float *g32, const
                  qsq, gsq, &tmA, &tmB, &tmA16, &tmB16, &p);
   if (rc) return rc;
   p.out = out; p.ld = ld;
-  static const char *dbg = getenv("DALI_DEBUG_EPI");
-  p.debug = dbg ? atoi(dbg) : 0;
   // TMA stores need 16-byte aligned rows (always true for the library's own matrices, whose
   // leading dimension is a multiple of 4; a caller's contiguous [Q, G] with odd G is not)
   static const char *env_tma = getenv("DALI_UMMA_TMA_STORE");
@@ -729,8 +712,6 @@ int launch_distmat_filter_umma(dali_ctx *ctx, const float *q32, const float *g32
   if (rc) return rc;
   p.thr = thr; p.cand_cnt = cand_cnt; p.cand = cand; p.cap = cap;
   p.largest = largest; p.direct = direct; p.id_base = id_base;
-  static const char *dbg = getenv("DALI_DEBUG_EPI");
-  p.debug = dbg ? atoi(dbg) : 0;
   return launch_prec<kFilter>(ctx, precision, tmA, tmB, tmA16, tmB16, tmA, p);
 }
 
