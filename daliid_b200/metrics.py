@@ -168,7 +168,7 @@ def normalize(x, return_norms=False):
 
 
 def compute_distance_matrix(input1, input2, metric="cosine", precision=DEFAULT_PRECISION,
-                            normalize=None, out=None, device=None, padded=False):
+                            normalize=None, out=None, device=None, padded=None):
     """``[Q,G]`` fp32 distance matrix between feature rows.
 
     ``metric``: ``cosine`` (``1 - q.g`` on L2-normalised rows), ``sqeuclidean`` (what
@@ -177,10 +177,10 @@ def compute_distance_matrix(input1, input2, metric="cosine", precision=DEFAULT_P
     The result lives where the inputs live (CUDA tensor in, CUDA tensor out) unless ``out``
     (a contiguous float32 CUDA tensor or numpy array) or ``device`` (a CUDA ordinal: host
     features are streamed to the GPU in chunks overlapped with compute, the matrix stays
-    there) says otherwise.  ``padded=True`` (CUDA results only) returns a ``[Q,G]`` view of a
+    there) says otherwise.  CUDA results are by default (``padded=None``) a ``[Q,G]`` view of a
     matrix whose rows are padded to a multiple of 4 floats: 16-byte aligned rows let the
-    contraction store its tiles through TMA (the reference's contiguous layout with an odd G,
-    e.g. 15913, cannot)."""
+    contraction store its tiles through TMA (a contiguous layout with an odd G, e.g. 15913,
+    cannot).  ``padded=False`` returns a contiguous tensor; numpy results always are."""
     a = as_matrix(input1, np.float32, "input1")
     b = as_matrix(input2, np.float32, "input2")
     if a.shape[1] != b.shape[1]:
@@ -204,7 +204,7 @@ def compute_distance_matrix(input1, input2, metric="cosine", precision=DEFAULT_P
     else:
         if dev is None and device is not None:
             dev = int(device)
-        if padded and dev is not None and G % 4:
+        if (padded or padded is None) and dev is not None and G % 4 and Q:
             ld = (G + 3) // 4 * 4
             buf, optr = _alloc_out((Q, ld), dev)
             out = buf[:, :G]
@@ -239,9 +239,15 @@ def fuse_distmats(distmats, q_weights=None, g_weights=None):
             raise ValueError("all matrices must share shape, layout and device")
     Q, G = shape
     ctx = _ctx_for(*bufs)
-    out, optr = _alloc_out((Q, G), dev)
-    if bufs[0].ld != G and Q > 1:
-        raise ValueError("distance matrices must be contiguous")
+    ld = bufs[0].ld if Q > 1 else G
+    if ld != G:
+        # row-padded device matrices (what compute_distance_matrix returns on CUDA): same layout out
+        if dev is None:
+            raise ValueError("host distance matrices must be contiguous")
+        buf, optr = _alloc_out((Q, ld), dev)
+        out = buf[:, :G]
+    else:
+        out, optr = _alloc_out((Q, G), dev)
     dptr = (c_vp * n)(*[b.ptr for b in bufs])
     wq = wg = None
     keep = []
@@ -262,7 +268,7 @@ def fuse_distmats(distmats, q_weights=None, g_weights=None):
         wq = (c_vp * n)(*[vec(v, Q) for v in q_weights])
         wg = (c_vp * n)(*[vec(v, G) for v in g_weights])
     if Q and G:
-        ctx.check(ctx.lib.dali_fuse_f32(ctx.h, dptr, n, wq, wg, c_vp(optr), Q, G, G))
+        ctx.check(ctx.lib.dali_fuse_f32(ctx.h, dptr, n, wq, wg, c_vp(optr), Q, G, max(ld, 1)))
     return out
 
 

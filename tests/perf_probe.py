@@ -65,6 +65,25 @@ def main():
         ms, _ = timeit(lambda: (metrics.compute_distance_matrix(qf, qf, "sqeuclidean", normalize=True),
                                 metrics.compute_distance_matrix(gf, gf, "sqeuclidean", normalize=True)), n=3, warm=1)
         print(f"qq + gg distance matrices: {ms:.2f} ms", flush=True)
+    elif what == "ensemble":
+        # BASELINE config 4: three models' Market-shaped distance matrices, mean fusion, ranking
+        feats = []
+        for seed in (12, 13, 14):
+            q, g, qp, gp, qc, gc = synth.make_config("market_vit", device="cuda", seed=seed) \
+                if "seed" in synth.make_config.__code__.co_varnames else synth.make_config("market_vit", device="cuda")
+            feats.append((q + 0.01 * seed, g + 0.01 * seed))
+        Q, G = feats[0][0].shape[0], feats[0][1].shape[0]
+
+        def run():
+            ds = [metrics.compute_distance_matrix(q, g, "cosine") for q, g in feats]
+            fused = metrics.fuse_distmats(ds)
+            return metrics.evaluate_rank(fused, qp, gp, qc, gc)
+        ctx.timing_enable(True); ctx.timing_reset()
+        ms, (cmc, mAP) = timeit(run, n=5, warm=2)
+        kt = {k: round(v[1] / 5, 4) for k, v in ctx.timing_read().items() if v[0]}
+        ctx.timing_enable(False)
+        print(f"ensemble of 3 (market_vit shape): {ms:.3f} ms per run (3 distmats + mean fusion + rank), "
+              f"{3 * Q * G / ms / 1e6:.1f} Gpairs/s, mAP={mAP:.4f}; kernel ms per run: {kt}", flush=True)
     elif what == "plan":
         # host cost of the rank plan for an 8-slab global gallery (the sharded path builds it on
         # every rank and every step)
