@@ -143,8 +143,16 @@ class PeerExchange:
             handles = [None] * self.world
             dist.all_gather_object(handles, bytes(mine.raw), group=group)
             blob = ctypes.create_string_buffer(b"".join(handles), 64 * self.world)
-            ctx.check(ctx.lib.dali_peer_connect(self.h, blob))
+            err = None
+            try:
+                ctx.check(ctx.lib.dali_peer_connect(self.h, blob))
+            except _lib.DaliError as e:  # keep the collective sequence identical on every rank
+                err = e
             dist.barrier(group=group)  # every rank has mapped every block before anyone signals
+            if err is not None:
+                ctx.lib.dali_peer_destroy(self.h)
+                self.h = c_vp()
+                raise err
         self.out = [torch.empty(self.capacity, dtype=torch.int32, device=ops.device) for _ in range(2)]
 
     def buffer_ptr(self, which):
@@ -170,15 +178,37 @@ class PeerExchange:
 _peer_cache = {}
 
 
+_peer_disabled = set()
+
+
 def peer_exchange(ops, need, group=None):
     """Process-wide PeerExchange for this (device, group); re-created collectively when a larger
-    capacity is needed (``need`` = number of matches, identical on every rank)."""
+    capacity is needed (``need`` = number of matches, identical on every rank).  Returns None --
+    on every rank -- when peer mapping is not possible (CUDA IPC refused on some rank): the
+    caller then uses the NCCL exchange."""
     key = (ops.ctx.device, id(group))
+    if key in _peer_disabled:
+        return None
     px = _peer_cache.get(key)
     if px is None or px.capacity < need:
         if px is not None:
             px.close()
-        px = PeerExchange(ops, max(int(need * 1.25), 1 << 16), group)
+            _peer_cache.pop(key, None)
+        ok = 1
+        try:
+            px = PeerExchange(ops, max(int(need * 1.25), 1 << 16), group)
+        except _lib.DaliError:
+            px, ok = None, 0
+        world, _ = _world(group)
+        if world > 1:  # all ranks take the same branch
+            t = torch.tensor([ok], dtype=torch.int32, device=ops.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            ok = int(t.item())
+        if not ok:
+            if px is not None:
+                px.close()
+            _peer_disabled.add(key)
+            return None
         _peer_cache[key] = px
     return px
 
@@ -219,10 +249,14 @@ def evaluate_rank_sharded(dist_slab, g0, q_pids, g_pids_all, q_camids, g_camids_
                                        and dist.get_backend(group) == "nccl"))
     plan = ops.plan(qp, gp, qc, gc)
     try:
+        px = None
         if use_peer:
-            # exchange steps as single kernels over NVLink peer memory (PeerExchange)
             M = ops.num_matches(plan)
             px = peer_exchange(ops, M, group)
+            if px is None and exchange == "peer":
+                raise _lib.DaliError("peer exchange requested but CUDA IPC mapping failed on some rank")
+        if px is not None:
+            # exchange steps as single kernels over NVLink peer memory (PeerExchange)
             ops.gather_keys(plan, dist_slab, g0, out_ptr=px.buffer_ptr(0))
             keys = px.allreduce(0, M)
             ops.count(plan, dist_slab, g0, keys, out_ptr=px.buffer_ptr(1))
