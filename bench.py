@@ -145,6 +145,11 @@ def run_reference(args):
         return
     from oracle import c_oracle
     c_oracle.build()
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it can
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     wl = make_workload(WORKLOAD, 0, 1, "cpu")
     cfg = wl["cfg"]
     G = cfg["G"]
@@ -167,7 +172,8 @@ def run_reference(args):
                    "note": "torch.mm uses all host threads; argsort + evaluator loop are single-threaded "
                            "as upstream"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "full workload per step (CPU torch.mm + np.argsort + compiled loop)"},
+                         "sample": "one Market-sized slab (Q=3368 x G=15913) per step: CPU torch.mm + "
+                                   "np.argsort + compiled loop; at N>1 the arm's gallery is N such slabs"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "mAP": mAP, "host_cpus": os.cpu_count(),
     }
