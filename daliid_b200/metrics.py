@@ -229,6 +229,9 @@ def fuse_distmats(distmats, q_weights=None, g_weights=None):
     ``sum(w_m d_m)/sum(w_m)`` (evaluateCleanATModels.py:154-157).  Bit-identical to the
     reference's numpy / torch expression."""
     bufs = [as_matrix(d, np.float32, "distmat") for d in distmats]
+    if len({b.ld for b in bufs}) > 1 and all(b.device is not None for b in bufs):
+        # mixed row pitches (a padded view next to its .clone()): bring all to the contiguous layout
+        bufs = [as_matrix(b.keep.contiguous(), np.float32, "distmat") for b in bufs]
     n = len(bufs)
     if n < 1 or n > 8:
         raise ValueError("between 1 and 8 matrices can be fused")
