@@ -367,8 +367,28 @@ static int check_metric_prec(dali_ctx *ctx, int metric, int precision, int norma
 static int rank_from_device(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist, int64_t ld,
                             int max_rank, int accum_mode, float *cmc, double *mAP, double *ap_opt,
                             int32_t *first_rank_opt, int64_t *num_valid_opt) {
+  int rc;
+  if (accum_mode == DALI_ACCUM_CY_F32 || accum_mode == DALI_ACCUM_PY_F64) {
+    // common case (one CTA per query): thresholds, counts, junk subtraction, AP and the
+    // first-match histogram in ONE launch (rank.cu, FUSED); same result block as dali_rank_finalize
+    const int mr = max_rank > plan->G ? static_cast<int>(std::max<int64_t>(plan->G, 1)) : max_rank;
+    void *ranks, *blk;
+    if ((rc = ws_ensure(ctx, WS_RANKS, sizeof(int32_t) * std::max<int64_t>(plan->M, 1), &ranks))) return rc;
+    const int64_t Qp = std::max<int64_t>(plan->Q, 1);
+    if ((rc = ws_ensure(ctx, WS_AP, sizeof(float) * Qp + sizeof(int32_t) * Qp + sizeof(int32_t) * (mr + 1), &blk)))
+      return rc;
+    float *ap = static_cast<float *>(blk);
+    int32_t *first = reinterpret_cast<int32_t *>(ap + Qp);
+    int32_t *cmcd = first + Qp;
+    int done = 0;
+    rc = launch_rank_fused(ctx, plan, dist, ld, mr, static_cast<int32_t *>(ranks), ap, first, cmcd, &done);
+    if (rc) return rc;
+    if (done)
+      return finish_on_host(ctx, plan, static_cast<int32_t *>(ranks), ap, first, cmcd, mr, accum_mode, cmc, mAP,
+                            ap_opt, first_rank_opt, num_valid_opt);
+  }
   void *keys = nullptr, *counts = nullptr;
-  int rc = ws_ensure(ctx, WS_KEYS, sizeof(uint32_t) * std::max<int64_t>(plan->M, 1), &keys);
+  rc = ws_ensure(ctx, WS_KEYS, sizeof(uint32_t) * std::max<int64_t>(plan->M, 1), &keys);
   if (rc) return rc;
   rc = ws_ensure(ctx, WS_COUNTS, sizeof(int32_t) * std::max<int64_t>(plan->M, 1), &counts);
   if (rc) return rc;

@@ -198,6 +198,9 @@ int launch_rank_gather(dali_ctx *ctx, const dali_rank_plan *plan, const float *d
                        int64_t g0, int64_t Gs, uint32_t *keys);
 int launch_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist, int64_t ld,
                       int64_t g0, int64_t Gs, const uint32_t *keys, int32_t *counts);
+int launch_rank_fused(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist, int64_t ld,
+                      int max_rank, int32_t *ranks_sorted, float *ap, int32_t *first_rank,
+                      int32_t *cmc_cnt, int *done);
 int launch_rank_finalize(dali_ctx *ctx, const dali_rank_plan *plan, const uint32_t *keys,
                          const int32_t *counts, int max_rank, int32_t *ranks_sorted, float *ap,
                          int32_t *first_rank, int32_t *cmc_cnt /* [max_rank+1], last = num_valid */);

@@ -217,12 +217,25 @@ __device__ __noinline__ uint32_t bucket_exact(const uint64_t *T, uint32_t base, 
 // BYTEC: 8-bit private counters (a thread must then see <= 255 elements: the launcher splits the
 // row accordingly), rows of counters skewed by 4 bytes so that lanes hitting different buckets
 // spread over the banks.  Halves the shared memory of a many-threshold CTA again.
-template <int LOG2NB, int kV2Threads, bool BYTEC>
+// FUSED (single GPU, one CTA per query: no threshold chunks, no column splits): the CTA reads its
+// thresholds straight from the matrix row (no gather kernel) and, having the counts of all its
+// positives, finishes the query itself -- junk subtraction, kept ranks, torchreid's sequential
+// float AP, first-match histogram (what rank_finalize_kernel does) -- so the rank stage of an
+// evaluation is ONE launch instead of three.
+struct FusedOut {
+  int32_t *ranks_sorted;  // [M] kept ranks in rank order (py_f64 accumulation on the host)
+  float *ap;              // [Q]
+  int32_t *first_rank;    // [Q]
+  int32_t *cmc_cnt;       // [max_rank + 1]
+  int max_rank;
+};
+
+template <int LOG2NB, int kV2Threads, bool BYTEC, bool FUSED = false>
 __global__ void __launch_bounds__(kV2Threads)
 rank_count_v2_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int64_t Gs,
                      const int64_t *__restrict__ off, const int32_t *__restrict__ nvalid,
                      const int32_t *__restrict__ gid, const uint32_t *__restrict__ keys,
-                     int32_t *__restrict__ counts, int nsplit, int tchunk) {
+                     int32_t *__restrict__ counts, int nsplit, int tchunk, FusedOut fo) {
   constexpr int NB = 1 << LOG2NB;
   extern __shared__ __align__(16) uint8_t smem_v2[];
   uint64_t *Tu = reinterpret_cast<uint64_t *>(smem_v2);            // [256] unsorted
@@ -237,14 +250,24 @@ rank_count_v2_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
   const int64_t q = blockIdx.x;
   const int chunk = blockIdx.y;
   const int nv = nvalid[q];
+  if (FUSED && nv == 0) {  // query without a valid match: not counted (torchreid skips it)
+    if (threadIdx.x == 0) {
+      fo.ap[q] = 0.f;
+      fo.first_rank[q] = -1;
+    }
+    return;
+  }
   if (chunk * tchunk >= nv) return;  // uniform exit
   const int n = min(tchunk, nv - chunk * tchunk);
   const int64_t o = off[q] + static_cast<int64_t>(chunk) * tchunk;
   const int tid = threadIdx.x;
 
   // 1. sort the thresholds by counting (composites are distinct: gallery ids differ)
-  for (int t = tid; t < n; t += kV2Threads)
-    Tu[t] = composite(__ldg(keys + o + t), static_cast<uint32_t>(__ldg(gid + o + t)));
+  for (int t = tid; t < n; t += kV2Threads) {
+    const uint32_t g = static_cast<uint32_t>(__ldg(gid + o + t));
+    const uint32_t k = FUSED ? dist_key(__ldg(dist + q * ld + g)) : __ldg(keys + o + t);
+    Tu[t] = composite(k, g);
+  }
   __syncthreads();
   for (int t = tid; t < n; t += kV2Threads) {
     const uint64_t c = Tu[t];
@@ -361,15 +384,48 @@ rank_count_v2_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
   }
   __syncthreads();
   // 6. count_below(T[i]) = sum_{b <= i} hist[b]; scatter back to plan order
+  if (!FUSED) {
+    for (int t = tid; t < n; t += kV2Threads) {
+      uint32_t below = 0;
+      for (int b = 0; b <= t; ++b) below += hist[b];
+      int32_t *dst = counts + o + orig[t];
+      if (nsplit > 1) {
+        if (below) atomicAdd(dst, static_cast<int32_t>(below));
+      } else {
+        *dst = static_cast<int32_t>(below);
+      }
+    }
+    return;
+  }
+  // 7. FUSED: finish the query.  T[] is sorted by (key, gallery id) = by rank, so sorted index i
+  // is the positive with the i-th best rank; junk matches (same identity, same camera) ahead of
+  // it are subtracted, exactly as rank_finalize_kernel does.
+  int32_t *s_rank = reinterpret_cast<int32_t *>(Tu);  // Tu is free after the sort
+  const int m = static_cast<int>(off[q + 1] - off[q]);
+  __syncthreads();
   for (int t = tid; t < n; t += kV2Threads) {
     uint32_t below = 0;
     for (int b = 0; b <= t; ++b) below += hist[b];
-    int32_t *dst = counts + o + orig[t];
-    if (nsplit > 1) {
-      if (below) atomicAdd(dst, static_cast<int32_t>(below));
-    } else {
-      *dst = static_cast<int32_t>(below);
+    const uint64_t ck = T[t];
+    int below_junk = 0;
+    for (int u = nv; u < m; ++u) {
+      const uint32_t g = static_cast<uint32_t>(__ldg(gid + o + u));
+      below_junk += composite(dist_key(__ldg(dist + q * ld + g)), g) < ck ? 1 : 0;
     }
+    const int r = static_cast<int>(below) - below_junk + 1;  // 1-based rank among kept items
+    s_rank[t] = r;
+    fo.ranks_sorted[o + t] = r;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;  // torchreid Cython accumulation: float running sum, each term formed in double
+    for (int k = 1; k <= n; ++k)
+      s = static_cast<float>(static_cast<double>(s) + static_cast<double>(k) / static_cast<double>(s_rank[k - 1]));
+    fo.ap[q] = s / static_cast<float>(n);
+    const int fr = s_rank[0];
+    fo.first_rank[q] = fr;
+    if (fr <= fo.max_rank) atomicAdd(fo.cmc_cnt + (fr - 1), 1);
+    atomicAdd(fo.cmc_cnt + fo.max_rank, 1);  // num_valid_q
   }
 }
 
@@ -472,7 +528,7 @@ static int launch_v2(dali_ctx *ctx, dim3 grid, size_t smem, const dali_rank_plan
     attr = want;
   }
   rank_count_v2_kernel<LOG2NB, THREADS, BYTEC><<<grid, THREADS, smem, ctx->stream>>>(
-      dist, ld, g0, Gs, plan->d_off, plan->d_nv, plan->d_gid, keys, counts, nsplit, tchunk);
+      dist, ld, g0, Gs, plan->d_off, plan->d_nv, plan->d_gid, keys, counts, nsplit, tchunk, FusedOut{});
   return DALI_OK;
 }
 
@@ -529,6 +585,41 @@ int launch_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *di
     if (rc) return rc;
   }
   DALI_CUDA_OK(ctx, cudaGetLastError());
+  return DALI_OK;
+}
+
+// Whole rank stage of a single-GPU evaluation in one launch; *done = 0 (nothing launched) when the
+// shape needs threshold chunks, column splits or the many-threshold variants.
+int launch_rank_fused(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist, int64_t ld,
+                      int max_rank, int32_t *ranks_sorted, float *ap, int32_t *first_rank,
+                      int32_t *cmc_cnt, int *done) {
+  *done = 0;
+  static const char *env = getenv("DALI_RANK_FUSED");
+  if (env && atoi(env) == 0) return DALI_OK;
+  const int64_t G = plan->G;
+  if (plan->Q == 0 || plan->M == 0 || G == 0 || plan->max_nv == 0 || plan->max_nv > 64) return DALI_OK;
+  if (getenv("DALI_RANK_V1") || getenv("DALI_RANK_CHUNK") || getenv("DALI_RANK_THREADS")) return DALI_OK;
+  // the same split rule as launch_rank_count: only the one-CTA-per-query case is fused
+  const int64_t want = (4ll * ctx->num_sms + plan->Q - 1) / plan->Q;
+  const int64_t max_split = (G + 4095) / 4096;
+  const int64_t min_split = (G + (4ll << 20) - 1) / (4ll << 20);
+  if (std::max<int64_t>(std::max<int64_t>(1, std::min(want, max_split)), min_split) != 1) return DALI_OK;
+  DALI_CUDA_OK(ctx, cudaMemsetAsync(cmc_cnt, 0, sizeof(int32_t) * (max_rank + 1), ctx->stream));
+  const size_t smem = v2_smem_bytes(11, plan->max_nv, 256);
+  static size_t attr = 0;
+  if (smem > attr) {
+    const size_t want_b = std::max<size_t>(smem, 48 * 1024);
+    DALI_CUDA_OK(ctx, cudaFuncSetAttribute(rank_count_v2_kernel<11, 256, false, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(want_b)));
+    attr = want_b;
+  }
+  FusedOut fo{ranks_sorted, ap, first_rank, cmc_cnt, max_rank};
+  KTimer t(ctx, DALI_K_RANK_COUNT);
+  rank_count_v2_kernel<11, 256, false, true><<<dim3(static_cast<unsigned>(plan->Q), 1, 1), 256, smem, ctx->stream>>>(
+      dist, ld, 0, G, plan->d_off, plan->d_nv, plan->d_gid, nullptr, nullptr, 1, kV2Chunk, fo);
+  DALI_CUDA_OK(ctx, cudaGetLastError());
+  *done = 1;
   return DALI_OK;
 }
 
