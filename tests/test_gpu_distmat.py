@@ -351,3 +351,39 @@ def test_two_cta_kernel_equals_one_cta_kernel():
             assert np.array_equal(np.load(os.path.join(td, "notma_" + p + ".npy")), b), p
             if p != "f16x3":
                 assert np.array_equal(np.load(os.path.join(td, "one_" + p + ".npy")), b), p
+
+
+def test_property_topk_and_fusion_hypothesis():
+    """Property test (hypothesis, derandomised): top-k of arbitrary small matrices full of ties,
+    signed zeros, infinities and NaN equals the stable argsort prefix (smallest) / torch.topk
+    order (largest); mean fusion of 2-4 matrices equals numpy's left-to-right expression bitwise."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    from daliid_b200 import metrics
+    specials = np.array([0.0, -0.0, 0.5, 0.5, 1.0, np.inf, -np.inf, np.nan, -2.0, 3.0], dtype=np.float32)
+
+    @settings(max_examples=80, deadline=None, derandomize=True,
+              suppress_health_check=[HealthCheck.too_slow])
+    @given(st.integers(1, 9), st.integers(1, 200), st.integers(1, 40), st.integers(0, 2 ** 31 - 1),
+           st.booleans(), st.integers(2, 4))
+    def run(Q, G, k, seed, largest, nmat):
+        rng = np.random.default_rng(seed)
+        d = rng.choice(specials, size=(Q, G)) if seed % 2 else rng.random((Q, G), dtype=np.float32)
+        d = d.astype(np.float32)
+        v, i = metrics.topk_identify(d, k=k, largest=largest)
+        kk = min(k, G)
+        if largest:  # torch.topk order: NaN above +inf, then descending, ties by ascending index
+            order = np.array([sorted(range(G), key=lambda j: (0 if np.isnan(r[j]) else 1,
+                                                              -(float(r[j]) + 0.0) if not np.isnan(r[j]) else 0.0, j))
+                              for r in d])[:, :kk]
+        else:
+            order = ro.stable_argsort(d)[:, :kk]
+        assert np.array_equal(i[:, :kk], order.astype(np.int32))
+        assert np.array_equal(v[:, :kk], np.take_along_axis(d, order, 1), equal_nan=True)
+        assert (i[:, kk:] == -1).all()
+        ms = [rng.random((Q, G), dtype=np.float32) * 3 for _ in range(nmat)]
+        acc = ms[0]
+        for m in ms[1:]:
+            acc = acc + m
+        assert np.array_equal(metrics.fuse_distmats(ms), acc / nmat)
+
+    run()

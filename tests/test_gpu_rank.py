@@ -203,3 +203,53 @@ def test_re_ranking_golden():
         k1, k2, lam = z["params_" + name]
         out = metrics.re_ranking(z["qg"], z["qq"], z["gg"], int(k1), int(k2), float(lam))
         assert np.abs(out - z["final_" + name]).max() <= 2e-6, name
+
+
+def test_property_random_cases_hypothesis():
+    """Property test (hypothesis, derandomised): arbitrary small shapes, label alphabets, value
+    alphabets full of ties / signed zeros / infinities / NaN, any max_rank and both accumulation
+    modes -- CMC, AP, first ranks and mAP equal the oracle bit for bit; queries with no valid match
+    are skipped; all-invalid inputs raise torchreid's AssertionError."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    from daliid_b200 import metrics
+
+    specials = [0.0, -0.0, 0.25, 0.5, 0.5, 1.0, 1.5, np.inf, -np.inf, np.nan, 1e-38, -3.0, 7.0]
+
+    @st.composite
+    def cases(draw):
+        Q = draw(st.integers(1, 12))
+        G = draw(st.integers(1, 90))
+        n_ids = draw(st.integers(1, 6))
+        n_cams = draw(st.integers(1, 3))
+        seed = draw(st.integers(0, 2 ** 31 - 1))
+        mode = draw(st.sampled_from(["specials", "quantised", "continuous"]))
+        max_rank = draw(st.sampled_from([1, 3, 20, 50]))
+        rng = np.random.default_rng(seed)
+        if mode == "specials":
+            d = rng.choice(np.array(specials, dtype=np.float32), size=(Q, G))
+        elif mode == "quantised":
+            d = (rng.integers(0, 5, size=(Q, G)) / 4).astype(np.float32)
+        else:
+            d = rng.random((Q, G), dtype=np.float32) * 2 - 0.5
+        return (d.astype(np.float32), rng.integers(0, n_ids, Q).astype(np.int32),
+                rng.integers(0, n_ids, G).astype(np.int32), rng.integers(0, n_cams, Q).astype(np.int32),
+                rng.integers(0, n_cams, G).astype(np.int32), max_rank)
+
+    @settings(max_examples=120, deadline=None, derandomize=True,
+              suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+    @given(cases())
+    def run(case):
+        d, qp, gp, qc, gc, max_rank = case
+        for accum, fn in (("cy_f32", ro.eval_market1501_cy_f32), ("py_f64", ro.eval_market1501_py_f64)):
+            try:
+                e_cmc, e_map, e_ap, e_first = fn(d, qp, gp, qc, gc, max_rank, return_details=True)
+            except AssertionError:
+                with pytest.raises(AssertionError):
+                    metrics.evaluate_rank_detailed(d, qp, gp, qc, gc, max_rank, accum)
+                continue
+            cmc, mAP, ap, first, _ = metrics.evaluate_rank_detailed(d, qp, gp, qc, gc, max_rank, accum)
+            assert np.array_equal(first, e_first)
+            assert np.array_equal(cmc, e_cmc) and mAP == e_map
+            assert np.array_equal(ap, e_ap, equal_nan=True)
+
+    run()
