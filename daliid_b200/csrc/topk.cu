@@ -154,45 +154,97 @@ topk_kernel(const float *__restrict__ dist, int64_t G, int64_t ld, int k, int la
 constexpr int kCompactThreads = 128;
 constexpr int kCompactCap = 1024;
 
+// Four rows per CTA.  A row whose list holds <= 256 entries (all but pathological chunks: k kept +
+// about f*k survivors) is sorted by ONE warp in its own 2 KiB of shared memory with warp-level
+// barriers only; longer lists (up to cap) are then sorted by the whole CTA, one row after the other.
+constexpr int kWarpSort = 256;
+
+__device__ __forceinline__ void warp_bitonic(uint64_t *a, int n, int lane) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncwarp();
+      for (int i = lane; i < (n >> 1); i += 32) {
+        const int pos = 2 * i - (i & (stride - 1));
+        const bool asc = (pos & size) == 0;
+        const uint64_t x = a[pos], y = a[pos + stride];
+        if ((x > y) == asc) {
+          a[pos] = y;
+          a[pos + stride] = x;
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(kCompactThreads)
 topk_compact_kernel(uint64_t *__restrict__ cand, int32_t *__restrict__ cnt, float *__restrict__ thr,
-                    int cap, int k, int largest, int fixed_cnt, int32_t *__restrict__ overflow,
+                    int64_t Q, int cap, int k, int largest, int fixed_cnt, int32_t *__restrict__ overflow,
                     float *__restrict__ d_out, int32_t *__restrict__ i_out,
                     int32_t *__restrict__ row_flags) {
-  __shared__ uint64_t s[kCompactCap];
-  const int64_t q = blockIdx.x;
-  const int tid = threadIdx.x;
+  __shared__ uint64_t s_small[4][kWarpSort];
+  __shared__ uint64_t s_big[kCompactCap];
+  __shared__ int s_n[4];
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const uint32_t flip = largest ? 0xFFFFFFFFu : 0u;
-  int n = fixed_cnt >= 0 ? fixed_cnt : cnt[q];
-  if (n > cap) {
-    if (tid == 0) {
-      atomicOr(overflow, 1);
-      if (row_flags) row_flags[q] = 1;
+  const int64_t q_w = static_cast<int64_t>(blockIdx.x) * 4 + w;
+
+  // writes the outcome of one sorted row; `t`/`nt`: the participating thread and their number
+  auto emit = [&](int64_t q, const uint64_t *srt, int n, int t, int nt) {
+    uint64_t *list = cand + q * cap;
+    const int m = n < k ? n : k;
+    for (int i = t; i < m; i += nt) list[i] = srt[i];
+    if (t == 0) {
+      cnt[q] = m;
+      thr[q] = n >= k ? key_to_dist(static_cast<uint32_t>(srt[k - 1] >> 32) ^ flip)
+                      : (largest ? -INFINITY : INFINITY);
     }
-    n = cap;
-  }
-  uint64_t *list = cand + q * cap;
-  const int np2 = next_pow2(n);
-  for (int i = tid; i < np2; i += kCompactThreads) s[i] = i < n ? list[i] : ~0ull;
-  bitonic_sort(s, np2);
-  const int m = n < k ? n : k;
-  for (int i = tid; i < m; i += kCompactThreads) list[i] = s[i];
-  if (tid == 0) {
-    cnt[q] = m;
-    thr[q] = n >= k ? key_to_dist(static_cast<uint32_t>(s[k - 1] >> 32) ^ flip)
-                    : (largest ? -INFINITY : INFINITY);
-  }
-  if (d_out) {
-    for (int i = tid; i < k; i += kCompactThreads) {
-      float dv = largest ? -INFINITY : INFINITY;
-      int32_t iv = -1;
-      if (i < m) {
-        dv = key_to_dist(static_cast<uint32_t>(s[i] >> 32) ^ flip);
-        iv = static_cast<int32_t>(static_cast<uint32_t>(s[i]));
+    if (d_out) {
+      for (int i = t; i < k; i += nt) {
+        float dv = largest ? -INFINITY : INFINITY;
+        int32_t iv = -1;
+        if (i < m) {
+          dv = key_to_dist(static_cast<uint32_t>(srt[i] >> 32) ^ flip);
+          iv = static_cast<int32_t>(static_cast<uint32_t>(srt[i]));
+        }
+        d_out[q * k + i] = dv;
+        i_out[q * k + i] = iv;
       }
-      d_out[q * k + i] = dv;
-      i_out[q * k + i] = iv;
     }
+  };
+
+  int n = 0;
+  if (q_w < Q) {
+    n = fixed_cnt >= 0 ? fixed_cnt : cnt[q_w];
+    if (n > cap) {
+      if (lane == 0) {
+        atomicOr(overflow, 1);
+        if (row_flags) row_flags[q_w] = 1;
+      }
+      n = cap;
+    }
+    if (n <= kWarpSort) {
+      uint64_t *a = s_small[w];
+      const uint64_t *list = cand + q_w * cap;
+      const int np2 = next_pow2(n);
+      for (int i = lane; i < np2; i += 32) a[i] = i < n ? list[i] : ~0ull;
+      warp_bitonic(a, np2, lane);
+      emit(q_w, a, n, lane, 32);
+      n = 0;  // done
+    }
+  }
+  if (lane == 0) s_n[w] = n;
+  __syncthreads();
+  for (int r = 0; r < 4; ++r) {  // long lists: the whole CTA, block-uniform
+    const int nr = s_n[r];
+    if (nr == 0) continue;
+    const int64_t q = static_cast<int64_t>(blockIdx.x) * 4 + r;
+    const uint64_t *list = cand + q * cap;
+    const int np2 = next_pow2(nr);
+    for (int i = tid; i < np2; i += kCompactThreads) s_big[i] = i < nr ? list[i] : ~0ull;
+    bitonic_sort(s_big, np2);
+    emit(q, s_big, nr, tid, kCompactThreads);
+    __syncthreads();
   }
 }
 
@@ -205,8 +257,8 @@ int launch_topk_compact(dali_ctx *ctx, uint64_t *cand, int32_t *cand_cnt, float 
   if (cap > kCompactCap || k > cap)
     return set_err(ctx, DALI_ERR_INVALID, "top-k compaction: cap <= 1024 and k <= cap");
   KTimer t(ctx, DALI_K_TOPK);
-  topk_compact_kernel<<<static_cast<unsigned>(Q), kCompactThreads, 0, ctx->stream>>>(
-      cand, cand_cnt, thr, cap, k, largest, fixed_cnt, overflow, d_out, i_out, row_flags);
+  topk_compact_kernel<<<static_cast<unsigned>((Q + 3) / 4), kCompactThreads, 0, ctx->stream>>>(
+      cand, cand_cnt, thr, Q, cap, k, largest, fixed_cnt, overflow, d_out, i_out, row_flags);
   DALI_CUDA_OK(ctx, cudaGetLastError());
   return DALI_OK;
 }
