@@ -1,5 +1,8 @@
-// Q x G x D distance contraction on the 5th-generation tensor cores (SURVEY 8a rows a2/a2',
-// precisions DALI_PREC_TF32, DALI_PREC_TF32X3 and DALI_PREC_TF32C).
+// Q x G x D distance contraction on the 5th-generation tensor cores, one CTA per tile (SURVEY 8a
+// rows a2/a2', precisions DALI_PREC_TF32, DALI_PREC_TF32X3 and DALI_PREC_TF32C).  The first
+// tcgen05 kernel of this repo; the default path is now the CTA-pair kernel of distmat_umma2.cu and
+// this one is kept as its bit-identical cross-check (DALI_UMMA_2CTA=0, see
+// tests/test_gpu_distmat.py::test_two_cta_kernel_equals_one_cta_kernel).
 //
 //   out[i,j] = epilogue( sum_k A[i,k] * B[j,k] )        A = prepared queries, B = gallery
 //

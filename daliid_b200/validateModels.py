@@ -33,7 +33,8 @@ class validateModels:
 
     #: callable(subset, img_height, img_width, model, batch_size, gpu_index) -> [N, D] tensor
     feature_extractor = staticmethod(_reference_extract_features)
-    #: arithmetic of the contraction: "tf32x3" (fp32 class, tensor cores), "fp32", "tf32"
+    #: arithmetic of the contraction: "auto" (fp32 class on the tensor cores: f16x3 for the unit
+    #: rows of the cosine path), "fp32" (exact SIMT path), "tf32" / "f16" (single pass)
     precision = metrics.DEFAULT_PRECISION
     #: keep extracted features on the GPU when the extractor returns CUDA tensors
     ranks = [1, 5, 10]
