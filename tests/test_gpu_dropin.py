@@ -139,3 +139,31 @@ def test_device_feature_sink_equals_reference_loop():
     a = metrics.evaluate_features(dev[:37].contiguous(), dev[37:].contiguous(), qp, gp, qc, gc)
     b = metrics.evaluate_features(ref[:37].contiguous(), ref[37:].contiguous(), qp, gp, qc, gc)
     assert np.array_equal(a[0], b[0]) and a[1] == b[1]
+
+
+def test_training_side_proxy_utilities():
+    """the trainer's two torch.cdist uses (train_encodersKIT.py:146-153, 252-284) on
+    the library's Euclidean kernel -- same numbers as the reference expressions on the CPU."""
+    from daliid_b200 import proxies
+    g = torch.Generator().manual_seed(2)
+    X = torch.randn(400, 96, generator=g)
+    X = X / torch.norm(X, dim=1, keepdim=True)
+    labels = np.arange(400) // 5
+    # reference: min distance between different-label proxies
+    d = torch.cdist(X, X, p=2.0)
+    temp = np.array([labels])
+    rep = temp.repeat(temp.shape[1], axis=0)
+    mask = torch.Tensor(np.int32(rep == rep.T))
+    ref_min = torch.min(mask * torch.max(d) + (1 - mask) * d).item()
+    assert abs(proxies.min_negative_distance(X, labels) - ref_min) <= 1e-5
+    # reference: farthest-point selection with the same random start
+    np.random.seed(12)
+    sel, mx = proxies.selectProxiesByTriagulation(X[:60], num_proxies=5)
+    np.random.seed(12)
+    cum = torch.ones(60) * torch.max(d[:60, :60])
+    ref = [np.random.choice(60)]
+    for j in range(4):
+        cum = np.minimum(cum, d[:60, :60][ref[j]])
+        ref.append(torch.argsort(cum, stable=True)[-1].item())
+    assert sel.tolist() == ref
+    assert abs(mx - torch.max(d[:60, :60][ref, :][:, ref]).item()) <= 1e-5
