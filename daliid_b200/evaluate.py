@@ -33,12 +33,19 @@ def calculate_metrics(distmat, queries, gallery):
 
 def calculateMetrics(queries_images, gallery_images, distmat, pooling=None, version=None):
     """``calculateMetrics(queries_images, gallery_images, distmat, pooling=None, version=None)``
-    -- evaluateCleanATModels.py:259-274.  The ``pooling`` ROC branch (276-292) is dead code in
-    the reference (never passed) and out of scope."""
-    if pooling:
-        raise NotImplementedError("the ROC branch (evaluateCleanATModels.py:276-292) is out of scope")
+    -- evaluateCleanATModels.py:259-292.  With ``pooling`` set, the ROC over all pairs is computed
+    and saved as ``FPR_<version>.npy``, ``TPR_<version>.npy``, ``Thresholds_<version>.npy`` exactly
+    as the reference's (never exercised) branch does (276-292)."""
     calculate_metrics(distmat, queries_images, gallery_images)
     calculateMetrics.last = calculate_metrics.last
+    if pooling:
+        print((queries_images.shape[0], gallery_images.shape[0]), (queries_images.shape[0], gallery_images.shape[0]))
+        from .verification import roc_curve_pairs
+        fpr, tpr, thresholds = roc_curve_pairs(distmat, queries_images[:, 1], gallery_images[:, 1])
+        np.save("FPR_%s" % version, fpr)
+        np.save("TPR_%s" % version, tpr)
+        np.save("Thresholds_%s" % version, thresholds)
+        print("ROC Curve calculated!")
 
 
 def evaluate_single_model(queries_fvs, gallery_fvs, queries, gallery, precision=metrics.DEFAULT_PRECISION):

@@ -167,3 +167,25 @@ def test_training_side_proxy_utilities():
         ref.append(torch.argsort(cum, stable=True)[-1].item())
     assert sel.tolist() == ref
     assert abs(mx - torch.max(d[:60, :60][ref, :][:, ref]).item()) <= 1e-5
+
+
+def test_roc_over_all_pairs_equals_sklearn(tiny, tmp_path, monkeypatch):
+    """the reference's ROC branch (evaluateCleanATModels.py:276-292) -- same arrays
+    as sklearn.metrics.roc_curve on the flattened pair labels / scores, ties included."""
+    from sklearn.metrics import roc_curve
+    from daliid_b200 import evaluate, verification
+    z, q_rows, g_rows, _ = tiny
+    rng = np.random.default_rng(0)
+    for dist in (z["cosine"], (np.round(rng.random((60, 500)) * 64) / 32).astype(np.float32)):
+        Q, G = dist.shape
+        qp = z["q_pid"][:Q] if Q <= len(z["q_pid"]) else rng.integers(0, 9, Q)
+        gp = z["g_pid"][:G] if G <= len(z["g_pid"]) else rng.integers(0, 9, G)
+        labels = np.int32(np.asarray(qp)[:, None] == np.asarray(gp)[None, :]).flatten()
+        preds = 1.0 - dist.flatten() / 2.0
+        e_fpr, e_tpr, e_thr = roc_curve(labels, preds, pos_label=1)
+        fpr, tpr, thr = verification.roc_curve_pairs(dist, qp, gp)
+        assert np.array_equal(fpr, e_fpr) and np.array_equal(tpr, e_tpr) and np.array_equal(thr, e_thr)
+    monkeypatch.chdir(tmp_path)
+    evaluate.calculateMetrics(q_rows, g_rows, z["cosine"], pooling="gap", version="t")
+    assert np.array_equal(np.load(tmp_path / "FPR_t.npy"), roc_curve(
+        np.int32(z["q_pid"][:, None] == z["g_pid"][None, :]).flatten(), 1.0 - z["cosine"].flatten() / 2.0)[0])
