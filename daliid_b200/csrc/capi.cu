@@ -93,6 +93,52 @@ static bool is_device_ptr(const void *p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+static int next_event(dali_ctx *ctx, cudaEvent_t *out) {
+  if (ctx->next_event == ctx->chunk_events.size()) {
+    cudaEvent_t e;
+    DALI_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->chunk_events.push_back(e);
+  }
+  *out = ctx->chunk_events[ctx->next_event++];
+  return DALI_OK;
+}
+
+// Host -> device copy of one contiguous block, split over the context's copy streams (concurrent
+// DMA), ordered after everything enqueued on the compute stream when `fence` is set, and with the
+// compute stream made to wait for its completion.  Events come from a pool that a call resets.
+static int h2d_parallel(dali_ctx *ctx, void *dst, const void *src, size_t bytes, bool fence) {
+  for (auto &st : ctx->copy_streams)
+    if (!st) DALI_CUDA_OK(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cudaEvent_t ev;
+  if (fence) {
+    int rc = next_event(ctx, &ev);
+    if (rc) return rc;
+    DALI_CUDA_OK(ctx, cudaEventRecord(ev, ctx->stream));
+    for (auto st : ctx->copy_streams) DALI_CUDA_OK(ctx, cudaStreamWaitEvent(st, ev, 0));
+  }
+  static const char *env_s = getenv("DALI_H2D_STREAMS");
+  if (env_s) ctx->h2d_streams = std::max(1, std::min(static_cast<int>(dali_ctx::kCopyStreams), atoi(env_s)));
+  // Default: one DMA stream.  Splitting a copy over several streams raised the raw copy rate on
+  // one host (39 -> 53 GB/s) but made the chunked copy/compute pipeline slower on the hosts where
+  // a single stream already reaches ~55 GB/s (e2e 3.15 -> 3.54 ms), and a per-process probe did
+  // not predict which; DALI_H2D_STREAMS=2..4 opts in.
+  const int want = ctx->h2d_streams ? ctx->h2d_streams : 1;
+  const int parts = bytes >= (2u << 20) ? want : 1;
+  const size_t per = ((bytes + parts - 1) / parts + 255) & ~size_t(255);
+  for (int i = 0; i < parts; ++i) {
+    const size_t b0 = per * i;
+    if (b0 >= bytes) break;
+    const size_t nb = std::min(per, bytes - b0);
+    DALI_CUDA_OK(ctx, cudaMemcpyAsync(static_cast<char *>(dst) + b0, static_cast<const char *>(src) + b0, nb,
+                                      cudaMemcpyHostToDevice, ctx->copy_streams[i]));
+    int rc = next_event(ctx, &ev);
+    if (rc) return rc;
+    DALI_CUDA_OK(ctx, cudaEventRecord(ev, ctx->copy_streams[i]));
+    DALI_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ev, 0));
+  }
+  return DALI_OK;
+}
+
 // Returns a device pointer holding rows x cols fp32 with leading dimension *ld_out.
 static int stage_in(dali_ctx *ctx, int slot, const float *p, int64_t rows, int64_t cols, int64_t ld,
                     const float **out, int64_t *ld_out) {
@@ -105,8 +151,9 @@ static int stage_in(dali_ctx *ctx, int slot, const float *p, int64_t rows, int64
   int rc = ws_ensure(ctx, slot, sizeof(float) * rows * cols, &d);
   if (rc) return rc;
   if (ld == cols) {
-    DALI_CUDA_OK(ctx, cudaMemcpyAsync(d, p, sizeof(float) * rows * cols, cudaMemcpyHostToDevice,
-                                      ctx->stream));
+    ctx->next_event = 0;  // the event pool is reused call by call (stream order keeps this safe)
+    rc = h2d_parallel(ctx, d, p, sizeof(float) * rows * cols, true);
+    if (rc) return rc;
   } else {
     DALI_CUDA_OK(ctx, cudaMemcpy2DAsync(d, sizeof(float) * cols, p, sizeof(float) * ld,
                                         sizeof(float) * cols, rows, cudaMemcpyHostToDevice,
@@ -479,7 +526,8 @@ void dali_ctx_destroy(dali_ctx *ctx) {
   if (ctx->plan_stage) cudaFreeHost(ctx->plan_stage);
   if (ctx->plan_stage_done) cudaEventDestroy(ctx->plan_stage_done);
   for (auto e : ctx->chunk_events) cudaEventDestroy(e);
-  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (auto st : ctx->copy_streams)
+    if (st) cudaStreamDestroy(st);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -593,28 +641,20 @@ static int gallery_pipelined(dali_ctx *ctx, const Prepared &a, const float *g_ho
   rc = ws_ensure(ctx, WS_GIN, sizeof(float) * G * D, &gin_v);
   if (rc) return rc;
   float *gin = static_cast<float *>(gin_v);
-  if (!ctx->copy_stream)
-    DALI_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   int64_t chunk = round_up(std::max<int64_t>(256, (12ll << 20) / (sizeof(float) * D)), 256);
   if ((G + chunk - 1) / chunk > 24) chunk = round_up((G + 23) / 24, 256);
   const int nchunks = static_cast<int>((b.rows_pad + chunk - 1) / chunk);
-  while (static_cast<int>(ctx->chunk_events.size()) < nchunks + 1) {
-    cudaEvent_t e;
-    DALI_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    ctx->chunk_events.push_back(e);
-  }
-  // the copy stream starts after everything already enqueued on the compute stream
-  DALI_CUDA_OK(ctx, cudaEventRecord(ctx->chunk_events[nchunks], ctx->stream));
-  DALI_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_events[nchunks], 0));
+  bool first = true;
   for (int c = 0; c < nchunks; ++c) {
     const int64_t r0 = c * chunk;
     const int64_t r1 = std::min(b.rows_pad, r0 + chunk);
     const int64_t n_valid = std::max<int64_t>(0, std::min(G, r1) - r0);
     if (n_valid > 0) {
-      DALI_CUDA_OK(ctx, cudaMemcpyAsync(gin + r0 * D, g_host + r0 * D, sizeof(float) * n_valid * D,
-                                        cudaMemcpyHostToDevice, ctx->copy_stream));
-      DALI_CUDA_OK(ctx, cudaEventRecord(ctx->chunk_events[c], ctx->copy_stream));
-      DALI_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_events[c], 0));
+      // the first copy starts after everything already enqueued on the compute stream (the
+      // staging buffer may still be read by a previous call); later ones follow in stream order
+      rc = h2d_parallel(ctx, gin + r0 * D, g_host + r0 * D, sizeof(float) * n_valid * D, first);
+      if (rc) return rc;
+      first = false;
     }
     rc = prep_rows(ctx, b, gin + r0 * D, D, D, r0, n_valid, r1, precision, normalize);
     if (rc) return rc;

@@ -104,8 +104,12 @@ struct dali_ctx {
   size_t plan_stage_cap = 0;
   cudaEvent_t plan_stage_done = nullptr;  // the last upload out of plan_stage
   bool pool_ready = false;
-  cudaStream_t copy_stream = nullptr;  // H2D of host operands, overlapped with compute
+  // H2D of host operands on side streams, overlapped with compute
+  static constexpr int kCopyStreams = 4;
+  cudaStream_t copy_streams[kCopyStreams] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> chunk_events;
+  size_t next_event = 0;
+  int h2d_streams = 1;  // DMA streams one H2D copy is split over (DALI_H2D_STREAMS)
   // timing
   bool timing = false;
   int t_launches[DALI_K_COUNT_] = {0};
