@@ -26,11 +26,16 @@ def test_market_exact_paths_vs_cpu_reference(market):
     qf, gf, qp, gp, qc, gc = market
     sel = torch.arange(0, qf.shape[0], 17, device="cuda")[:160]
     ref = do.cosine_distmat(qf[sel].cpu(), gf.cpu()).numpy()
-    for precision in ("fp32", "tf32x3", "tf32c"):
+    for precision in ("fp32", "tf32x3", "tf32c", "f16x3"):
         d = metrics.compute_distance_matrix(qf, gf, "cosine", precision)
         sub = d[sel].cpu().numpy()
         err = np.abs(sub.astype(np.float64) - ref) / np.maximum(1.0, np.abs(ref))
         assert err.max() <= 1e-5, (precision, err.max())
+        # north_star's wording, "within 1e-5 relative": purely relative wherever 1 - cos is not
+        # ill-conditioned (the CPU sgemm itself is only good to ~1e-6 absolute)
+        big = np.abs(ref) >= 0.05
+        rel = np.abs(sub.astype(np.float64) - ref)[big] / np.abs(ref)[big]
+        assert big.mean() > 0.99 and rel.max() <= 1e-5, (precision, rel.max())
         cmc, mAP, ap, first, nv = metrics.evaluate_rank_detailed(
             d[sel].contiguous(), qp[sel.cpu().numpy()], gp, qc[sel.cpu().numpy()], gc)
         e = c_oracle.evaluate_rank_c(sub, qp[sel.cpu().numpy()], gp, qc[sel.cpu().numpy()], gc,
