@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libdaliid_b200.so")
 # ---- constants mirrored from include/daliid_b200.h -------------------------------
 ABI_VERSION = 1
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_VALID_QUERY, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3, -4, -5
+ERR_PEER_CAPACITY = -6
 METRICS = {"cosine": 0, "sqeuclidean": 1, "euclidean": 2, "dot": 3}
 PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2, "tf32c": 3, "f16x3": 4, "f16": 5}
 ACCUMS = {"cy_f32": 0, "py_f64": 1}
@@ -72,6 +73,9 @@ _SIGNATURES = {
     "dali_peer_capacity": (i64, [c_vp]),
     "dali_peer_buffer": (c_vp, [c_vp, ci]),
     "dali_peer_allreduce_i32": (ci, [c_vp, c_vp, ci, c_vp, i64]),
+    "dali_eval_features_sharded_f32": (ci, [c_vp, c_vp, c_vp, i64, c_vp, i64, i64, i64, i64, c_i32p, c_i32p,
+                                            c_i32p, c_i32p, ci, ci, ci, ci, ci, c_f32p, c_f64p, c_f64p,
+                                            c_i32p, c_i64p, c_i64p]),
     "dali_rerank_f32": (ci, [c_vp, c_vp, i64, c_vp, i64, c_vp, i64, i64, i64, ci, ci, ctypes.c_double, c_vp, i64]),
     "dali_fuse_f32": (ci, [c_vp, ctypes.POINTER(c_vp), ci, ctypes.POINTER(c_vp),
                            ctypes.POINTER(c_vp), c_vp, i64, i64, i64]),

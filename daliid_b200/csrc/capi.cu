@@ -1166,6 +1166,62 @@ int dali_rerank_f32(dali_ctx *ctx, const float *qg, int64_t ld_qg, const float *
   return DALI_OK;
 }
 
+int dali_eval_features_sharded_f32(dali_ctx *ctx, dali_peer *peer, const float *q, int64_t Q,
+                                   const float *g_slab, int64_t Gs, int64_t D, int64_t g0,
+                                   int64_t G_total, const int32_t *q_pid, const int32_t *g_pid_all,
+                                   const int32_t *q_cam, const int32_t *g_cam_all, int metric,
+                                   int precision, int normalize, int max_rank, int accum_mode,
+                                   float *cmc, double *mAP, double *ap_opt, int32_t *first_rank_opt,
+                                   int64_t *num_valid_opt, int64_t *matches_out) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (!peer || Q < 0 || Gs < 0 || D <= 0 || g0 < 0 || g0 + Gs > G_total || (!q && Q) || (!g_slab && Gs) ||
+      !cmc || !mAP || max_rank < 1)
+    return set_err(ctx, DALI_ERR_INVALID, "eval_features_sharded: bad shape or null pointer");
+  rc = check_metric_prec(ctx, metric, precision, normalize);
+  if (rc) return rc;
+  if (metric == DALI_METRIC_DOT)
+    return set_err(ctx, DALI_ERR_INVALID, "eval_features_sharded ranks distances; DOT is a similarity");
+  // 1. slab contraction (asynchronous), 2. plan of the WHOLE gallery while the GPU works
+  const int64_t ldd = round_up(std::max<int64_t>(Gs, 1), 4);
+  void *t;
+  rc = ws_ensure(ctx, WS_DIST, sizeof(float) * std::max<int64_t>(Q, 1) * ldd, &t);
+  if (rc) return rc;
+  float *dd = static_cast<float *>(t);
+  if (Q && Gs) {
+    rc = distmat_to(ctx, q, Q, g_slab, Gs, D, metric, precision, normalize, dd, ldd);
+    if (rc) return rc;
+  }
+  dali_rank_plan *plan = nullptr;
+  rc = dali_rank_plan_create(ctx, q_pid, g_pid_all, q_cam, g_cam_all, Q, G_total, &plan);
+  if (rc) return rc;
+  const int64_t M = plan->M;
+  if (matches_out) *matches_out = M;
+  if (M > dali_peer_capacity(peer)) {
+    dali_rank_plan_destroy(plan);
+    return set_err(ctx, DALI_ERR_PEER_CAPACITY, "peer block holds fewer words than there are matches");
+  }
+  void *keys = nullptr, *counts = nullptr;
+  if ((rc = ws_ensure(ctx, WS_KEYS, sizeof(uint32_t) * std::max<int64_t>(M, 1), &keys)) ||
+      (rc = ws_ensure(ctx, WS_COUNTS, sizeof(int32_t) * std::max<int64_t>(M, 1), &counts))) {
+    dali_rank_plan_destroy(plan);
+    return rc;
+  }
+  // 3. gather -> exchange -> count -> exchange (contributions written straight into the peer block)
+  rc = launch_rank_gather(ctx, plan, dd, ldd, g0, Gs, static_cast<uint32_t *>(dali_peer_buffer(peer, 0)));
+  if (!rc) rc = dali_peer_allreduce_i32(ctx, peer, 0, static_cast<int32_t *>(keys), M);
+  if (!rc)
+    rc = launch_rank_count(ctx, plan, dd, ldd, g0, Gs, static_cast<const uint32_t *>(keys),
+                           static_cast<int32_t *>(dali_peer_buffer(peer, 1)));
+  if (!rc) rc = dali_peer_allreduce_i32(ctx, peer, 1, static_cast<int32_t *>(counts), M);
+  // 4. finalize on every rank
+  if (!rc)
+    rc = dali_rank_finalize(ctx, plan, static_cast<const uint32_t *>(keys), static_cast<const int32_t *>(counts),
+                            max_rank, accum_mode, cmc, mAP, ap_opt, first_rank_opt, num_valid_opt);
+  dali_rank_plan_destroy(plan);
+  return rc;
+}
+
 static int topk_features_unfused(dali_ctx *ctx, const Prepared &b, const float *q, int64_t Q, int64_t G,
                                  int64_t D, int metric, int precision, int normalize, int k,
                                  int largest, int32_t g_base, float *d_out, int32_t *i_out) {

@@ -278,11 +278,68 @@ def evaluate_features_sharded(qf, gf_slab, g0, q_pids, g_pids_all, q_camids, g_c
     ops = ops or CudaOps(qf.device.index if getattr(qf, "is_cuda", False) else None)
     if normalize is None:
         normalize = metric == "cosine"
+    world, _ = _world(group)
+    if (isinstance(ops, CudaOps) and world > 1 and exchange in ("auto", "peer")
+            and dist.get_backend(group) == "nccl"):
+        res = _evaluate_features_one_call(ops, qf, gf_slab, g0, q_pids, g_pids_all, q_camids, g_camids_all,
+                                          metric, precision, normalize, max_rank, accum, group,
+                                          strict=exchange == "peer")
+        if res is not None:
+            return res if return_details else res[:2]
     dist_slab = ops.distmat(qf, gf_slab, metric, precision, normalize)
     if not isinstance(dist_slab, torch.Tensor):
         dist_slab = torch.from_numpy(dist_slab)
     return evaluate_rank_sharded(dist_slab, g0, q_pids, g_pids_all, q_camids, g_camids_all,
                                  max_rank, accum, group, ops, return_details, exchange)
+
+
+def _evaluate_features_one_call(ops, qf, gf_slab, g0, q_pids, g_pids_all, q_camids, g_camids_all, metric,
+                                precision, normalize, max_rank, accum, group, strict):
+    """The whole per-rank sequence inside ``dali_eval_features_sharded_f32`` (exchange over NVLink
+    peer memory): one library call per evaluation.  Returns None -- on every rank -- when peer
+    mapping is unavailable, so that the caller falls back to the step-by-step NCCL path."""
+    from ._lib import as_matrix
+    a = as_matrix(qf, np.float32, "qf")
+    b = as_matrix(gf_slab, np.float32, "gf_slab")
+    if a.shape[1] != b.shape[1] or a.ld != a.shape[1] or b.ld != b.shape[1]:
+        raise ValueError("feature matrices must be contiguous with equal dimension")
+    qp, gp = metrics.canonicalize_labels(q_pids, g_pids_all)
+    qc, gc = metrics.canonicalize_labels(q_camids, g_camids_all)
+    Q, D = a.shape
+    Gs, G = b.shape[0], len(gp)
+    if len(qp) != Q or len(qc) != Q or len(gc) != G or g0 < 0 or g0 + Gs > G:
+        raise ValueError("label arrays do not match the feature matrices / slab")
+    if G < max_rank:
+        max_rank = G
+        print("Note: number of gallery samples is quite small, got {}".format(G))
+    ctx = ops.ctx
+    ctx.attach_torch_stream()
+    need = getattr(ops, "_last_matches", 1 << 16)
+    for _ in range(3):
+        px = peer_exchange(ops, need, group)
+        if px is None:
+            if strict:
+                raise _lib.DaliError("peer exchange requested but CUDA IPC mapping failed on some rank")
+            return None
+        cmc = np.zeros(max_rank, dtype=np.float32)
+        mAP = ctypes.c_double(0.0)
+        ap = np.zeros(Q, dtype=np.float64)
+        first = np.zeros(Q, dtype=np.int32)
+        nvalid = ctypes.c_int64(0)
+        matches = ctypes.c_int64(0)
+        rc = ctx.lib.dali_eval_features_sharded_f32(
+            ctx.h, px.h, c_vp(a.ptr), Q, c_vp(b.ptr), Gs, D, int(g0), G, p_i32(qp), p_i32(gp), p_i32(qc),
+            p_i32(gc), metrics._enum(metrics.METRICS, metric, "metric"), metrics._precision(precision, normalize),
+            1 if normalize else 0, int(max_rank), ACCUMS[accum], cmc.ctypes.data_as(_lib.c_f32p),
+            ctypes.byref(mAP), ap.ctypes.data_as(_lib.c_f64p), first.ctypes.data_as(_lib.c_i32p),
+            ctypes.byref(nvalid), ctypes.byref(matches))
+        ops._last_matches = int(matches.value)
+        if rc == _lib.ERR_PEER_CAPACITY:  # same answer on every rank: grow the block collectively
+            need = int(matches.value)
+            continue
+        ctx.check(rc)
+        return cmc, float(mAP.value), {"ap": ap, "first_rank": first, "num_valid": int(nvalid.value)}
+    raise _lib.DaliError("peer block could not be sized for the number of matches")
 
 
 def topk_features_sharded(qf, gf_slab, g0, k=20, metric="cosine", precision=metrics.DEFAULT_PRECISION,

@@ -45,6 +45,7 @@ extern "C" {
                                         identities do not appear in gallery')             */
 #define DALI_ERR_UNSUPPORTED (-4)
 #define DALI_ERR_NOMEM (-5)
+#define DALI_ERR_PEER_CAPACITY (-6) /* peer block smaller than the number of matches: re-create it */
 
 /* ---- enums --------------------------------------------------------------- */
 /* distance metric (a2 / a2') */
@@ -252,6 +253,20 @@ void dali_peer_destroy(dali_peer *peer);
 int64_t dali_peer_capacity(const dali_peer *peer);
 void *dali_peer_buffer(dali_peer *peer, int which);
 int dali_peer_allreduce_i32(dali_ctx *ctx, dali_peer *peer, int which, int32_t *out, int64_t n);
+/* The whole sharded evaluation of one rank in one call: slab contraction, plan, gather, exchange,
+ * count, exchange, finalize (the sequence daliid_b200/sharded.py otherwise drives call by call).
+ * q [Q,D] and g_slab [Gs,D]: host or device; g0 = first gallery index of the slab; labels of the
+ * WHOLE gallery (G_total).  Outputs as dali_eval_rank_f32, identical on every rank.  Returns
+ * DALI_ERR_PEER_CAPACITY with *matches_out = required capacity when the peer block is too small
+ * (every rank gets the same answer: re-create the block collectively and call again).
+ * Collective: all ranks call it together. */
+int dali_eval_features_sharded_f32(dali_ctx *ctx, dali_peer *peer, const float *q, int64_t Q,
+                                   const float *g_slab, int64_t Gs, int64_t D, int64_t g0,
+                                   int64_t G_total, const int32_t *q_pid, const int32_t *g_pid_all,
+                                   const int32_t *q_cam, const int32_t *g_cam_all, int metric,
+                                   int precision, int normalize, int max_rank, int accum_mode,
+                                   float *cmc, double *mAP, double *ap_opt, int32_t *first_rank_opt,
+                                   int64_t *num_valid_opt, int64_t *matches_out);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop
