@@ -24,7 +24,7 @@ PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2, "tf32c": 3, "f16x3": 4, "f16": 
 ACCUMS = {"cy_f32": 0, "py_f64": 1}
 K_NORMALIZE, K_DISTMAT, K_RANK_COUNT, K_RANK_FINALIZE, K_TOPK, K_FUSE, K_RANK_GATHER, K_RERANK = range(8)
 KERNEL_SLOTS = {"normalize": 0, "distmat": 1, "rank_count": 2, "rank_finalize": 3, "topk": 4,
-                "fuse": 5, "rank_gather": 6, "rerank": 7}
+                "fuse": 5, "rank_gather": 6, "rerank": 7, "mrfuse": 8}
 CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy handle
 
 NO_VALID_MSG = "Error: all query identities do not appear in gallery"
@@ -79,6 +79,8 @@ _SIGNATURES = {
     "dali_rerank_f32": (ci, [c_vp, c_vp, i64, c_vp, i64, c_vp, i64, i64, i64, ci, ci, ctypes.c_double, c_vp, i64]),
     "dali_fuse_f32": (ci, [c_vp, ctypes.POINTER(c_vp), ci, ctypes.POINTER(c_vp),
                            ctypes.POINTER(c_vp), c_vp, i64, i64, i64]),
+    "dali_mrfuse_f32": (ci, [c_vp, ctypes.POINTER(c_vp), ci, i64, i64, i64, ci, ci, ctypes.c_float, c_vp, i64,
+                             c_vp, c_vp, c_vp]),
     "dali_eval_rank_f32": (ci, [c_vp, c_vp, i64, i64, i64, c_i32p, c_i32p, c_i32p, c_i32p, ci, ci,
                                 c_f32p, c_f64p, c_f64p, c_i32p, c_i64p]),
     "dali_eval_features_f32": (ci, [c_vp, c_vp, i64, c_vp, i64, i64, c_i32p, c_i32p, c_i32p,

@@ -1166,6 +1166,49 @@ int dali_rerank_f32(dali_ctx *ctx, const float *qg, int64_t ld_qg, const float *
   return DALI_OK;
 }
 
+int dali_mrfuse_f32(dali_ctx *ctx, const float *const *scores, int n, int64_t Q, int64_t G,
+                    int64_t ld, int topk, int use_columns, float killscale, double *fused,
+                    int64_t ld_out, double *fit_opt, float *small_opt, double *weights_opt) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (!scores || n < 1 || n > 3 || Q < 1 || G < 1 || ld < G || ld_out < G || !fused)
+    return set_err(ctx, DALI_ERR_INVALID, "mrfuse: bad shape or null pointer");
+  const float *ds[3] = {nullptr, nullptr, nullptr};
+  const int slots[3] = {WS_STAGE_A, WS_STAGE_B, WS_STAGE_C};
+  int64_t lds[3] = {0, 0, 0};
+  for (int m = 0; m < n; ++m) {
+    if (!scores[m]) return set_err(ctx, DALI_ERR_INVALID, "mrfuse: null score matrix");
+    if ((rc = stage_in(ctx, slots[m], scores[m], Q, G, ld, &ds[m], &lds[m]))) return rc;
+    if (lds[m] != lds[0]) return set_err(ctx, DALI_ERR_INVALID, "mrfuse: score matrices must share one layout");
+  }
+  const bool odev = is_device_ptr(fused);
+  const bool wdev = !weights_opt || is_device_ptr(weights_opt);
+  double *od = fused, *wd = weights_opt;
+  int64_t ldo = ld_out;
+  if (!odev || !wdev) {
+    // host outputs: device images in the internal matrix slot ([1 + n] x [Q, G] fp64)
+    void *t;
+    ldo = G;
+    const size_t one = sizeof(double) * Q * G;
+    if ((rc = ws_ensure(ctx, WS_DIST, one * (weights_opt ? 1 + n : 1), &t))) return rc;
+    od = static_cast<double *>(t);
+    if (weights_opt) wd = od + static_cast<size_t>(Q) * G;
+    if (odev != wdev && weights_opt)
+      return set_err(ctx, DALI_ERR_INVALID, "mrfuse: fused and weights_opt must both be host or both device");
+  }
+  rc = launch_mrfuse(ctx, ds, n, Q, G, lds[0], topk, use_columns, killscale, od, ldo, fit_opt, small_opt, wd);
+  if (rc) return rc;
+  if (!odev) {
+    DALI_CUDA_OK(ctx, cudaMemcpy2DAsync(fused, sizeof(double) * ld_out, od, sizeof(double) * ldo,
+                                        sizeof(double) * G, Q, cudaMemcpyDeviceToHost, ctx->stream));
+    if (weights_opt)
+      DALI_CUDA_OK(ctx, cudaMemcpy2DAsync(weights_opt, sizeof(double) * ld_out, wd, sizeof(double) * ldo,
+                                          sizeof(double) * G, Q * n, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (!odev || fit_opt || small_opt) DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return DALI_OK;
+}
+
 int dali_eval_features_sharded_f32(dali_ctx *ctx, dali_peer *peer, const float *q, int64_t Q,
                                    const float *g_slab, int64_t Gs, int64_t D, int64_t g0,
                                    int64_t G_total, const int32_t *q_pid, const int32_t *g_pid_all,

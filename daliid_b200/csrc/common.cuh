@@ -83,6 +83,8 @@ enum WsSlot {
   WS_RR_V,
   WS_RR_CSC,
   WS_RR_TEMP,
+  WS_MR_T,      // meta-recognition fusion: cleaned transpose [G,Q]
+  WS_MR_MISC,   // kill / low lists, Weibull parameters
   WS_COUNT_
 };
 
@@ -219,6 +221,10 @@ int launch_topk_compact(dali_ctx *ctx, uint64_t *cand, int32_t *cand_cnt, float 
 int launch_rerank(dali_ctx *ctx, const float *qg, int64_t ld_qg, const float *qq, int64_t ld_qq,
                   const float *gg, int64_t ld_gg, int64_t Q, int64_t G, int k1, int k2, double lambda,
                   float *out, int64_t ld_out);
+// mrfuse.cu
+int launch_mrfuse(dali_ctx *ctx, const float *const *s, int n, int64_t Q, int64_t G, int64_t ld,
+                  int topk, int use_columns, float killscale, double *out, int64_t ld_out,
+                  double *fit_opt, float *small_opt, double *weights_opt);
 // fuse.cu
 int launch_fuse(dali_ctx *ctx, const float *const *d_ptrs_dev, int n, const float *const *wq_dev,
                 const float *const *wg_dev, float *out, int64_t Q, int64_t G, int64_t ld);

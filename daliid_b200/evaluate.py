@@ -117,3 +117,22 @@ def evaluate_clean_at_models(q_clean, g_clean, q_dist, g_dist, queries_images, g
         calculateMetrics(queries_images, gallery_images, ens)
         out["weighted"] = ens
     return out
+
+
+class Meta_Recognition(object):
+    """``Meta_Recognition`` of evaluate.py:583-627 / evaluate_ensembled_models.py:593-637: the
+    Weibull fitting (``libmr``) and the fusion run on the GPU (``csrc/mrfuse.cu``)."""
+
+    def metarec(self, scorematrix, topk, use_columns=True, killscale=1):
+        """Per-score weights ``[Q,G]`` fp64 (evaluate.py:587-608)."""
+        _, det = metrics.mrfuse([scorematrix], topk, use_columns, killscale, return_details=True)
+        return det["weights"][0]
+
+    def mrfuse(self, scores01, scores02, scores03):
+        """evaluate.py:610-627: ``metarec(., 20, use_columns=False)`` per model, weighted mean;
+        numpy fp64 ``[Q,G]`` like the reference's ``scores.numpy()`` (the reference also prints
+        three 5x5 weight corners, kept)."""
+        fused, det = metrics.mrfuse([scores01, scores02, scores03], 20, False, 1, return_details=True)
+        for w in det["weights"]:
+            print(w[:5, :5])
+        return fused.cpu().numpy() if hasattr(fused, "cpu") else fused

@@ -33,7 +33,7 @@ from . import _lib
 from ._lib import ACCUMS, METRICS, PRECISIONS, as_i32, as_matrix, c_vp, get_ctx, p_i32
 
 __all__ = [
-    "re_ranking",
+    "re_ranking", "mrfuse",
     "canonicalize_labels",
     "evaluate_rank",
     "evaluate_rank_detailed",
@@ -390,3 +390,38 @@ def evaluate_features(qf, gf, q_pids, g_pids, q_camids, g_camids, metric="cosine
     if return_details:
         res = res + ({"ap": ap, "first_rank": first, "num_valid": int(nvalid.value)},)
     return res
+
+
+def mrfuse(score_mats, topk=20, use_columns=False, killscale=1.0, return_details=False):
+    """Meta-recognition fusion of up to three ``[Q,G]`` SIMILARITY matrices (fp32):
+    ``sum_m(w_m*s_m) / sum_m(w_m)`` with ``w_m`` the CDF of a Weibull fitted per gallery column --
+    ``Meta_Recognition.mrfuse`` / ``metarec`` of evaluate.py:583-627.  Returns fp64 ``[Q,G]`` on the
+    side the inputs live on; with ``return_details`` also ``{"weights": [n,Q,G] fp64,
+    "fit": [n,G,2] (shape, scale), "small": [n,G]}``."""
+    bufs = [as_matrix(m, np.float32, "scores") for m in score_mats]
+    n = len(bufs)
+    if not 1 <= n <= 3:
+        raise ValueError("mrfuse takes one to three score matrices")
+    Q, G = bufs[0].shape
+    dev = bufs[0].device
+    for b in bufs:
+        if b.shape != (Q, G) or b.device != dev:
+            raise ValueError("score matrices must have one shape and live on one device")
+    if len({b.ld for b in bufs}) != 1:  # mixed padded / contiguous layouts: one leading dimension for all
+        bufs = [as_matrix(b.keep.contiguous() if hasattr(b.keep, "contiguous") else np.ascontiguousarray(b.keep),
+                          np.float32, "scores") for b in bufs]
+    ctx = _ctx_for(*bufs)
+    out, optr = _alloc_out((Q, G), dev, "float64")
+    fit = small = weights = None
+    fptr = sptr = wptr = None
+    if return_details:
+        weights, wptr = _alloc_out((n, Q, G), dev, "float64")
+        fit = np.empty((n, G, 2), dtype=np.float64)
+        small = np.empty((n, G), dtype=np.float32)
+        fptr, sptr = fit.ctypes.data, small.ctypes.data
+    ptrs = (c_vp * n)(*[c_vp(b.ptr) for b in bufs])
+    ctx.check(ctx.lib.dali_mrfuse_f32(ctx.h, ptrs, n, Q, G, bufs[0].ld, int(topk), 1 if use_columns else 0,
+                                      float(killscale), c_vp(optr), G, c_vp(fptr), c_vp(sptr), c_vp(wptr)))
+    if return_details:
+        return out, {"weights": weights, "fit": fit, "small": small}
+    return out

@@ -99,7 +99,8 @@ const char *dali_strerror(int code);
 #define DALI_K_FUSE 5
 #define DALI_K_RANK_GATHER 6
 #define DALI_K_RERANK 7
-#define DALI_K_COUNT_ 8
+#define DALI_K_MRFUSE 8
+#define DALI_K_COUNT_ 9
 int dali_ctx_timing_enable(dali_ctx *ctx, int on);
 int dali_ctx_timing_reset(dali_ctx *ctx);
 int dali_ctx_timing_read(dali_ctx *ctx, int which, int *launches, float *total_ms);
@@ -203,6 +204,27 @@ int dali_topk_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float
 int dali_rerank_f32(dali_ctx *ctx, const float *qg, int64_t ld_qg, const float *qq, int64_t ld_qq,
                     const float *gg, int64_t ld_gg, int64_t Q, int64_t G, int k1, int k2,
                     double lambda_value, float *out, int64_t ld_out);
+
+/* ---- next row N3: meta-recognition score fusion --------------------------------- */
+/* fused[Q,G] (fp64) = Meta_Recognition.mrfuse(scores...) of evaluate.py:610-627 (call site, kept
+ * commented by the reference: evaluate.py:277; same class in evaluate_ensembled_models.py:593-637):
+ * per model and gallery column a 2-parameter Weibull is fitted (libmr.FitHigh / _fit,
+ * evaluate.py:429-432, 531-580) to the column's Q-topk-1 largest scores after the top-`topk`
+ * scores of every query row (use_columns = 0, what mrfuse uses) or of every gallery column
+ * (use_columns = 1, metarec's default) were reduced by killscale * themselves; the weight of a
+ * score is that Weibull's CDF (libmr.wscore, evaluate.py:434-473) and
+ * fused = sum_m(w_m * s_m) / sum_m(w_m).
+ * scores: n (1..3) pointers to fp32 [Q,ld] SIMILARITY matrices (1 - distance), all host or all
+ * device.  fused: fp64 [Q,ld_out], host or device.  Optional outputs (NULL to skip; host or
+ * device): fit_opt fp64 [n][G][2] = (shape, scale) exactly as libmr.wbFits holds them (0,0 for a
+ * column whose Newton iteration did not converge in 100 steps, NaN,NaN when it turned NaN),
+ * small_opt fp32 [n][G] = libmr.smallScoreTensor, weights_opt fp64 [n][Q][ld_out] = metarec's
+ * return value.  Needs topk+2 <= Q <= 17066, topk <= 126, and G >= topk when use_columns = 0.
+ * Values agree with the reference run on the same inputs to ~1e-6 relative (the reference's fp32
+ * log / mean intermediates are not reproducible beyond that across libm implementations). */
+int dali_mrfuse_f32(dali_ctx *ctx, const float *const *scores, int n, int64_t Q, int64_t G,
+                    int64_t ld, int topk, int use_columns, float killscale, double *fused,
+                    int64_t ld_out, double *fit_opt, float *small_opt, double *weights_opt);
 
 /* ---- (e) gallery-sharded building blocks ------------------------------------ */
 /* One process per GPU holds all Q queries and a contiguous gallery slab

@@ -65,6 +65,37 @@ def main():
         ms, _ = timeit(lambda: (metrics.compute_distance_matrix(qf, qf, "sqeuclidean", normalize=True),
                                 metrics.compute_distance_matrix(gf, gf, "sqeuclidean", normalize=True)), n=3, warm=1)
         print(f"qq + gg distance matrices: {ms:.2f} ms", flush=True)
+    elif what == "mrfuse":
+        # SURVEY 8f N3 at the Market shape: three models' similarity matrices -> Weibull weights -> fusion
+        sims = []
+        for seed in (12, 13, 14):
+            qf, gf, qp, gp, qc, gc = synth.make_config("market_vit", device="cuda")
+            g = torch.Generator(device="cuda").manual_seed(seed)
+            qf = qf + 0.5 * torch.randn(qf.shape, device="cuda", generator=g)
+            gf = gf + 0.5 * torch.randn(gf.shape, device="cuda", generator=g)
+            sims.append(metrics.compute_distance_matrix(qf, gf, "dot", normalize=True, padded=False))
+        Q, G = sims[0].shape
+        ctx.timing_enable(True); ctx.timing_reset()
+        ms, fused = timeit(lambda: metrics.mrfuse(sims, 20), n=3, warm=1)
+        kt = {k: (v[0], round(v[1], 3)) for k, v in ctx.timing_read().items() if v[0]}
+        ctx.timing_enable(False)
+        c0, m0 = metrics.evaluate_rank((1.0 - sims[0]).contiguous(), qp, gp, qc, gc)
+        c1, m1 = metrics.evaluate_rank((1.0 - fused).float().contiguous(), qp, gp, qc, gc)
+        print(f"mrfuse 3 x [{Q},{G}]: {ms:.2f} ms per call; kernels (launches, total ms over 3 calls): {kt}; "
+              f"mAP {m0:.4f} (model 0) -> {m1:.4f} (fused)", flush=True)
+        # CPU restatement of the reference on a column sample, scaled to all columns
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from oracle import mrfuse_oracle
+        sub = sims[0].cpu()
+        t0 = time.time()
+        srt, small = mrfuse_oracle.tail_of_columns(sub)
+        t1 = time.time()
+        cols = slice(0, 1024)
+        mrfuse_oracle.weibull_fit(srt[cols] + 1 - small[cols, None])
+        t2 = time.time()
+        print(f"CPU (oracle, {torch.get_num_threads()} threads): tail selection {t1 - t0:.2f} s per model, "
+              f"Weibull fit {t2 - t1:.2f} s per 1024 columns -> ~{(t1 - t0 + (t2 - t1) * G / 1024) * 3:.0f} s "
+              f"for three models (without the CDF pass)", flush=True)
     elif what == "ensemble":
         # BASELINE config 4: three models' Market-shaped distance matrices, mean fusion, ranking
         feats = []

@@ -173,3 +173,21 @@ def test_rerank_oracle_matches_golden():
         k1, k2, lam = z["params_" + name]
         out = rr.re_ranking(z["qg"], z["qq"], z["gg"], int(k1), int(k2), float(lam))
         np.testing.assert_allclose(out, z["final_" + name], rtol=0, atol=1e-7)
+
+
+def test_mrfuse_oracle_matches_reference_golden():
+    """oracle/mrfuse_oracle.py against the output of the reference's own libmr / Meta_Recognition
+    classes (tests/golden/make_golden_mrfuse.py)."""
+    from oracle import mrfuse_oracle
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "mrfuse.npz"))
+    for c in "ab":
+        s = [z[f"{c}_s{m}"] for m in range(3)]
+        for m in range(3):
+            w, fit, small = mrfuse_oracle.metarec(s[m])
+            np.testing.assert_array_equal(small, z[f"{c}_small{m}"])
+            np.testing.assert_allclose(fit, z[f"{c}_fit{m}"], rtol=1e-9, equal_nan=True)
+            np.testing.assert_allclose(w, z[f"{c}_w{m}"], rtol=0, atol=1e-9)
+        fused = mrfuse_oracle.mrfuse(*s)
+        np.testing.assert_allclose(fused, z[f"{c}_fused"], rtol=0, atol=1e-9, equal_nan=True)
+    # the degenerate (constant) column of case b never converges: parameters stay (0, 0), weight 0.5
+    assert np.all(z["b_fit0"][5] == 0) and np.all(z["b_w0"][:, 5] == 0.5)
