@@ -1166,6 +1166,31 @@ int dali_rerank_f32(dali_ctx *ctx, const float *qg, int64_t ld_qg, const float *
   return DALI_OK;
 }
 
+int dali_argsort_f32(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t ld,
+                     int descending, int32_t *idx_out) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (Q < 0 || G < 0 || ld < G || (Q && G && (!dist || !idx_out)))
+    return set_err(ctx, DALI_ERR_INVALID, "argsort: bad shape or null pointer");
+  if (Q == 0 || G == 0) return DALI_OK;
+  const float *dd;
+  int64_t ldd;
+  if ((rc = stage_in(ctx, WS_STAGE_A, dist, Q, G, ld, &dd, &ldd))) return rc;
+  const bool odev = is_device_ptr(idx_out);
+  int32_t *od = idx_out;
+  if (!odev) {
+    void *t;
+    if ((rc = ws_ensure(ctx, WS_TOPK_I, sizeof(int32_t) * Q * G, &t))) return rc;
+    od = static_cast<int32_t *>(t);
+  }
+  if ((rc = launch_argsort_rows(ctx, dd, Q, G, ldd, descending, od))) return rc;
+  if (!odev) {
+    DALI_CUDA_OK(ctx, cudaMemcpyAsync(idx_out, od, sizeof(int32_t) * Q * G, cudaMemcpyDeviceToHost, ctx->stream));
+    DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return DALI_OK;
+}
+
 int dali_mrfuse_f32(dali_ctx *ctx, const float *const *scores, int n, int64_t Q, int64_t G,
                     int64_t ld, int topk, int use_columns, float killscale, double *fused,
                     int64_t ld_out, double *fit_opt, float *small_opt, double *weights_opt) {

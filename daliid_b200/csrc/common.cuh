@@ -85,6 +85,7 @@ enum WsSlot {
   WS_RR_TEMP,
   WS_MR_T,      // meta-recognition fusion: cleaned transpose [G,Q]
   WS_MR_MISC,   // kill / low lists, Weibull parameters
+  WS_SORT,      // full row ordering: composite keys, payload, radix scratch
   WS_COUNT_
 };
 
@@ -225,6 +226,9 @@ int launch_rerank(dali_ctx *ctx, const float *qg, int64_t ld_qg, const float *qq
 int launch_mrfuse(dali_ctx *ctx, const float *const *s, int n, int64_t Q, int64_t G, int64_t ld,
                   int topk, int use_columns, float killscale, double *out, int64_t ld_out,
                   double *fit_opt, float *small_opt, double *weights_opt);
+// sortrows.cu
+int launch_argsort_rows(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t ld,
+                        int descending, int32_t *idx_out);
 // fuse.cu
 int launch_fuse(dali_ctx *ctx, const float *const *d_ptrs_dev, int n, const float *const *wq_dev,
                 const float *const *wg_dev, float *out, int64_t Q, int64_t G, int64_t ld);

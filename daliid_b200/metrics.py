@@ -33,7 +33,7 @@ from . import _lib
 from ._lib import ACCUMS, METRICS, PRECISIONS, as_i32, as_matrix, c_vp, get_ctx, p_i32
 
 __all__ = [
-    "re_ranking", "mrfuse",
+    "re_ranking", "mrfuse", "argsort_rows",
     "canonicalize_labels",
     "evaluate_rank",
     "evaluate_rank_detailed",
@@ -425,3 +425,17 @@ def mrfuse(score_mats, topk=20, use_columns=False, killscale=1.0, return_details
     if return_details:
         return out, {"weights": weights, "fit": fit, "small": small}
     return out
+
+
+def argsort_rows(distmat, descending=False):
+    """``torch.argsort(distmat, dim=1, descending=descending, stable=True)`` as int32 ``[Q,G]``:
+    the whole ranked list of every row (getFeatures.py:303,347; ``np.argsort(distmat, axis=1)`` of
+    the torchreid evaluation).  Ties by ascending column; NaN after +inf.  Output lives where the
+    input does."""
+    d = as_matrix(distmat, np.float32, "distmat")
+    Q, G = d.shape
+    ctx = _ctx_for(d)
+    idx, iptr = _alloc_out((Q, G), d.device, "int32")
+    if Q and G:
+        ctx.check(ctx.lib.dali_argsort_f32(ctx.h, c_vp(d.ptr), Q, G, d.ld, 1 if descending else 0, c_vp(iptr)))
+    return idx

@@ -205,6 +205,16 @@ int dali_rerank_f32(dali_ctx *ctx, const float *qg, int64_t ld_qg, const float *
                     const float *gg, int64_t ld_gg, int64_t Q, int64_t G, int k1, int k2,
                     double lambda_value, float *out, int64_t ld_out);
 
+/* ---- next row N4: whole ranked lists ------------------------------------------- */
+/* idx_out[q, r] = column holding the r-th smallest (largest when `descending`) value of row q:
+ * torch.argsort(dist, dim=1, descending=..., stable=True).  replaces the full orderings of
+ * getFeatures.py:303,347 (get_subset / get_subset_one_encoder: one row of similarities to the
+ * whole training set, best first) and the `indices` matrix inside torchreid's evaluation.
+ * Ties by ascending column, NaN after +inf (first when descending), -0 == +0.
+ * dist fp32 [Q,ld] and idx_out int32 [Q,G] contiguous: each host or device. */
+int dali_argsort_f32(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t ld,
+                     int descending, int32_t *idx_out);
+
 /* ---- next row N3: meta-recognition score fusion --------------------------------- */
 /* fused[Q,G] (fp64) = Meta_Recognition.mrfuse(scores...) of evaluate.py:610-627 (call site, kept
  * commented by the reference: evaluate.py:277; same class in evaluate_ensembled_models.py:593-637):

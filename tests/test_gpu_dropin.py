@@ -189,3 +189,52 @@ def test_roc_over_all_pairs_equals_sklearn(tiny, tmp_path, monkeypatch):
     evaluate.calculateMetrics(q_rows, g_rows, z["cosine"], pooling="gap", version="t")
     assert np.array_equal(np.load(tmp_path / "FPR_t.npy"), roc_curve(
         np.int32(z["q_pid"][:, None] == z["g_pid"][None, :]).flatten(), 1.0 - z["cosine"].flatten() / 2.0)[0])
+
+
+# ---- whole ranked lists (get_subset*) -------------------------------------------
+
+@pytest.mark.parametrize("Q,G", [(1, 100003), (7, 4099), (300, 257), (1, 1)])
+@pytest.mark.parametrize("descending", [False, True])
+def test_argsort_rows_equals_torch_stable(Q, G, descending):
+    from daliid_b200 import metrics
+    g = torch.Generator().manual_seed(Q * 31 + G)
+    d = torch.randn(Q, G, generator=g)
+    d = torch.round(d * 16) / 16  # heavy ties: the tie order must be ascending column
+    if G > 10:
+        d[0, 3] = float("nan"); d[0, 5] = float("inf"); d[0, 7] = -float("inf"); d[0, 8] = -0.0; d[0, 9] = 0.0
+    ref = torch.argsort(d, dim=1, descending=descending, stable=True)
+    out = metrics.argsort_rows(d.cuda(), descending)
+    assert out.dtype == torch.int32 and out.is_cuda
+    assert torch.equal(out.cpu().long(), ref)
+    host = metrics.argsort_rows(d.numpy(), descending)
+    np.testing.assert_array_equal(host, ref.numpy())
+
+
+def test_rank_by_similarity_matches_reference_arithmetic():
+    """get_subset / get_subset_one_encoder (getFeatures.py:243-353) from features."""
+    from daliid_b200.getFeatures import rank_by_similarity
+    g = torch.Generator().manual_seed(3)
+    N, D = 20011, 256
+    centers = torch.randn(40, D, generator=g)
+    lab = torch.randint(0, 40, (N,), generator=g)
+    trains = [centers[lab] + 1.5 * torch.randn(N, D, generator=g) for _ in range(3)]
+    sels = [centers[7:8] + 1.5 * torch.randn(1, D, generator=g) for _ in range(3)]
+
+    def ref_sim(sel, tr):
+        sel = sel / torch.norm(sel, dim=1, keepdim=True)
+        tr = tr / torch.norm(tr, dim=1, keepdim=True)
+        return torch.mm(sel, tr.T)
+
+    sim1 = ref_sim(sels[0], trains[0])
+    sim3 = (sim1 + ref_sim(sels[1], trains[1]) + ref_sim(sels[2], trains[2])) / 3
+    for sim, order in ((sim1, rank_by_similarity(sels[0].cuda(), trains[0].cuda())),
+                       (sim3, rank_by_similarity([s.cuda() for s in sels], [t.cuda() for t in trains]))):
+        order = order.cpu()
+        assert order.dtype == torch.int64 and sorted(order.tolist()) == list(range(N))
+        # the reference's own ordering, up to swaps of samples whose similarities differ by rounding only
+        ref = torch.argsort(sim, dim=1, descending=True)[0]
+        got = sim[0][order]
+        assert bool((got[:-1] - got[1:] >= -2e-6).all())
+        topK = int(N * 0.1)
+        assert len(set(order[:topK].tolist()) ^ set(ref[:topK].tolist())) <= 4
+        assert (lab[order[:200]] == 7).float().mean() > 0.9
