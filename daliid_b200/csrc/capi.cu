@@ -17,6 +17,16 @@ int set_err(dali_ctx *ctx, int code, const std::string &msg) {
   return code;
 }
 
+int ensure_dyn_smem(dali_ctx *ctx, const void *func, size_t bytes) {
+  if (bytes <= 48 * 1024) return DALI_OK;
+  size_t &have = ctx->func_smem[func];
+  if (bytes > have) {
+    DALI_CUDA_OK(ctx, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    have = bytes;
+  }
+  return DALI_OK;
+}
+
 int ws_ensure(dali_ctx *ctx, int slot, size_t bytes, void **out) {
   DevBuf &b = ctx->ws[slot];
   if (bytes > b.cap) {

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/daliid_b200.h"
@@ -127,6 +128,9 @@ struct dali_ctx {
   int64_t plan_cache_hits = 0;
   int64_t launches = 0;
   int64_t fallbacks = 0;  // fused calls that had to be redone through the materialised path
+  // opt-in dynamic shared memory already granted per kernel on THIS device (the attribute is
+  // per device, so it cannot be a process-wide static)
+  std::unordered_map<const void *, size_t> func_smem;
   // tensor-map encoder (driver entry point, resolved lazily)
   void *encode_tiled = nullptr;
 };
@@ -159,6 +163,8 @@ namespace dali {
 
 int set_err(dali_ctx *ctx, int code, const std::string &msg);
 int ws_ensure(dali_ctx *ctx, int slot, size_t bytes, void **out);
+// raise a kernel's dynamic shared-memory limit on the context's device (cached per context)
+int ensure_dyn_smem(dali_ctx *ctx, const void *func, size_t bytes);
 
 // RAII-less timing helpers: call before/after a kernel launch on ctx->stream.
 struct KTimer {

@@ -299,13 +299,8 @@ template <int MODE, int MH>
 int launch_t(dali_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmA16,
              const CUtensorMap &tmB16, const UmmaParams &p) {
   using C = Cfg<MH>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DALI_CUDA_OK(ctx, cudaFuncSetAttribute(distmat_umma_kernel<MODE, MH>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           C::kSmemBytes));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(ctx, reinterpret_cast<const void *>(&distmat_umma_kernel<MODE, MH>), C::kSmemBytes))
+    return rc;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
   KTimer t(ctx, DALI_K_DISTMAT);

@@ -556,12 +556,8 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 template <int MODE, int EPI>
 int launch_t(dali_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmA16,
              const CUtensorMap &tmB16, const CUtensorMap &tmOut, const Umma2Params &p) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    DALI_CUDA_OK(ctx, cudaFuncSetAttribute(distmat_umma2_kernel<MODE, EPI>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(ctx, reinterpret_cast<const void *>(&distmat_umma2_kernel<MODE, EPI>), kSmemBytes))
+    return rc;
   const int tiles = p.num_m_pairs * p.num_n_tiles;
   const int max_pairs = ctx->num_sms / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;

@@ -275,11 +275,7 @@ int launch_mrfuse(dali_ctx *ctx, const float *const *s, int n, int64_t Q, int64_
     fi.s[m] = m < n ? s[m] : nullptr;
     fi.scale[m] = fo[m].scale; fi.kk[m] = fo[m].kk; fi.sign[m] = fo[m].sign; fi.small[m] = fo[m].small;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    DALI_CUDA_OK(ctx, cudaFuncSetAttribute(mr_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  if ((rc = ensure_dyn_smem(ctx, reinterpret_cast<const void *>(&mr_fit_kernel), smem))) return rc;
   for (int m = 0; m < n; ++m) {
     dim3 tg(static_cast<unsigned>((G + 31) / 32), static_cast<unsigned>((Q + 31) / 32));
     ctx->launches++;

@@ -519,14 +519,9 @@ template <int LOG2NB, int THREADS, bool BYTEC = false>
 static int launch_v2(dali_ctx *ctx, dim3 grid, size_t smem, const dali_rank_plan *plan, const float *dist,
                      int64_t ld, int64_t g0, int64_t Gs, const uint32_t *keys, int32_t *counts,
                      int nsplit, int tchunk) {
-  static size_t attr = 0;
-  if (smem > attr) {
-    const size_t want = std::max<size_t>(smem, 48 * 1024);
-    DALI_CUDA_OK(ctx, cudaFuncSetAttribute(rank_count_v2_kernel<LOG2NB, THREADS, BYTEC>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(want)));
-    attr = want;
-  }
+  if (int rc = ensure_dyn_smem(ctx, reinterpret_cast<const void *>(&rank_count_v2_kernel<LOG2NB, THREADS, BYTEC>),
+                               smem))
+    return rc;
   rank_count_v2_kernel<LOG2NB, THREADS, BYTEC><<<grid, THREADS, smem, ctx->stream>>>(
       dist, ld, g0, Gs, plan->d_off, plan->d_nv, plan->d_gid, keys, counts, nsplit, tchunk, FusedOut{});
   return DALI_OK;
@@ -606,14 +601,9 @@ int launch_rank_fused(dali_ctx *ctx, const dali_rank_plan *plan, const float *di
   if (std::max<int64_t>(std::max<int64_t>(1, std::min(want, max_split)), min_split) != 1) return DALI_OK;
   DALI_CUDA_OK(ctx, cudaMemsetAsync(cmc_cnt, 0, sizeof(int32_t) * (max_rank + 1), ctx->stream));
   const size_t smem = v2_smem_bytes(11, plan->max_nv, 256);
-  static size_t attr = 0;
-  if (smem > attr) {
-    const size_t want_b = std::max<size_t>(smem, 48 * 1024);
-    DALI_CUDA_OK(ctx, cudaFuncSetAttribute(rank_count_v2_kernel<11, 256, false, true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(want_b)));
-    attr = want_b;
-  }
+  if (int rc = ensure_dyn_smem(ctx, reinterpret_cast<const void *>(&rank_count_v2_kernel<11, 256, false, true>),
+                               smem))
+    return rc;
   FusedOut fo{ranks_sorted, ap, first_rank, cmc_cnt, max_rank};
   KTimer t(ctx, DALI_K_RANK_COUNT);
   rank_count_v2_kernel<11, 256, false, true><<<dim3(static_cast<unsigned>(plan->Q), 1, 1), 256, smem, ctx->stream>>>(

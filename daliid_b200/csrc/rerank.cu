@@ -436,12 +436,7 @@ int launch_rerank(dali_ctx *ctx, const float *qg, int64_t ld_qg, const float *qq
       int np2 = 2;
       while (np2 < cap2) np2 <<= 1;
       const size_t smem = sizeof(uint64_t) * np2 + sizeof(float) * cap2;
-      static size_t attr = 0;
-      if (smem > attr) {
-        DALI_CUDA_OK(ctx, cudaFuncSetAttribute(qexpand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               static_cast<int>(std::max<size_t>(smem, 48 * 1024))));
-        attr = std::max<size_t>(smem, 48 * 1024);
-      }
+      if (int rc2 = ensure_dyn_smem(ctx, reinterpret_cast<const void *>(&qexpand_kernel), smem)) return rc2;
       qexpand_kernel<<<static_cast<unsigned>(N), 128, smem, st>>>(N, rank, K, k2, v0_idx, v0_val, v0_cnt, cap2,
                                                                  v_idx, v_val, v_cnt);
       cnt_final = v_cnt;
