@@ -2,8 +2,10 @@
 // operands, the rank plan (gallery CSR by identity), orchestration of the kernels and the
 // host-side tail of the CMC/mAP reduction in both upstream accumulation modes.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <limits>
 #include <numeric>
@@ -81,6 +83,17 @@ KTimer::~KTimer() {
 static void timing_drain(dali_ctx *ctx) {
   if (ctx->t_pending.empty()) return;
   cudaStreamSynchronize(ctx->stream);
+  static const bool trace = getenv("DALI_TRACE") != nullptr;  // debugging: start/end of every timed launch
+  if (trace) {
+    cudaEvent_t base = ctx->t_pending.front().second.first;
+    for (auto &pe : ctx->t_pending) {
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, base, pe.second.first);
+      cudaEventElapsedTime(&b, base, pe.second.second);
+      fprintf(stderr, "[dali trace] slot %d  start %8.1f us  end %8.1f us  (%.1f us)\n", pe.first, a * 1e3f, b * 1e3f,
+              (b - a) * 1e3f);
+    }
+  }
   for (auto &pe : ctx->t_pending) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, pe.second.first, pe.second.second) == cudaSuccess) {
@@ -1047,6 +1060,9 @@ int dali_eval_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float
                            int normalize, int max_rank, int accum_mode, float *cmc, double *mAP,
                            double *ap_opt, int32_t *first_rank_opt, int64_t *num_valid_opt,
                            float *distmat_opt, int64_t ld_opt) {
+  static const bool trace = getenv("DALI_TRACE") != nullptr;  // debugging: host-side timeline of the call
+  const auto t_in = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_in).count(); };
   int rc = check_ctx(ctx);
   if (rc) return rc;
   if (Q < 0 || G < 0 || D <= 0 || (!q && Q) || (!g && G) || !cmc || !mAP || max_rank < 1 ||
@@ -1075,12 +1091,17 @@ int dali_eval_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float
     DALI_CUDA_OK(ctx, cudaMemcpy2DAsync(distmat_opt, sizeof(float) * ld_opt, dd, sizeof(float) * ldd,
                                         sizeof(float) * G, Q, cudaMemcpyDeviceToHost, ctx->stream));
   // 2. ... so the host builds the rank plan (gallery CSR by identity) while the GPU works
+  const double t_launched = since();
   dali_rank_plan *plan = nullptr;
   rc = dali_rank_plan_create(ctx, q_pid, g_pid, q_cam, g_cam, Q, G, &plan);
   if (rc) return rc;
+  const double t_plan = since();
   rc = rank_from_device(ctx, plan, dd, ldd, max_rank, accum_mode, cmc, mAP, ap_opt,
                         first_rank_opt, num_valid_opt);
   dali_rank_plan_destroy(plan);
+  if (trace)
+    fprintf(stderr, "[dali trace] eval_features host: contraction enqueued %.1f us, plan ready %.1f us, done %.1f us\n",
+            t_launched, t_plan, since());
   return rc;
 }
 

@@ -30,7 +30,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import ACCUMS, METRICS, PRECISIONS, as_i32, as_matrix, c_vp, get_ctx, p_i32
+from ._lib import ACCUMS, METRICS, PRECISIONS, as_i32, as_matrix, c_vp, get_ctx, np_ptr, p_i32
 
 __all__ = [
     "re_ranking", "mrfuse", "argsort_rows",
@@ -122,8 +122,7 @@ def evaluate_rank_detailed(distmat, q_pids, g_pids, q_camids, g_camids, max_rank
     rc = ctx.lib.dali_eval_rank_f32(
         ctx.h, c_vp(d.ptr), num_q, num_g, d.ld, p_i32(qp), p_i32(gp), p_i32(qc), p_i32(gc),
         int(max_rank), _enum(ACCUMS, accum, "accumulation mode"),
-        cmc.ctypes.data_as(_lib.c_f32p), ctypes.byref(mAP), ap.ctypes.data_as(_lib.c_f64p),
-        first.ctypes.data_as(_lib.c_i32p), ctypes.byref(nvalid))
+        np_ptr(cmc), ctypes.byref(mAP), np_ptr(ap), np_ptr(first), ctypes.byref(nvalid))
     ctx.check(rc)
     return cmc, float(mAP.value), ap, first, int(nvalid.value)
 
@@ -378,11 +377,10 @@ def evaluate_features(qf, gf, q_pids, g_pids, q_camids, g_camids, metric="cosine
     if return_distmat:
         dist, dptr = _alloc_out((Q, G), dev)
     rc = ctx.lib.dali_eval_features_f32(
-        ctx.h, c_vp(a.ptr), Q, c_vp(b.ptr), G, D, p_i32(qp), p_i32(gp), p_i32(qc), p_i32(gc), m,
+        ctx.h, a.ptr, Q, b.ptr, G, D, p_i32(qp), p_i32(gp), p_i32(qc), p_i32(gc), m,
         _precision(precision, normalize), 1 if normalize else 0, int(max_rank),
-        _enum(ACCUMS, accum, "accumulation mode"), cmc.ctypes.data_as(_lib.c_f32p),
-        ctypes.byref(mAP), ap.ctypes.data_as(_lib.c_f64p), first.ctypes.data_as(_lib.c_i32p),
-        ctypes.byref(nvalid), c_vp(dptr), G)
+        _enum(ACCUMS, accum, "accumulation mode"), np_ptr(cmc), ctypes.byref(mAP), np_ptr(ap), np_ptr(first),
+        ctypes.byref(nvalid), dptr, G)
     ctx.check(rc)
     res = (cmc, float(mAP.value))
     if return_distmat:
