@@ -12,7 +12,8 @@
 //   T[g][q] = nan_to_num(S[q][g]); killed entries x -> x - killscale*x    (transpose + scatter)
 //   (topk+2) smallest of every row of T: the tail is everything but the topk+1 smallest,
 //       `small` is the (topk+2)-th smallest = the last element of the reference's sorted tail
-//   fit: one CTA per gallery column, logs staged in shared memory, Newton in fp64
+//   fit: one CTA per gallery column, logs staged in shared memory (recomputed per step for very
+//        long columns), Newton in fp64
 //   fuse: one pass over the n score matrices, fp64 out
 // The reference sorts the tail (torch.topk of Q-topk-1 values); only sums over the tail enter the
 // fit, so no sort is needed: excluding the topk+1 smallest by index gives the same multiset.
@@ -24,6 +25,7 @@
 // relative -- the reproducibility limit of the reference's own fp32 intermediates.
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -101,33 +103,38 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
 
 __device__ __forceinline__ double sgn(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : (x == 0 ? 0.0 : x)); }
 
-// one CTA per gallery column g; T row g holds the column's Q cleaned scores
+// one CTA per gallery column g; T row g holds the column's Q cleaned scores.  STAGED: ln(x) of the
+// column is kept in shared memory (8 B per query, Q <= ~28k); otherwise it is recomputed from the
+// row every Newton step (any Q; one more fp64 log per element and step).  The topk+1 smallest
+// entries, which are not part of the tail, are marked with a NaN.
+template <bool STAGED>
 __global__ void __launch_bounds__(kFitThreads)
-mr_fit_kernel(const float *__restrict__ T, int64_t ldT, int64_t Q, const float *__restrict__ low_v,
+mr_fit_kernel(float *__restrict__ T, int64_t ldT, int64_t Q, const float *__restrict__ low_v,
               const int32_t *__restrict__ low_i, int nlow /* topk+2 */, FitOut out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *lnd = reinterpret_cast<double *>(smem_raw);
-  float *lnf = reinterpret_cast<float *>(lnd + Q);
   __shared__ double red[kFitThreads / 32];
   const int64_t g = blockIdx.x;
   const int tid = threadIdx.x;
   const float small = low_v[g * nlow + (nlow - 1)];
-  const float *row = T + g * ldT;
-  for (int64_t q = tid; q < Q; q += kFitThreads) {
-    const float p = (row[q] + 1.0f) - small;  // sortedTensor + translateAmount - smallScoreTensor
-    const double l = log(static_cast<double>(p));
-    lnd[q] = l;
-    lnf[q] = static_cast<float>(l);
+  float *row = T + g * ldT;
+  auto ln_of = [&](float t) {  // sortedTensor + translateAmount - smallScoreTensor, then the log
+    return log(static_cast<double>((t + 1.0f) - small));
+  };
+  if (STAGED) {
+    for (int64_t q = tid; q < Q; q += kFitThreads) lnd[q] = ln_of(row[q]);
+    __syncthreads();
+    if (tid < nlow - 1) lnd[low_i[g * nlow + tid]] = nan("");
+  } else {
+    if (tid < nlow - 1) row[low_i[g * nlow + tid]] = __int_as_float(0x7fc00000);  // this CTA owns row g
   }
   __syncthreads();
-  // the topk+1 smallest are not part of the tail
-  if (tid < nlow - 1) lnf[low_i[g * nlow + tid]] = __int_as_float(0x7fc00000);
-  __syncthreads();
+  auto ln_at = [&](int64_t q) { return STAGED ? lnd[q] : ln_of(row[q]); };
   const double n_tail = static_cast<double>(Q - (nlow - 1));
   double sl = 0.0;
   for (int64_t q = tid; q < Q; q += kFitThreads) {
-    const float l = lnf[q];
-    if (!isnan(l)) sl += static_cast<double>(l);
+    const double l = ln_at(q);
+    if (!isnan(l)) sl += static_cast<double>(static_cast<float>(l));  // the reference's log is fp32
   }
   sl = block_sum(sl, red);
   const double mean_ln = static_cast<double>(static_cast<float>(sl / n_tail));  // torch.mean of fp32
@@ -138,10 +145,10 @@ mr_fit_kernel(const float *__restrict__ T, int64_t ldT, int64_t Q, const float *
   for (int it = 0; it < kIters; ++it) {
     double fg = 0.0, ff = 0.0, fp = 0.0;
     for (int64_t q = tid; q < Q; q += kFitThreads) {
-      const float lf = lnf[q];
-      if (isnan(lf)) continue;
-      const double e = exp(k * lnd[q]);
-      const double l = static_cast<double>(lf);
+      const double ld_ = ln_at(q);
+      if (isnan(ld_)) continue;
+      const double e = exp(k * ld_);
+      const double l = static_cast<double>(static_cast<float>(ld_));
       const double t = e * l;
       fg += e;
       ff += t;
@@ -163,8 +170,10 @@ mr_fit_kernel(const float *__restrict__ T, int64_t ldT, int64_t Q, const float *
   double shape = 0.0, scale = 0.0;
   if (!open) {
     double fg = 0.0;
-    for (int64_t q = tid; q < Q; q += kFitThreads)
-      if (!isnan(lnf[q])) fg += exp(k * lnd[q]);
+    for (int64_t q = tid; q < Q; q += kFitThreads) {
+      const double ld_ = ln_at(q);
+      if (!isnan(ld_)) fg += exp(k * ld_);
+    }
     fg = block_sum(fg, red);
     shape = k;
     scale = pow(fg / n_tail, 1.0 / k);
@@ -240,8 +249,9 @@ int launch_mrfuse(dali_ctx *ctx, const float *const *s, int n, int64_t Q, int64_
   if (Q < topk + 2 || G < 1 || (!use_columns && G < topk))
     return set_err(ctx, DALI_ERR_INVALID, "mrfuse: needs Q >= topk+2 scores per gallery column (tail = Q-topk-1 >= 1) "
                                           "and G >= topk");
-  const size_t smem = static_cast<size_t>(Q) * 12;
-  if (smem > 200 * 1024) return set_err(ctx, DALI_ERR_UNSUPPORTED, "mrfuse: more than 17066 queries per column fit");
+  const char *env_staged = getenv("DALI_MRFUSE_STAGED");  // 0: force the recompute path (cross-check)
+  const bool staged = static_cast<size_t>(Q) * 8 <= 225 * 1024 && !(env_staged && atoi(env_staged) == 0);
+  const size_t smem = staged ? static_cast<size_t>(Q) * 8 : 0;
   KTimer timer(ctx, DALI_K_MRFUSE);
   const int64_t ldT = (Q + 3) / 4 * 4;
   const int nlow = topk + 2;
@@ -275,7 +285,7 @@ int launch_mrfuse(dali_ctx *ctx, const float *const *s, int n, int64_t Q, int64_
     fi.s[m] = m < n ? s[m] : nullptr;
     fi.scale[m] = fo[m].scale; fi.kk[m] = fo[m].kk; fi.sign[m] = fo[m].sign; fi.small[m] = fo[m].small;
   }
-  if ((rc = ensure_dyn_smem(ctx, reinterpret_cast<const void *>(&mr_fit_kernel), smem))) return rc;
+  if ((rc = ensure_dyn_smem(ctx, reinterpret_cast<const void *>(&mr_fit_kernel<true>), smem))) return rc;
   for (int m = 0; m < n; ++m) {
     dim3 tg(static_cast<unsigned>((G + 31) / 32), static_cast<unsigned>((Q + 31) / 32));
     ctx->launches++;
@@ -297,7 +307,10 @@ int launch_mrfuse(dali_ctx *ctx, const float *const *s, int n, int64_t Q, int64_
     DALI_CUDA_OK(ctx, cudaGetLastError());
     if ((rc = launch_topk(ctx, T, G, Q, ldT, nlow, 0, nullptr, 0, low_v, low_i))) return rc;
     ctx->launches++;
-    mr_fit_kernel<<<static_cast<unsigned>(G), kFitThreads, smem, ctx->stream>>>(T, ldT, Q, low_v, low_i, nlow, fo[m]);
+    if (staged)
+      mr_fit_kernel<true><<<static_cast<unsigned>(G), kFitThreads, smem, ctx->stream>>>(T, ldT, Q, low_v, low_i, nlow, fo[m]);
+    else
+      mr_fit_kernel<false><<<static_cast<unsigned>(G), kFitThreads, 0, ctx->stream>>>(T, ldT, Q, low_v, low_i, nlow, fo[m]);
     DALI_CUDA_OK(ctx, cudaGetLastError());
     if (fit_opt) {
       DALI_CUDA_OK(ctx, cudaMemcpy2DAsync(fit_opt + static_cast<size_t>(m) * G * 2, 2 * sizeof(double), fo[m].shape,

@@ -229,7 +229,7 @@ int dali_argsort_f32(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int
  * device): fit_opt fp64 [n][G][2] = (shape, scale) exactly as libmr.wbFits holds them (0,0 for a
  * column whose Newton iteration did not converge in 100 steps, NaN,NaN when it turned NaN),
  * small_opt fp32 [n][G] = libmr.smallScoreTensor, weights_opt fp64 [n][Q][ld_out] = metarec's
- * return value.  Needs topk+2 <= Q <= 17066, topk <= 126, and G >= topk when use_columns = 0.
+ * return value.  Needs Q >= topk+2, topk <= 126, and G >= topk when use_columns = 0.
  * Values agree with the reference run on the same inputs to ~1e-6 relative (the reference's fp32
  * log / mean intermediates are not reproducible beyond that across libm implementations). */
 int dali_mrfuse_f32(dali_ctx *ctx, const float *const *scores, int n, int64_t Q, int64_t G,

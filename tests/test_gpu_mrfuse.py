@@ -99,6 +99,17 @@ def test_mrfuse_class_and_properties():
     np.testing.assert_array_equal(host, fused)
 
 
+def test_mrfuse_recompute_path_equals_staged(monkeypatch):
+    """Columns too long for shared-memory staging recompute ln(x) every Newton step: same fit."""
+    s = [_scores(60 + m, 500, 90, 32).cuda() for m in range(2)]
+    a, da = metrics.mrfuse(s, 20, return_details=True)
+    monkeypatch.setenv("DALI_MRFUSE_STAGED", "0")
+    b, db = metrics.mrfuse(s, 20, return_details=True)
+    np.testing.assert_array_equal(da["small"], db["small"])
+    np.testing.assert_allclose(da["fit"], db["fit"], rtol=1e-12)
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-12, atol=0)
+
+
 def test_mrfuse_argument_errors():
     s = _scores(1, 21, 40, 8).cuda()
     with pytest.raises(Exception):
