@@ -592,22 +592,35 @@ int launch_rank_fused(dali_ctx *ctx, const dali_rank_plan *plan, const float *di
   static const char *env = getenv("DALI_RANK_FUSED");
   if (env && atoi(env) == 0) return DALI_OK;
   const int64_t G = plan->G;
-  if (plan->Q == 0 || plan->M == 0 || G == 0 || plan->max_nv == 0 || plan->max_nv > 64) return DALI_OK;
+  if (plan->Q == 0 || plan->M == 0 || G == 0 || plan->max_nv == 0 || plan->max_nv > kV2Chunk) return DALI_OK;
   if (getenv("DALI_RANK_V1") || getenv("DALI_RANK_CHUNK") || getenv("DALI_RANK_THREADS")) return DALI_OK;
   // the same split rule as launch_rank_count: only the one-CTA-per-query case is fused
   const int64_t want = (4ll * ctx->num_sms + plan->Q - 1) / plan->Q;
   const int64_t max_split = (G + 4095) / 4096;
   const int64_t min_split = (G + (4ll << 20) - 1) / (4ll << 20);
   if (std::max<int64_t>(std::max<int64_t>(1, std::min(want, max_split)), min_split) != 1) return DALI_OK;
+  // many thresholds per query (DeepChange: ~120): byte counters, which limit a thread to 255
+  // elements -- one 256-thread CTA then covers rows of up to 65280 columns
+  const bool bytec = plan->max_nv > 64;
+  static const char *env_b = getenv("DALI_RANK_FUSED_BYTE");
+  if (bytec && (G > 255ll * 256 || (env_b && atoi(env_b) == 0))) return DALI_OK;
   DALI_CUDA_OK(ctx, cudaMemsetAsync(cmc_cnt, 0, sizeof(int32_t) * (max_rank + 1), ctx->stream));
-  const size_t smem = v2_smem_bytes(11, plan->max_nv, 256);
-  if (int rc = ensure_dyn_smem(ctx, reinterpret_cast<const void *>(&rank_count_v2_kernel<11, 256, false, true>),
-                               smem))
-    return rc;
   FusedOut fo{ranks_sorted, ap, first_rank, cmc_cnt, max_rank};
   KTimer t(ctx, DALI_K_RANK_COUNT);
-  rank_count_v2_kernel<11, 256, false, true><<<dim3(static_cast<unsigned>(plan->Q), 1, 1), 256, smem, ctx->stream>>>(
-      dist, ld, 0, G, plan->d_off, plan->d_nv, plan->d_gid, nullptr, nullptr, 1, kV2Chunk, fo);
+  const dim3 grid(static_cast<unsigned>(plan->Q), 1, 1);
+  if (bytec) {
+    const size_t smem = v2_smem_bytes(12, plan->max_nv, 256, true);
+    if (int rc = ensure_dyn_smem(ctx, reinterpret_cast<const void *>(&rank_count_v2_kernel<12, 256, true, true>), smem))
+      return rc;
+    rank_count_v2_kernel<12, 256, true, true><<<grid, 256, smem, ctx->stream>>>(
+        dist, ld, 0, G, plan->d_off, plan->d_nv, plan->d_gid, nullptr, nullptr, 1, kV2Chunk, fo);
+  } else {
+    const size_t smem = v2_smem_bytes(11, plan->max_nv, 256);
+    if (int rc = ensure_dyn_smem(ctx, reinterpret_cast<const void *>(&rank_count_v2_kernel<11, 256, false, true>), smem))
+      return rc;
+    rank_count_v2_kernel<11, 256, false, true><<<grid, 256, smem, ctx->stream>>>(
+        dist, ld, 0, G, plan->d_off, plan->d_nv, plan->d_gid, nullptr, nullptr, 1, kV2Chunk, fo);
+  }
   DALI_CUDA_OK(ctx, cudaGetLastError());
   *done = 1;
   return DALI_OK;
