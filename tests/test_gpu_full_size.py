@@ -88,6 +88,33 @@ def test_market_sharded_equals_unsharded(market):
         assert np.array_equal(det["first_rank"], base[2]["first_rank"])
 
 
+def test_market_one_call_sharded_entry_point(market):
+    """dali_eval_features_sharded_f32 with a one-rank peer block (the exchange kernels run, with
+    nobody else to wait for): same bits as the unsharded evaluation.  The default block is smaller
+    than the ~71k matches of this shape, so the DALI_ERR_PEER_CAPACITY -> re-create -> retry path
+    runs too."""
+    from daliid_b200 import metrics, sharded
+    qf, gf, qp, gp, qc, gc = market
+    base = metrics.evaluate_features(qf, gf, qp, gp, qc, gc, return_details=True)
+    ops = sharded.CudaOps()
+    sharded._peer_cache.clear()
+    ops._last_matches = 1 << 10
+    res = sharded._evaluate_features_one_call(ops, qf, gf, 0, qp, gp, qc, gc, "cosine", "auto", True, 50,
+                                              "cy_f32", None, strict=True)
+    assert res is not None and ops._last_matches > (1 << 16)
+    cmc, mAP, det = res
+    assert np.array_equal(cmc, base[0]) and mAP == base[1]
+    assert np.array_equal(det["first_rank"], base[2]["first_rank"])
+    assert np.array_equal(det["ap"], base[2]["ap"], equal_nan=True)
+    # second call: the block is large enough now, no retry
+    res2 = sharded._evaluate_features_one_call(ops, qf, gf, 0, qp, gp, qc, gc, "cosine", "auto", True, 50,
+                                               "cy_f32", None, strict=True)
+    assert res2[1] == base[1]
+    for px in list(sharded._peer_cache.values()):
+        px.close()
+    sharded._peer_cache.clear()
+
+
 def test_market_gallery_permutation_invariance(market):
     """Permuting the gallery (features and labels together) leaves CMC identical and mAP within
     float32 summation noise; exact equality would need tie-free distances."""
