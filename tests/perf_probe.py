@@ -65,6 +65,23 @@ def main():
         ms, _ = timeit(lambda: (metrics.compute_distance_matrix(qf, qf, "sqeuclidean", normalize=True),
                                 metrics.compute_distance_matrix(gf, gf, "sqeuclidean", normalize=True)), n=3, warm=1)
         print(f"qq + gg distance matrices: {ms:.2f} ms", flush=True)
+    elif what == "peaks":
+        # measured library peaks beside MEASURED_PEAKS.json (bf16): cuBLAS TF32 and fp32 matmul 8192^3
+        n = 8192
+        a = torch.randn(n, n, device="cuda"); b = torch.randn(n, n, device="cuda")
+        for name, allow in (("tf32", True), ("fp32", False)):
+            torch.backends.cuda.matmul.allow_tf32 = allow
+            ms, _ = timeit(lambda: a @ b, n=10, warm=3)
+            print(f"cuBLAS {name} matmul {n}^3: {ms:.3f} ms -> {2 * n ** 3 / ms / 1e9:.1f} TFLOP/s", flush=True)
+        ah, bh = a.bfloat16(), b.bfloat16()
+        ms, _ = timeit(lambda: ah @ bh, n=10, warm=3)
+        print(f"cuBLAS bf16 matmul {n}^3: {ms:.3f} ms -> {2 * n ** 3 / ms / 1e9:.1f} TFLOP/s", flush=True)
+        ah, bh = a.half(), b.half()
+        ms, _ = timeit(lambda: ah @ bh, n=10, warm=3)
+        print(f"cuBLAS fp16 matmul {n}^3: {ms:.3f} ms -> {2 * n ** 3 / ms / 1e9:.1f} TFLOP/s", flush=True)
+        src = torch.empty(1 << 28, device="cuda"); dst = torch.empty_like(src)
+        ms, _ = timeit(lambda: dst.copy_(src), n=10, warm=3)
+        print(f"device copy 1 GiB: {ms:.3f} ms -> {2 * src.numel() * 4 / ms / 1e6:.0f} GB/s (read + write)", flush=True)
     elif what == "mrfuse":
         # SURVEY 8f N3 at the Market shape: three models' similarity matrices -> Weibull weights -> fusion
         sims = []
