@@ -555,7 +555,9 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": pairs_per_step * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                 "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int((Q + G) * D * 4 + (Q + G * world) * 8),
+                # per rank: its share of the queries (the ranks exchange the shares over NVLink,
+                # sharded.share_queries) + its gallery slab, fp32, + the int32 label arrays
+                "h2d_bytes_per_step": int((-(-Q // world) + G) * D * 4 + (Q + G * world) * 8),
                 "d2h_bytes_per_step": int(Q * 8 + 51 * 4)},
         "gpu_launches": int(launches),
         "numa_binding": numa,

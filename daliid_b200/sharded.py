@@ -213,6 +213,32 @@ def peer_exchange(ops, need, group=None):
     return px
 
 
+def share_queries(qf, device, group=None):
+    """Queries are replicated on every rank, so when they live in HOST memory each rank uploads only
+    its 1/world share over PCIe and the ranks exchange the shares over NVLink (one all_gather):
+    per-rank host traffic drops from Q*D + Gs*D to Q*D/world + Gs*D floats -- 16 % less at the
+    Market shape on 8 GPUs, where the ranks compete for the host's memory path.  Every rank must
+    pass the SAME query matrix (the sharded evaluation requires that anyway).  Returns a ``[Q, D]``
+    fp32 CUDA tensor; device inputs and single-rank runs are returned unchanged."""
+    world, rank = _world(group)
+    if world == 1 or getattr(qf, "is_cuda", False) or dist.get_backend(group) != "nccl":
+        return qf
+    t = qf if isinstance(qf, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(qf, dtype=np.float32))
+    if t.dim() != 2 or t.dtype != torch.float32 or not t.is_contiguous():
+        return qf
+    Q, D = t.shape
+    chunk = (Q + world - 1) // world
+    dev = torch.device(f"cuda:{device}") if not isinstance(device, torch.device) else device
+    full = torch.empty((world * chunk, D), dtype=torch.float32, device=dev)
+    mine = torch.zeros((chunk, D), dtype=torch.float32, device=dev) if (rank + 1) * chunk > Q else \
+        torch.empty((chunk, D), dtype=torch.float32, device=dev)
+    r0, r1 = rank * chunk, min(Q, (rank + 1) * chunk)
+    if r1 > r0:
+        mine[:r1 - r0].copy_(t[r0:r1], non_blocking=True)
+    dist.all_gather_into_tensor(full, mine, group=group)
+    return full[:Q]
+
+
 def gather_gallery_labels(g_pid_slab, g_cam_slab, group=None):
     """All ranks learn the labels of the whole gallery (two int32 vectors; tiny) and the
     slab offsets.  Returns (g_pid_all, g_cam_all, g0_of_this_rank, sizes)."""
@@ -273,12 +299,15 @@ def evaluate_rank_sharded(dist_slab, g0, q_pids, g_pids_all, q_camids, g_camids_
 def evaluate_features_sharded(qf, gf_slab, g0, q_pids, g_pids_all, q_camids, g_camids_all,
                               metric="cosine", precision=metrics.DEFAULT_PRECISION,
                               normalize=None, max_rank=50, accum="cy_f32", group=None, ops=None,
-                              return_details=False, exchange="auto"):
-    """Features in (all queries + this rank's gallery slab), ``(cmc, mAP)`` out."""
+                              return_details=False, exchange="auto", share_host_queries=True):
+    """Features in (all queries + this rank's gallery slab), ``(cmc, mAP)`` out.  Host-resident
+    queries are uploaded once in total (``share_queries``), not once per rank."""
     ops = ops or CudaOps(qf.device.index if getattr(qf, "is_cuda", False) else None)
     if normalize is None:
         normalize = metric == "cosine"
     world, _ = _world(group)
+    if share_host_queries and isinstance(ops, CudaOps) and world > 1:
+        qf = share_queries(qf, ops.device, group)
     if (isinstance(ops, CudaOps) and world > 1 and exchange in ("auto", "peer")
             and dist.get_backend(group) == "nccl"):
         res = _evaluate_features_one_call(ops, qf, gf_slab, g0, q_pids, g_pids_all, q_camids, g_camids_all,
@@ -349,6 +378,8 @@ def topk_features_sharded(qf, gf_slab, g0, k=20, metric="cosine", precision=metr
     ops = ops or CudaOps(qf.device.index if getattr(qf, "is_cuda", False) else None)
     if normalize is None:
         normalize = metric == "cosine"
+    if isinstance(ops, CudaOps):
+        qf = share_queries(qf, ops.device, group)
     vals, ids = ops.topk_features(qf, gf_slab, k, metric, precision, normalize, largest, g0)
     world, _ = _world(group)
     if world == 1:

@@ -34,6 +34,13 @@ def main():
                                                             return_details=True)
             assert np.array_equal(cmc, e_cmc) and mAP == e_map, (name, precision, exchange, mAP, e_map)
             assert np.array_equal(det["first_rank"], e_det["first_rank"])
+        # host-resident features: every rank uploads 1/world of the queries, the shares travel over NVLink
+        qh, gh = qf.cpu().pin_memory(), gf[g0:g0 + gs].cpu().pin_memory()
+        cmc, mAP, det = sharded.evaluate_features_sharded(qh, gh, g0, qp, gp, qc, gc, return_details=True)
+        e_cmc, e_map, e_det = metrics.evaluate_features(qf, gf, qp, gp, qc, gc, return_details=True)
+        assert np.array_equal(cmc, e_cmc) and mAP == e_map, (name, "host features", mAP, e_map)
+        assert np.array_equal(det["first_rank"], e_det["first_rank"])
+        assert torch.equal(sharded.share_queries(qh, local), qf)
         v, i = sharded.topk_features_sharded(qf, gf[g0:g0 + gs].contiguous(), g0, k=20)
         ev, ei = metrics.topk_features(qf, gf, k=20)
         assert torch.equal(i, ei) and torch.equal(v, ev), name
