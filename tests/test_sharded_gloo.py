@@ -70,6 +70,8 @@ def _worker(rank, world, port, out_dir):
     order = ro.stable_argsort(used)[:, :7]
     assert np.array_equal(np.asarray(i), order.astype(np.int32))
     assert np.array_equal(np.asarray(v), np.take_along_axis(used, order, 1))
+    # sharing the query upload is an NCCL / device matter: under gloo the matrix passes through untouched
+    assert sharded.share_queries(qf, 0) is qf
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     dist.destroy_process_group()
 
