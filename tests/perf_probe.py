@@ -63,7 +63,7 @@ def main():
         print(f"rerank market_vit N={Q + G}: {ms:.2f} ms per call; kernels (launches, total ms): {kt}; "
               f"mAP {m0:.4f} -> {m1:.4f}, R1 {c0[0]:.4f} -> {c1[0]:.4f}", flush=True)
         ms, _ = timeit(lambda: (metrics.compute_distance_matrix(qf, qf, "sqeuclidean", normalize=True),
-                                metrics.compute_distance_matrix(gf, gf, "sqeuclidean", normalize=True)), n=3, warm=1)
+                                metrics.compute_distance_matrix(gf, gf, "sqeuclidean", normalize=True)), n=3, warm=3)
         print(f"qq + gg distance matrices: {ms:.2f} ms", flush=True)
     elif what == "peaks":
         # measured library peaks beside MEASURED_PEAKS.json (bf16): cuBLAS TF32 and fp32 matmul 8192^3
