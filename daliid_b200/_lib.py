@@ -56,6 +56,7 @@ _SIGNATURES = {
     "dali_ctx_get_stream": (c_vp, [c_vp]),
     "dali_last_error": (ctypes.c_char_p, [c_vp]),
     "dali_strerror": (ctypes.c_char_p, [ci]),
+    "dali_ctx_h2d_streams": (ci, [c_vp]),
     "dali_ctx_timing_enable": (ci, [c_vp, ci]),
     "dali_ctx_timing_reset": (ci, [c_vp]),
     "dali_ctx_timing_read": (ci, [c_vp, ci, ctypes.POINTER(ci), c_f32p]),
@@ -181,6 +182,9 @@ class Context:
             self.check(self.lib.dali_ctx_timing_read(self.h, slot, ctypes.byref(n), ctypes.byref(ms)))
             out[name] = (n.value, ms.value)
         return out
+
+    def h2d_streams(self):
+        return int(self.lib.dali_ctx_h2d_streams(self.h))
 
     def launch_count(self):
         return int(self.lib.dali_ctx_launch_count(self.h))

@@ -141,10 +141,11 @@ static int h2d_parallel(dali_ctx *ctx, void *dst, const void *src, size_t bytes,
   }
   static const char *env_s = getenv("DALI_H2D_STREAMS");
   if (env_s) ctx->h2d_streams = std::max(1, std::min(static_cast<int>(dali_ctx::kCopyStreams), atoi(env_s)));
-  // Default: one DMA stream.  Splitting a copy over several streams raised the raw copy rate on
-  // one host (39 -> 53 GB/s) but made the chunked copy/compute pipeline slower on the hosts where
-  // a single stream already reaches ~55 GB/s (e2e 3.15 -> 3.54 ms), and a per-process probe did
-  // not predict which; DALI_H2D_STREAMS=2..4 opts in.
+  // One DMA stream unless the online comparison in gallery_pipelined found two faster.  Splitting a
+  // copy over several streams raised the raw copy rate on one host (39 -> 53 GB/s) but made the
+  // chunked copy/compute pipeline slower on the hosts where a single stream already reaches
+  // ~55 GB/s (e2e 3.15 -> 3.54 ms), and a raw-copy probe did not predict which -- so the pipeline
+  // itself is timed.  DALI_H2D_STREAMS=1..4 fixes the setting.
   const int want = ctx->h2d_streams ? ctx->h2d_streams : 1;
   const int parts = bytes >= (2u << 20) ? want : 1;
   const size_t per = ((bytes + parts - 1) / parts + 255) & ~size_t(255);
@@ -548,6 +549,8 @@ void dali_ctx_destroy(dali_ctx *ctx) {
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->plan_stage) cudaFreeHost(ctx->plan_stage);
   if (ctx->plan_stage_done) cudaEventDestroy(ctx->plan_stage_done);
+  if (ctx->h2d_ev0) cudaEventDestroy(ctx->h2d_ev0);
+  if (ctx->h2d_ev1) cudaEventDestroy(ctx->h2d_ev1);
   for (auto e : ctx->chunk_events) cudaEventDestroy(e);
   for (auto st : ctx->copy_streams)
     if (st) cudaStreamDestroy(st);
@@ -565,6 +568,8 @@ int dali_ctx_set_stream(dali_ctx *ctx, void *cuda_stream) {
 void *dali_ctx_get_stream(dali_ctx *ctx) { return ctx ? static_cast<void *>(ctx->stream) : nullptr; }
 
 const char *dali_last_error(dali_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int dali_ctx_h2d_streams(const dali_ctx *ctx) { return ctx ? ctx->h2d_streams : 0; }
 
 int dali_ctx_timing_enable(dali_ctx *ctx, int on) {
   if (!ctx) return DALI_ERR_INVALID;
@@ -667,6 +672,47 @@ static int gallery_pipelined(dali_ctx *ctx, const Prepared &a, const float *g_ho
   int64_t chunk = round_up(std::max<int64_t>(256, (12ll << 20) / (sizeof(float) * D)), 256);
   if ((G + chunk - 1) / chunk > 24) chunk = round_up((G + 23) / 24, 256);
   const int nchunks = static_cast<int>((b.rows_pad + chunk - 1) / chunk);
+  // Online choice of the number of DMA streams (see h2d_parallel): calls 1-2 of a context run with one
+  // stream, calls 3-4 with two, each timed by an event pair that is read at the start of the next call;
+  // from call 5 on the faster setting is kept (two streams only when at least 3 % faster).  Call 0
+  // pays for allocations and is not counted; a change of the gallery size restarts the comparison.
+  static const char *env_fixed = getenv("DALI_H2D_STREAMS");
+  const int64_t g_bytes = static_cast<int64_t>(sizeof(float)) * G * D;
+  bool timed_call = false;
+  if (!env_fixed) {
+    if (ctx->h2d_ev_streams) {  // collect the previous call's measurement
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ctx->h2d_ev0, ctx->h2d_ev1) == cudaSuccess && ms > 0.f) {
+        float &best = ctx->h2d_tune_ms[ctx->h2d_ev_streams - 1];
+        best = best == 0.f ? ms : std::min(best, ms);
+      } else {
+        (void)cudaGetLastError();  // not finished yet (stream-ordered caller): no sample
+      }
+      ctx->h2d_ev_streams = 0;
+    }
+    if (ctx->h2d_tune_bytes != g_bytes) {
+      ctx->h2d_tune_bytes = g_bytes;
+      ctx->h2d_tune_calls = 0;
+      ctx->h2d_tune_ms[0] = ctx->h2d_tune_ms[1] = 0.f;
+    }
+    const int call = ctx->h2d_tune_calls++;
+    if (call >= 1 && call <= 4) {
+      ctx->h2d_streams = call <= 2 ? 1 : 2;
+      timed_call = true;
+    } else if (call == 5) {
+      const float t1 = ctx->h2d_tune_ms[0], t2 = ctx->h2d_tune_ms[1];
+      ctx->h2d_streams = (t1 > 0.f && t2 > 0.f && t2 < 0.97f * t1) ? 2 : 1;
+    } else if (call == 0) {
+      ctx->h2d_streams = 1;
+    }
+    if (timed_call) {
+      if (!ctx->h2d_ev0) {
+        DALI_CUDA_OK(ctx, cudaEventCreate(&ctx->h2d_ev0));
+        DALI_CUDA_OK(ctx, cudaEventCreate(&ctx->h2d_ev1));
+      }
+      DALI_CUDA_OK(ctx, cudaEventRecord(ctx->h2d_ev0, ctx->stream));
+    }
+  }
   bool first = true;
   for (int c = 0; c < nchunks; ++c) {
     const int64_t r0 = c * chunk;
@@ -685,6 +731,10 @@ static int gallery_pipelined(dali_ctx *ctx, const Prepared &a, const float *g_ho
       rc = contract(ctx, a, b, Q, r0, n_valid, metric, precision, out_dev + r0, ld);
       if (rc) return rc;
     }
+  }
+  if (timed_call) {
+    DALI_CUDA_OK(ctx, cudaEventRecord(ctx->h2d_ev1, ctx->stream));
+    ctx->h2d_ev_streams = ctx->h2d_streams;
   }
   return DALI_OK;
 }

@@ -114,6 +114,13 @@ struct dali_ctx {
   std::vector<cudaEvent_t> chunk_events;
   size_t next_event = 0;
   int h2d_streams = 1;  // DMA streams one H2D copy is split over (DALI_H2D_STREAMS)
+  // online choice between one and two DMA streams for pipelined host galleries: the first calls
+  // of a context are timed (events around the copy/compute pipeline) with either setting
+  int h2d_tune_calls = 0;        // pipelined calls seen so far
+  int64_t h2d_tune_bytes = 0;    // gallery bytes of the calls being compared
+  float h2d_tune_ms[2] = {0.f, 0.f};  // best pipeline time with 1 / 2 streams
+  cudaEvent_t h2d_ev0 = nullptr, h2d_ev1 = nullptr;
+  int h2d_ev_streams = 0;        // setting the pending event pair was recorded with (0: none)
   // timing
   bool timing = false;
   int t_launches[DALI_K_COUNT_] = {0};

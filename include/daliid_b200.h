@@ -87,6 +87,11 @@ int dali_ctx_set_stream(dali_ctx *ctx, void *cuda_stream);
 void *dali_ctx_get_stream(dali_ctx *ctx);
 const char *dali_last_error(dali_ctx *ctx);
 const char *dali_strerror(int code);
+/* Number of DMA streams host operands are currently copied with (1 or 2).  For host galleries of
+ * 24 MB and more the library times its copy/compute pipeline with one and with two streams during
+ * the first calls of a context and keeps the faster setting; DALI_H2D_STREAMS=1..4 fixes it. */
+int dali_ctx_h2d_streams(const dali_ctx *ctx);
+
 /* Per-kernel device timing.  When enabled, every kernel launch of this context is
  * bracketed by cudaEvents on the context's stream; dali_ctx_timing_read returns, for
  * kernel slot `which` (DALI_K_*), the number of launches and their summed duration in
