@@ -19,12 +19,13 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libdaliid_b200.so")
 ABI_VERSION = 1
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_VALID_QUERY, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 ERR_PEER_CAPACITY = -6
+ERR_PEER_TIMEOUT = -7
 METRICS = {"cosine": 0, "sqeuclidean": 1, "euclidean": 2, "dot": 3}
 PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2, "tf32c": 3, "f16x3": 4, "f16": 5}
 ACCUMS = {"cy_f32": 0, "py_f64": 1}
 K_NORMALIZE, K_DISTMAT, K_RANK_COUNT, K_RANK_FINALIZE, K_TOPK, K_FUSE, K_RANK_GATHER, K_RERANK = range(8)
 KERNEL_SLOTS = {"normalize": 0, "distmat": 1, "rank_count": 2, "rank_finalize": 3, "topk": 4,
-                "fuse": 5, "rank_gather": 6, "rerank": 7, "mrfuse": 8}
+                "fuse": 5, "rank_gather": 6, "rerank": 7, "mrfuse": 8, "peer_exchange": 9, "h2d": 10}
 CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy handle
 
 NO_VALID_MSG = "Error: all query identities do not appear in gallery"
@@ -73,6 +74,7 @@ _SIGNATURES = {
     "dali_peer_capacity": (i64, [c_vp]),
     "dali_peer_buffer": (c_vp, [c_vp, ci]),
     "dali_peer_allreduce_i32": (ci, [c_vp, c_vp, ci, c_vp, i64]),
+    "dali_peer_status": (ci, [c_vp]),
     "dali_eval_features_sharded_f32": (ci, [c_vp, c_vp, c_vp, i64, c_vp, i64, i64, i64, i64, c_i32p, c_i32p,
                                             c_i32p, c_i32p, ci, ci, ci, ci, ci, c_f32p, c_f64p, c_f64p,
                                             c_i32p, c_i64p, c_i64p]),

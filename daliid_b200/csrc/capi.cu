@@ -175,7 +175,6 @@ static int stage_in(dali_ctx *ctx, int slot, const float *p, int64_t rows, int64
   int rc = ws_ensure(ctx, slot, sizeof(float) * rows * cols, &d);
   if (rc) return rc;
   if (ld == cols) {
-    ctx->next_event = 0;  // the event pool is reused call by call (stream order keeps this safe)
     rc = h2d_parallel(ctx, d, p, sizeof(float) * rows * cols, true);
     if (rc) return rc;
   } else {
@@ -342,11 +341,22 @@ static int finish_on_host(dali_ctx *ctx, const dali_rank_plan *plan, const int32
   return DALI_OK;
 }
 
-static int check_ctx(dali_ctx *ctx) {
+// Every entry point runs on the context's device and puts the caller's current device back on
+// exit (a process that drives several GPUs keeps torch's current device where it was).
+int DeviceGuard::enter(dali_ctx *ctx) {
   if (!ctx) return DALI_ERR_INVALID;
-  cudaError_t e = cudaSetDevice(ctx->device);
-  if (e != cudaSuccess) return set_err(ctx, DALI_ERR_CUDA, cudaGetErrorString(e));
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); cur = -1; }
+  if (cur != ctx->device) {
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return set_err(ctx, DALI_ERR_CUDA, cudaGetErrorString(e));
+    prev = cur;
+  }
+  ctx->next_event = 0;  // the copy-event pool is reused call by call (stream order keeps this safe)
   return DALI_OK;
+}
+DeviceGuard::~DeviceGuard() {
+  if (prev >= 0) cudaSetDevice(prev);
 }
 
 // Prepared operand planes for the contraction kernels.
@@ -394,7 +404,7 @@ static int prep_rows(dali_ctx *ctx, const Prepared &o, const float *xd, int64_t 
   return launch_prep(ctx, xd, n_valid, D, ldx, o.planes ? o.planes + off : nullptr,
                      o.npl == 2 ? o.planes + o.rows_pad * o.Dp + off : nullptr, o.Dp, o.Dp, r1 - r0,
                      normalize,
-                     precision == DALI_PREC_FP32 ? 0 : (precision == DALI_PREC_F16X3 || precision == DALI_PREC_F16) ? 2 : 1,
+                     precision == DALI_PREC_FP32 ? 0 : precision == DALI_PREC_F16X3 ? 3 : precision == DALI_PREC_F16 ? 2 : 1,
                      nullptr,
                      o.sq ? o.sq + r0 : nullptr, p16 ? p16 + 2 * off : nullptr,
                      p16 ? p16 + 2 * (o.rows_pad * o.Dp + off) : nullptr);
@@ -489,6 +499,9 @@ const char *dali_strerror(int code) {
     case DALI_ERR_NO_VALID_QUERY: return "Error: all query identities do not appear in gallery";
     case DALI_ERR_UNSUPPORTED: return "unsupported";
     case DALI_ERR_NOMEM: return "out of device memory";
+    case DALI_ERR_PEER_CAPACITY: return "peer block too small";
+    case DALI_ERR_PEER_TIMEOUT: return "peer exchange timed out";
+    case DALI_ERR_FUSED_FALLBACK: return "fused path not applicable";
     default: return "unknown error";
   }
 }
@@ -515,12 +528,19 @@ int dali_ctx_create(dali_ctx **out, int device) {
     g_create_err = "device is not compute capability 10.x (kernels are built for sm_100a only)";
     return DALI_ERR_CUDA;
   }
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
   if (cudaSetDevice(device) != cudaSuccess) return DALI_ERR_CUDA;
+  struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev == device ? -1 : prev_dev};
   dali_ctx *c = new dali_ctx();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
   c->cc_major = prop.major;
   c->cc_minor = prop.minor;
+  {
+    int khz = 0;
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device) == cudaSuccess && khz > 0) c->clock_khz = khz;
+  }
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete c;
     return DALI_ERR_CUDA;
@@ -532,7 +552,8 @@ int dali_ctx_create(dali_ctx **out, int device) {
 
 void dali_ctx_destroy(dali_ctx *ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
+  DeviceGuard dg;
+  dg.enter(ctx);
   cudaStreamSynchronize(ctx->stream);
   for (auto &pe : ctx->t_pending) {
     cudaEventDestroy(pe.second.first);
@@ -551,6 +572,7 @@ void dali_ctx_destroy(dali_ctx *ctx) {
   if (ctx->plan_stage_done) cudaEventDestroy(ctx->plan_stage_done);
   if (ctx->h2d_ev0) cudaEventDestroy(ctx->h2d_ev0);
   if (ctx->h2d_ev1) cudaEventDestroy(ctx->h2d_ev1);
+  if (ctx->handover) cudaEventDestroy(ctx->handover);
   for (auto e : ctx->chunk_events) cudaEventDestroy(e);
   for (auto st : ctx->copy_streams)
     if (st) cudaStreamDestroy(st);
@@ -560,8 +582,18 @@ void dali_ctx_destroy(dali_ctx *ctx) {
 
 int dali_ctx_set_stream(dali_ctx *ctx, void *cuda_stream) {
   if (!ctx) return DALI_ERR_INVALID;
+  DeviceGuard dg;
+  if (int rc = dg.enter(ctx)) return rc;
+  cudaStream_t next = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  if (next == ctx->stream) return DALI_OK;
   timing_drain(ctx);
-  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  // The context's workspaces (operand planes, the internal matrix, staging slots, cached plan) are
+  // ordered only on the stream of the previous call, and device-output calls return without a host
+  // synchronisation: the new stream must not reuse them before that work has finished.
+  if (!ctx->handover) DALI_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->handover, cudaEventDisableTiming));
+  DALI_CUDA_OK(ctx, cudaEventRecord(ctx->handover, ctx->stream));
+  DALI_CUDA_OK(ctx, cudaStreamWaitEvent(next, ctx->handover, 0));
+  ctx->stream = next;
   return DALI_OK;
 }
 
@@ -613,7 +645,8 @@ int dali_ctx_plan_cache_enable(dali_ctx *ctx, int on) {
 // ---------------------------------------------------------------------------
 int dali_normalize_f32(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx, float *out,
                        int64_t ldo, float *norms_opt) {
-  int rc = check_ctx(ctx);
+  DeviceGuard dg;
+  int rc = dg.enter(ctx);
   if (rc) return rc;
   if (n < 0 || d <= 0 || ldx < d || ldo < d || !x || !out)
     return set_err(ctx, DALI_ERR_INVALID, "normalize: bad shape or null pointer");
@@ -755,7 +788,8 @@ static int distmat_to(dali_ctx *ctx, const float *q, int64_t Q, const float *g, 
 
 int dali_distmat_f32(dali_ctx *ctx, const float *q, int64_t Q, const float *g, int64_t G, int64_t D,
                      int metric, int precision, int normalize, float *out, int64_t ld) {
-  int rc = check_ctx(ctx);
+  DeviceGuard dg;
+  int rc = dg.enter(ctx);
   if (rc) return rc;
   if (Q < 0 || G < 0 || D <= 0 || ld < G || !out || (!q && Q) || (!g && G))
     return set_err(ctx, DALI_ERR_INVALID, "distmat: bad shape or null pointer");
@@ -785,7 +819,8 @@ int dali_distmat_f32(dali_ctx *ctx, const float *q, int64_t Q, const float *g, i
 // ---------------------------------------------------------------------------
 int dali_fuse_f32(dali_ctx *ctx, const float *const *d, int n, const float *const *wq,
                   const float *const *wg, float *out, int64_t Q, int64_t G, int64_t ld) {
-  int rc = check_ctx(ctx);
+  DeviceGuard dg;
+  int rc = dg.enter(ctx);
   if (rc) return rc;
   if (!d || !out || n < 1 || n > 8 || Q < 0 || G < 0 || ld < G || ((wq == nullptr) != (wg == nullptr)))
     return set_err(ctx, DALI_ERR_INVALID, "fuse: bad arguments (1..8 matrices, wq and wg together)");
@@ -857,7 +892,8 @@ int dali_fuse_f32(dali_ctx *ctx, const float *const *d, int n, const float *cons
 int dali_rank_plan_create(dali_ctx *ctx, const int32_t *q_pid, const int32_t *g_pid,
                           const int32_t *q_cam, const int32_t *g_cam, int64_t Q, int64_t G,
                           dali_rank_plan **out) {
-  int rc = check_ctx(ctx);
+  DeviceGuard dg;
+  int rc = dg.enter(ctx);
   if (rc) return rc;
   if (!out || Q < 0 || G < 0 || (Q && (!q_pid || !q_cam)) || (G && (!g_pid || !g_cam)))
     return set_err(ctx, DALI_ERR_INVALID, "rank plan: bad arguments");
@@ -1029,7 +1065,8 @@ int64_t dali_rank_plan_num_matches(const dali_rank_plan *plan) { return plan ? p
 
 int dali_rank_gather_keys(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist_slab,
                           int64_t ld, int64_t g0, int64_t Gs, uint32_t *keys_out) {
-  int rc = check_ctx(ctx);
+  DeviceGuard dg;
+  int rc = dg.enter(ctx);
   if (rc) return rc;
   if (!plan || !keys_out || (!dist_slab && Gs) || ld < Gs || g0 < 0 || g0 + Gs > plan->G)
     return set_err(ctx, DALI_ERR_INVALID, "gather_keys: bad arguments");
@@ -1043,7 +1080,8 @@ int dali_rank_gather_keys(dali_ctx *ctx, const dali_rank_plan *plan, const float
 
 int dali_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist_slab, int64_t ld,
                     int64_t g0, int64_t Gs, const uint32_t *keys, int32_t *counts_out) {
-  int rc = check_ctx(ctx);
+  DeviceGuard dg;
+  int rc = dg.enter(ctx);
   if (rc) return rc;
   if (!plan || !keys || !counts_out || (!dist_slab && Gs) || ld < Gs || g0 < 0 || g0 + Gs > plan->G)
     return set_err(ctx, DALI_ERR_INVALID, "rank_count: bad arguments");
@@ -1054,7 +1092,8 @@ int dali_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist
 int dali_rank_finalize(dali_ctx *ctx, const dali_rank_plan *plan, const uint32_t *keys,
                        const int32_t *counts, int max_rank, int accum_mode, float *cmc, double *mAP,
                        double *ap_opt, int32_t *first_rank_opt, int64_t *num_valid_opt) {
-  int rc = check_ctx(ctx);
+  DeviceGuard dg;
+  int rc = dg.enter(ctx);
   if (rc) return rc;
   if (!plan || !cmc || !mAP || max_rank < 1 || (plan->M && (!keys || !counts)))
     return set_err(ctx, DALI_ERR_INVALID, "rank_finalize: bad arguments");
@@ -1083,7 +1122,8 @@ int dali_eval_rank_f32(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, i
                        const int32_t *q_pid, const int32_t *g_pid, const int32_t *q_cam,
                        const int32_t *g_cam, int max_rank, int accum_mode, float *cmc, double *mAP,
                        double *ap_opt, int32_t *first_rank_opt, int64_t *num_valid_opt) {
-  int rc = check_ctx(ctx);
+  DeviceGuard dg;
+  int rc = dg.enter(ctx);
   if (rc) return rc;
   if (Q < 0 || G < 0 || ld < G || (!dist && Q && G) || !cmc || !mAP || max_rank < 1)
     return set_err(ctx, DALI_ERR_INVALID, "eval_rank: bad shape or null pointer");
@@ -1113,7 +1153,8 @@ int dali_eval_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float
   static const bool trace = getenv("DALI_TRACE") != nullptr;  // debugging: host-side timeline of the call
   const auto t_in = std::chrono::steady_clock::now();
   auto since = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_in).count(); };
-  int rc = check_ctx(ctx);
+  DeviceGuard dg;
+  int rc = dg.enter(ctx);
   if (rc) return rc;
   if (Q < 0 || G < 0 || D <= 0 || (!q && Q) || (!g && G) || !cmc || !mAP || max_rank < 1 ||
       (distmat_opt && ld_opt < G))
@@ -1187,7 +1228,8 @@ static int topk_out(dali_ctx *ctx, const float *dist_dev, int64_t Q, int64_t G, 
 
 int dali_topk_f32(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t ld, int k,
                   int largest, const int32_t *col_ids_opt, float *d_out, int32_t *i_out) {
-  int rc = check_ctx(ctx);
+  DeviceGuard dg;
+  int rc = dg.enter(ctx);
   if (rc) return rc;
   if (Q < 0 || G < 0 || ld < G || (!dist && Q && G) || !d_out || !i_out || k < 1 || k > 128)
     return set_err(ctx, DALI_ERR_INVALID, "topk: bad arguments (1 <= k <= 128)");
@@ -1217,7 +1259,8 @@ int dali_topk_f32(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_
 int dali_rerank_f32(dali_ctx *ctx, const float *qg, int64_t ld_qg, const float *qq, int64_t ld_qq,
                     const float *gg, int64_t ld_gg, int64_t Q, int64_t G, int k1, int k2,
                     double lambda_value, float *out, int64_t ld_out) {
-  int rc = check_ctx(ctx);
+  DeviceGuard dg;
+  int rc = dg.enter(ctx);
   if (rc) return rc;
   if (Q < 0 || G < 0 || !out || (Q && G && (!qg || !qq || !gg)) || ld_qg < G || ld_qq < Q || ld_gg < G ||
       ld_out < G)
@@ -1249,7 +1292,8 @@ int dali_rerank_f32(dali_ctx *ctx, const float *qg, int64_t ld_qg, const float *
 
 int dali_argsort_f32(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t ld,
                      int descending, int32_t *idx_out) {
-  int rc = check_ctx(ctx);
+  DeviceGuard dg;
+  int rc = dg.enter(ctx);
   if (rc) return rc;
   if (Q < 0 || G < 0 || ld < G || (Q && G && (!dist || !idx_out)))
     return set_err(ctx, DALI_ERR_INVALID, "argsort: bad shape or null pointer");
@@ -1275,7 +1319,8 @@ int dali_argsort_f32(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int
 int dali_mrfuse_f32(dali_ctx *ctx, const float *const *scores, int n, int64_t Q, int64_t G,
                     int64_t ld, int topk, int use_columns, float killscale, double *fused,
                     int64_t ld_out, double *fit_opt, float *small_opt, double *weights_opt) {
-  int rc = check_ctx(ctx);
+  DeviceGuard dg;
+  int rc = dg.enter(ctx);
   if (rc) return rc;
   if (!scores || n < 1 || n > 3 || Q < 1 || G < 1 || ld < G || ld_out < G || !fused)
     return set_err(ctx, DALI_ERR_INVALID, "mrfuse: bad shape or null pointer");
@@ -1322,7 +1367,8 @@ int dali_eval_features_sharded_f32(dali_ctx *ctx, dali_peer *peer, const float *
                                    int precision, int normalize, int max_rank, int accum_mode,
                                    float *cmc, double *mAP, double *ap_opt, int32_t *first_rank_opt,
                                    int64_t *num_valid_opt, int64_t *matches_out) {
-  int rc = check_ctx(ctx);
+  DeviceGuard dg;
+  int rc = dg.enter(ctx);
   if (rc) return rc;
   if (!peer || Q < 0 || Gs < 0 || D <= 0 || g0 < 0 || g0 + Gs > G_total || (!q && Q) || (!g_slab && Gs) ||
       !cmc || !mAP || max_rank < 1)
@@ -1368,6 +1414,7 @@ int dali_eval_features_sharded_f32(dali_ctx *ctx, dali_peer *peer, const float *
     rc = dali_rank_finalize(ctx, plan, static_cast<const uint32_t *>(keys), static_cast<const int32_t *>(counts),
                             max_rank, accum_mode, cmc, mAP, ap_opt, first_rank_opt, num_valid_opt);
   dali_rank_plan_destroy(plan);
+  if (!rc) rc = dali_peer_status(peer);  // a wait that gave up made the sums meaningless
   return rc;
 }
 
@@ -1469,7 +1516,8 @@ static int topk_features_fused(dali_ctx *ctx, const Prepared &b, const float *q,
 int dali_topk_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float *g, int64_t G,
                            int64_t D, int metric, int precision, int normalize, int k, int largest,
                            int32_t g_base, float *d_out, int32_t *i_out) {
-  int rc = check_ctx(ctx);
+  DeviceGuard dg;
+  int rc = dg.enter(ctx);
   if (rc) return rc;
   if (Q < 0 || G < 0 || D <= 0 || (!q && Q) || (!g && G) || !d_out || !i_out || k < 1 || k > 128)
     return set_err(ctx, DALI_ERR_INVALID, "topk_features: bad arguments");

@@ -98,6 +98,7 @@ struct dali_ctx {
   int device = 0;
   int num_sms = 0;
   int cc_major = 0, cc_minor = 0;
+  int clock_khz = 1965000;  // SM clock the watchdogs convert milliseconds with
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   std::string err;
@@ -121,6 +122,7 @@ struct dali_ctx {
   float h2d_tune_ms[2] = {0.f, 0.f};  // best pipeline time with 1 / 2 streams
   cudaEvent_t h2d_ev0 = nullptr, h2d_ev1 = nullptr;
   int h2d_ev_streams = 0;        // setting the pending event pair was recorded with (0: none)
+  cudaEvent_t handover = nullptr;  // dali_ctx_set_stream: the new stream waits for the old one
   // timing
   bool timing = false;
   int t_launches[DALI_K_COUNT_] = {0};
@@ -173,6 +175,13 @@ int ws_ensure(dali_ctx *ctx, int slot, size_t bytes, void **out);
 // raise a kernel's dynamic shared-memory limit on the context's device (cached per context)
 int ensure_dyn_smem(dali_ctx *ctx, const void *func, size_t bytes);
 
+// Switches to the context's device for the duration of an entry point, restores the caller's.
+struct DeviceGuard {
+  int prev = -1;
+  int enter(dali_ctx *ctx);
+  ~DeviceGuard();
+};
+
 // RAII-less timing helpers: call before/after a kernel launch on ctx->stream.
 struct KTimer {
   dali_ctx *ctx;
@@ -196,6 +205,7 @@ int launch_prep(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx
                 float *plane1, int64_t ldo, int64_t d_pad, int64_t rows_pad, int do_normalize,
                 int round_mode, float *norms, float *sq, void *hi16 = nullptr,
                 void *lo16 = nullptr);
+float f16x3_hi_grid(int64_t d_pad);
 // distmat_simt.cu
 int launch_distmat_simt(dali_ctx *ctx, const float *qn, const float *gn, int64_t Q, int64_t G,
                         int64_t D, int64_t ldq, int64_t ldg, int metric, const float *qsq,

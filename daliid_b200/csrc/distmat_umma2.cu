@@ -29,6 +29,7 @@
 //           evaluate_ensembled_models.py:281,300, evaluateCleanATModels.py:109,121,124
 //           torch.argsort(distmat, dim=1)[:, :20]   validateModels.py:93 (kFilter)
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 #include "umma_common.cuh"
@@ -60,6 +61,10 @@ static_assert(8 * (2 * kSlots + 4) + 8 <= kBarBytes, "barrier block too small");
 
 enum Epi { kStore = 0, kFilter = 1 };
 
+// mean accumulator loss per MMA in units of 2^-24 * s with the fixed-point hi plane, fitted to
+// tests/probes/trunc_probe.py on B200 (constant over D = 512 .. 4096 to +-0.01)
+constexpr double kKappaInterleaved = 0.24, kKappaTwoPass = 0.22;
+
 struct Umma2Params {
   int64_t Q, G;
   int num_m_pairs, num_n_tiles, num_kb;
@@ -80,7 +85,9 @@ struct Umma2Params {
   int largest;
   int direct;           // 1: every column j is written to slot j of the list (first chunk)
   int32_t id_base;      // gallery id of column 0
-  float acc_scale;      // 2^-24 for kF16x3 (operands carry a factor 2^12 each), else 1
+  float acc_scale;      // 2^-24 for kF16x3 (operands carry a factor 2^12 each), else 1; times the
+                        // truncation compensation (see f16x3_schedule)
+  int two_pass;         // kF16x3: all correction MMAs (lo*hi, hi*lo) of a tile first, then hi*hi
 };
 
 // ---- kStore epilogue helpers -----------------------------------------------------------------
@@ -284,6 +291,36 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tile_mn(t, m, n);
         const int arow = m * PM + static_cast<int>(rank) * UM;
         const int brow = p.b_row0 + n * BN + static_cast<int>(rank) * HB;
+        if (MODE == kF16x3 && p.two_pass) {
+          // pass 1: the four planes of a k-block per slot (corrections); pass 2: the hi planes of
+          // TWO k-blocks per slot (same bytes per slot, half the barrier traffic per byte)
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(empty_bar(slot), phase ^ 1u);
+            if (rank == 0) mbar_expect_tx(full_bar(slot), 2 * kSlotBytes);
+            const uint32_t fbh = full0 + 8u * slot;
+            const uint32_t sb = slot_addr(slot);
+            tma_load_2d_pair(sb, &tmA16, fbh, kb * BK, arow);
+            tma_load_2d_pair(sb + A16_BYTES, &tmA16, fbh, kb * BK, p.a_plane_rows + arow);
+            tma_load_2d_pair(sb + 2 * A16_BYTES, &tmB16, fbh, kb * BK, brow);
+            tma_load_2d_pair(sb + 2 * A16_BYTES + B16_BYTES, &tmB16, fbh, kb * BK, p.b_plane_rows + brow);
+            advance();
+          }
+          for (int kb = 0; kb < p.num_kb; kb += 2) {
+            const bool two = kb + 1 < p.num_kb;
+            mbar_wait(empty_bar(slot), phase ^ 1u);
+            if (rank == 0) mbar_expect_tx(full_bar(slot), two ? 2 * kSlotBytes : kSlotBytes);
+            const uint32_t fbh = full0 + 8u * slot;
+            const uint32_t sb = slot_addr(slot);
+            tma_load_2d_pair(sb, &tmA16, fbh, kb * BK, arow);
+            tma_load_2d_pair(sb + 2 * A16_BYTES, &tmB16, fbh, kb * BK, brow);
+            if (two) {
+              tma_load_2d_pair(sb + A16_BYTES, &tmA16, fbh, (kb + 1) * BK, arow);
+              tma_load_2d_pair(sb + 2 * A16_BYTES + B16_BYTES, &tmB16, fbh, (kb + 1) * BK, brow);
+            }
+            advance();
+          }
+          continue;
+        }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           if (MODE == kF16x3 || MODE == kF16) {  // one slot: fp16 hi (and residual) planes of both operands
             mbar_wait(empty_bar(slot), phase ^ 1u);
@@ -343,6 +380,45 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mbar_wait_cluster(tempty_bar(as), ((it >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+        if (MODE == kF16x3 && p.two_pass) {
+          // The tensor core truncates its fp32 accumulator after every MMA; the loss is a fraction
+          // of an ulp of the RUNNING SUM per instruction.  The correction products are tiny, so they
+          // are accumulated first, while the sum is small and nothing is lost; only the D/16 hi*hi
+          // instructions then run on a large accumulator -- a third of the interleaved schedule's.
+          constexpr uint32_t kIdH = idesc_f16(PM);
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(full_bar(slot), phase);
+            tc_fence_after();
+            const uint32_t ahi = slot_addr(slot), alo = ahi + A16_BYTES;
+            const uint32_t bhi = ahi + 2 * A16_BYTES, blo = bhi + B16_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              tc_mma_bf16<2>(tmem_d, make_desc_sw64(alo + k * 32), make_desc_sw64(bhi + k * 32), kIdH,
+                             (kb | k) ? 1u : 0u);                                   // lo * hi
+              tc_mma_bf16<2>(tmem_d, make_desc_sw64(ahi + k * 32), make_desc_sw64(blo + k * 32), kIdH, 1u);  // hi * lo
+            }
+            tc_commit_pair(empty_bar(slot), 3);
+            advance();
+          }
+          for (int kb = 0; kb < p.num_kb; kb += 2) {
+            mbar_wait(full_bar(slot), phase);
+            tc_fence_after();
+            const uint32_t a0h = slot_addr(slot), b0h = a0h + 2 * A16_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              tc_mma_bf16<2>(tmem_d, make_desc_sw64(a0h + k * 32), make_desc_sw64(b0h + k * 32), kIdH, 1u);
+            if (kb + 1 < p.num_kb) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                tc_mma_bf16<2>(tmem_d, make_desc_sw64(a0h + A16_BYTES + k * 32),
+                               make_desc_sw64(b0h + B16_BYTES + k * 32), kIdH, 1u);
+            }
+            tc_commit_pair(empty_bar(slot), 3);
+            advance();
+          }
+          tc_commit_pair(tfull_bar(as), 3);
+          continue;
+        }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(full_bar(slot), phase);
           tc_fence_after();
@@ -582,6 +658,43 @@ int launch_prec(dali_ctx *ctx, int precision, const CUtensorMap &tmA, const CUte
   }
 }
 
+// F16X3 arithmetic: operand format, MMA schedule and truncation compensation.
+//
+// What the tensor core does (measured on B200, tests/probes/trunc_probe.py): the 16 products of a
+// kind::f16 MMA are aligned to the exponent of the fp32 accumulator and TRUNCATED (toward zero)
+// about two bits below its ulp, and the sum is truncated to fp32 again.  With plain fp16 hi
+// planes (22-bit products) every hi*hi MMA adding into a running sum s lost ~2.2 ulp(s), every
+// correction MMA ~0.3 ulp(s): invisible for ordinary pairs (|s| << 1, error ~1e-7), but a
+// near-duplicate pair (s -> 1) came out low by 1.5e-5 at D = 2048 and 2.8e-5 at D = 3840 --
+// beyond the 1e-5 parity bar.  Three measures, cheapest first:
+//   1. fixed-point hi plane (normalize.cu, hi_quant): hi = multiple of 0.5 of the 2^12-scaled
+//      value, so every hi*hi product is a multiple of 0.25 -- nothing is lost at the alignment
+//      step, and only the fractional part of the sum (0.22 ulp on average) at the final one.
+//      The residual plane then holds |lo| <= 0.25 and the dropped lo*lo term is D/48 * 2^-24 for
+//      an exact duplicate (2.5e-6 at D = 2048), ~0 otherwise.
+//   2. the mean loss that remains is given back: the accumulator is multiplied by
+//      1 + kappa * N * 2^-24 (N = MMAs issued on the large accumulator, kappa fitted: 0.24 per MMA
+//      interleaved, 0.22 corrections-first), folded into the 2^-24 that undoes the operand scaling
+//      -- no extra instruction, pairs with s ~ 0 unchanged.
+//   3. D > 2048: all correction MMAs of a tile first, hi*hi last (two_pass): the 2 D / 16 correction
+//      instructions then run on a small accumulator and lose nothing.  Costs 1.5x the operand
+//      traffic (13 % of the kernel at D = 2048), hence only where 1 + 2 are not enough.
+// Measured after 1-3 (float64 reference): exact duplicates <= 4.5e-6 at D = 2048 and <= 5.5e-6 at
+// D = 3840 / 4096; adversarial partial-sum trajectories (all energy in the first / last k-block)
+// <= 8e-6; ordinary pairs <= 1e-6.  DALI_F16X3_TWO_PASS=0/1, DALI_F16X3_COMP=<kappa> (0 = off)
+// and DALI_F16X3_GRID=<grid> (0 = plain fp16) override for calibration runs.
+void f16x3_schedule(int64_t Dp, int *two_pass, float *acc_scale) {
+  static const char *env_tp = getenv("DALI_F16X3_TWO_PASS");
+  static const char *env_k = getenv("DALI_F16X3_COMP");
+  const bool tp = env_tp ? atoi(env_tp) != 0 : Dp > 2048;
+  double kappa = tp ? kKappaTwoPass : kKappaInterleaved;
+  if (f16x3_hi_grid(Dp) != 0.5f) kappa = 0.0;  // the constants belong to the default operand format
+  if (env_k) kappa = atof(env_k);
+  const double n = tp ? static_cast<double>(Dp) / 16.0 : 3.0 * static_cast<double>(Dp) / 16.0;
+  *two_pass = tp ? 1 : 0;
+  *acc_scale = static_cast<float>(5.9604644775390625e-08 * (1.0 + kappa * n * 5.9604644775390625e-08));
+}
+
 // Output map: fp32 [Q][G] with row pitch ld, 32 x 32 boxes in the 128-byte swizzle the epilogue
 // writes its staging tiles in.
 int make_out_map(dali_ctx *ctx, CUtensorMap *map, float *out, int64_t Q, int64_t G, int64_t ld) {
@@ -639,6 +752,7 @@ int setup(dali_ctx *ctx, const float *q32, const float *g32, const void *q16, co
   p->b_row0 = static_cast<int32_t>(g_row0);
   p->metric = metric; p->qsq = qsq; p->gsq = gsq;
   p->acc_scale = f16 ? 5.9604644775390625e-08f /* 2^-24 */ : 1.0f;
+  if (precision == DALI_PREC_F16X3) f16x3_schedule(Dp, &p->two_pass, &p->acc_scale);
   {
     // bytes of operand planes one tile row of 256 rows reads per pass over K
     const int64_t bytes_per_row = Dp * (precision == DALI_PREC_F16 ? 2 : precision == DALI_PREC_TF32 ? 4 : precision == DALI_PREC_F16X3 ? 4 : 8);

@@ -38,6 +38,14 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(u);
 }
 
+// round_mode 2 with a fixed-point hi plane: hi = nearest multiple of `grid` (then fp16, which is
+// exact below 2048 * grid and coarser -- still a multiple -- above).  Products hi * hi are then
+// multiples of grid^2, which the tensor core adds into its fp32 accumulator without dropping low
+// bits at the alignment step (see distmat_umma2.cu, f16x3_schedule).
+__device__ __forceinline__ float hi_quant(float s, float grid_inv, float grid) {
+  return grid_inv != 0.f ? rintf(s * grid_inv) * grid : s;
+}
+
 struct PrepParams {
   const float *x;
   int64_t n, d, ldx;
@@ -46,6 +54,7 @@ struct PrepParams {
   int64_t ldo, d_pad, rows_pad;
   int do_normalize;
   int round_mode;  // 0 keep fp32, 1 round plane0 to tf32, 2 fp16 hi/residual of 2^12 * x (no fp32 plane)
+  float hi_grid_inv, hi_grid;  // round_mode 2: hi is first rounded to a multiple of hi_grid (0: off)
   float *norms;    // nullable: ||x|| of the input row
   float *sq;       // nullable: sum of squares of the OUTPUT row (fp32 values before tf32 rounding)
   __nv_bfloat16 *hi16;  // nullable: bf16 copy of plane0 (TF32C correction operand)
@@ -90,7 +99,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_rows_kernel(PrepParams p) {
       // unit rows: |v| <= 1, so 4096 v fits fp16 (max 65504) and a typical 1/sqrt(D) entry and
       // its residual stay in the normal range; the contraction's epilogue multiplies by 2^-24
       const float sv = v * 4096.0f;
-      const __half hi = __float2half_rn(sv);
+      const __half hi = __float2half_rn(hi_quant(sv, p.hi_grid_inv, p.hi_grid));
       reinterpret_cast<__half *>(h16)[c] = hi;
       reinterpret_cast<__half *>(l16)[c] = __float2half_rn(sv - __half2float(hi));
     } else if (p.round_mode) {
@@ -172,8 +181,9 @@ __global__ void __launch_bounds__(kPrepThreads) prep_rows_vec_kernel(PrepParams 
     acc2 = fmaf(v.z, v.z, acc2); acc2 = fmaf(v.w, v.w, acc2);
     if (p.round_mode == 2) {
       const float sx = v.x * 4096.0f, sy = v.y * 4096.0f, sz = v.z * 4096.0f, sw = v.w * 4096.0f;
-      const __half hx = __float2half_rn(sx), hy = __float2half_rn(sy), hz = __float2half_rn(sz),
-                   hw = __float2half_rn(sw);
+      const float gi = p.hi_grid_inv, gg = p.hi_grid;
+      const __half hx = __float2half_rn(hi_quant(sx, gi, gg)), hy = __float2half_rn(hi_quant(sy, gi, gg)),
+                   hz = __float2half_rn(hi_quant(sz, gi, gg)), hw = __float2half_rn(hi_quant(sw, gi, gg));
       h16[c] = pack_f16x4(hx, hy, hz, hw);
       l16[c] = pack_f16x4(__float2half_rn(sx - __half2float(hx)), __float2half_rn(sy - __half2float(hy)),
                           __float2half_rn(sz - __half2float(hz)), __float2half_rn(sw - __half2float(hw)));
@@ -243,7 +253,9 @@ __global__ void __launch_bounds__(kPrepThreads) prep_f16_kernel(PrepParams p) {
       const float4 v = cache[i];  // zeros beyond d (0 * inf: only in a NaN row anyway)
       const float sx = c < nv ? v.x * scale : 0.f, sy = c < nv ? v.y * scale : 0.f;
       const float sz = c < nv ? v.z * scale : 0.f, sw = c < nv ? v.w * scale : 0.f;
-      const __half2 h01 = __floats2half2_rn(sx, sy), h23 = __floats2half2_rn(sz, sw);
+      const float gi = p.hi_grid_inv, gg = p.hi_grid;
+      const __half2 h01 = __floats2half2_rn(hi_quant(sx, gi, gg), hi_quant(sy, gi, gg)),
+                    h23 = __floats2half2_rn(hi_quant(sz, gi, gg), hi_quant(sw, gi, gg));
       const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
       const __half2 l01 = __floats2half2_rn(sx - f01.x, sy - f01.y), l23 = __floats2half2_rn(sz - f23.x, sw - f23.y);
       h16[c] = make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
@@ -309,7 +321,9 @@ __global__ void __launch_bounds__(kPrepThreads) prep_f16_warp_kernel(PrepParams 
       const float4 v = cache[i];
       const float sx = c < nv ? v.x * scale : 0.f, sy = c < nv ? v.y * scale : 0.f;
       const float sz = c < nv ? v.z * scale : 0.f, sw = c < nv ? v.w * scale : 0.f;
-      const __half2 h01 = __floats2half2_rn(sx, sy), h23 = __floats2half2_rn(sz, sw);
+      const float gi = p.hi_grid_inv, gg = p.hi_grid;
+      const __half2 h01 = __floats2half2_rn(hi_quant(sx, gi, gg), hi_quant(sy, gi, gg)),
+                    h23 = __floats2half2_rn(hi_quant(sz, gi, gg), hi_quant(sw, gi, gg));
       const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
       const __half2 l01 = __floats2half2_rn(sx - f01.x, sy - f01.y), l23 = __floats2half2_rn(sz - f23.x, sw - f23.y);
       h16[c] = make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
@@ -330,11 +344,23 @@ __global__ void __launch_bounds__(kPrepThreads) prep_f16_warp_kernel(PrepParams 
 
 }  // namespace
 
+// Grid of the fixed-point hi plane (0 = plain fp16 rounding); DALI_F16X3_GRID overrides (probes).
+float f16x3_hi_grid(int64_t) {
+  static const char *env = getenv("DALI_F16X3_GRID");
+  if (env) return static_cast<float>(atof(env));
+  return 0.5f;
+}
+
 int launch_prep(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx, float *plane0,
                 float *plane1, int64_t ldo, int64_t d_pad, int64_t rows_pad, int do_normalize,
                 int round_mode, float *norms, float *sq, void *hi16, void *lo16) {
   if (rows_pad == 0) return DALI_OK;
-  PrepParams p{x, n, d, ldx, plane0, plane1, ldo, d_pad, rows_pad, do_normalize, round_mode, norms, sq,
+  // round_mode 3 = round_mode 2 with the fixed-point hi plane of the three-pass fp16 arithmetic
+  // (the single-pass F16 mode keeps plain fp16 rounding: it has no residual to absorb a coarser hi)
+  const float hgrid = round_mode == 3 ? f16x3_hi_grid(d_pad) : 0.f;
+  if (round_mode == 3) round_mode = 2;
+  PrepParams p{x, n, d, ldx, plane0, plane1, ldo, d_pad, rows_pad, do_normalize, round_mode,
+               hgrid > 0.f ? 1.0f / hgrid : 0.f, hgrid, norms, sq,
                static_cast<__nv_bfloat16 *>(hi16), static_cast<__nv_bfloat16 *>(lo16)};
   KTimer t(ctx, DALI_K_NORMALIZE);
   const bool vec = d % 4 == 0 && d_pad <= 4 * kPrepThreads * kVecCache && ldx % 4 == 0 && ldo % 4 == 0 &&

@@ -14,6 +14,7 @@
 // buffer is two epochs later and therefore after every peer finished reading it.
 // One process per GPU; kernels of different ranks run on different GPUs (never on one device).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -34,13 +35,15 @@ namespace dali {
 namespace {
 
 constexpr int kFlagBytes = 256;
-constexpr unsigned long long kPeerWatchdog = 6000000000ull;  // ~3 s
+constexpr int kStatusWord = 32;  // flags[32]: first epoch whose wait ran out of time (0 = none)
 
 struct PeerPtrs {
   const uint32_t *flags_local;   // this rank's flag words
   uint32_t *flags[8];            // every rank's flag block
   const int32_t *buf[8];         // every rank's contribution
   int world, rank;
+  uint32_t *status;              // this rank's timeout word
+  unsigned long long watchdog;   // clock64 ticks a wait may take
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
@@ -61,8 +64,15 @@ peer_allreduce_kernel(PeerPtrs pp, uint32_t epoch, int32_t *__restrict__ out, in
   if (threadIdx.x < pp.world) {
     const unsigned long long t0 = clock64();
     // epochs are compared modulo 2^32 (signed difference): they only ever differ by a few
+    // A peer that never arrives (a rank died, or is stuck in first-call allocations for longer
+    // than the limit) must not hang the GPU, and a trap would poison the whole context: the wait
+    // gives up, records the epoch in the status word and lets the kernel finish (its sums are then
+    // meaningless); the host reads the word with the results and reports DALI_ERR_PEER_TIMEOUT.
     while (static_cast<int32_t>(ld_acquire_sys(pp.flags_local + threadIdx.x) - epoch) < 0) {
-      if (clock64() - t0 > kPeerWatchdog) __trap();
+      if (clock64() - t0 > pp.watchdog) {
+        atomicCAS(pp.status, 0u, epoch);
+        break;
+      }
     }
   }
   __syncthreads();
@@ -86,7 +96,8 @@ extern "C" {
 int dali_peer_create(dali_ctx *ctx, int rank, int world, int64_t capacity, dali_peer **out) {
   if (!ctx || !out || world < 1 || world > 8 || rank < 0 || rank >= world || capacity < 1)
     return set_err(ctx, DALI_ERR_INVALID, "peer_create: 1 <= world <= 8, 0 <= rank < world, capacity >= 1");
-  DALI_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DeviceGuard dg;
+  if (int rc = dg.enter(ctx)) return rc;
   dali_peer *p = new dali_peer();
   p->ctx = ctx; p->rank = rank; p->world = world;
   p->cap = (capacity + 63) / 64 * 64;
@@ -108,7 +119,8 @@ int dali_peer_ipc_handle(dali_peer *p, void *handle64) {
   if (!p || !handle64) return DALI_ERR_INVALID;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   cudaIpcMemHandle_t h;
-  DALI_CUDA_OK(p->ctx, cudaSetDevice(p->ctx->device));
+  DeviceGuard dg;
+  if (int rc = dg.enter(p->ctx)) return rc;
   DALI_CUDA_OK(p->ctx, cudaIpcGetMemHandle(&h, p->local));
   std::memcpy(handle64, &h, 64);
   return DALI_OK;
@@ -116,7 +128,8 @@ int dali_peer_ipc_handle(dali_peer *p, void *handle64) {
 
 int dali_peer_connect(dali_peer *p, const void *handles) {
   if (!p || !handles) return DALI_ERR_INVALID;
-  DALI_CUDA_OK(p->ctx, cudaSetDevice(p->ctx->device));
+  DeviceGuard dg;
+  if (int rc = dg.enter(p->ctx)) return rc;
   for (int r = 0; r < p->world; ++r) {
     if (r == p->rank) continue;
     cudaIpcMemHandle_t h;
@@ -134,7 +147,8 @@ int dali_peer_connect(dali_peer *p, const void *handles) {
 
 void dali_peer_destroy(dali_peer *p) {
   if (!p) return;
-  cudaSetDevice(p->ctx->device);
+  DeviceGuard dg;
+  dg.enter(p->ctx);
   cudaStreamSynchronize(p->ctx->stream);
   for (int r = 0; r < p->world; ++r)
     if (r != p->rank && p->peers[r]) cudaIpcCloseMemHandle(p->peers[r]);
@@ -149,11 +163,26 @@ void *dali_peer_buffer(dali_peer *p, int which) {
   return static_cast<char *>(p->local) + kFlagBytes + sizeof(int32_t) * p->cap * which;
 }
 
+int dali_peer_status(dali_peer *p) {
+  if (!p) return DALI_ERR_INVALID;
+  DeviceGuard dg;
+  if (int rc = dg.enter(p->ctx)) return rc;
+  uint32_t word = 0;
+  DALI_CUDA_OK(p->ctx, cudaMemcpyAsync(&word, reinterpret_cast<uint32_t *>(p->local) + kStatusWord, sizeof(word),
+                                       cudaMemcpyDeviceToHost, p->ctx->stream));
+  DALI_CUDA_OK(p->ctx, cudaStreamSynchronize(p->ctx->stream));
+  if (word)
+    return set_err(p->ctx, DALI_ERR_PEER_TIMEOUT,
+                   "peer exchange " + std::to_string(word) + " timed out waiting for another rank (DALI_PEER_TIMEOUT_MS)");
+  return DALI_OK;
+}
+
 int dali_peer_allreduce_i32(dali_ctx *ctx, dali_peer *p, int which, int32_t *out, int64_t n) {
   if (!ctx || !p || !out || which < 0 || which > 1 || n < 0 || n > p->cap || p->ctx != ctx)
     return set_err(ctx, DALI_ERR_INVALID, "peer_allreduce: bad arguments");
   if (!p->connected) return set_err(ctx, DALI_ERR_INVALID, "peer_allreduce: peers not connected");
-  DALI_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  DeviceGuard dg;
+  if (int rc = dg.enter(ctx)) return rc;
   PeerPtrs pp;
   pp.world = p->world; pp.rank = p->rank;
   pp.flags_local = static_cast<const uint32_t *>(p->local);
@@ -162,9 +191,15 @@ int dali_peer_allreduce_i32(dali_ctx *ctx, dali_peer *p, int which, int32_t *out
     pp.flags[r] = reinterpret_cast<uint32_t *>(base);
     pp.buf[r] = reinterpret_cast<const int32_t *>(base + kFlagBytes + sizeof(int32_t) * p->cap * which);
   }
+  pp.status = reinterpret_cast<uint32_t *>(p->local) + kStatusWord;
+  {
+    static const char *env = getenv("DALI_PEER_TIMEOUT_MS");  // default 20 s
+    const double ms = env ? std::max(1.0, atof(env)) : 20000.0;
+    pp.watchdog = static_cast<unsigned long long>(ms * 1e-3 * ctx->clock_khz * 1e3);
+  }
   p->epoch += 1;
   const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 2 * ctx->num_sms)));
-  ctx->launches++;
+  KTimer t(ctx, DALI_K_PEER_EXCHANGE);
   peer_allreduce_kernel<<<blocks, 256, 0, ctx->stream>>>(pp, p->epoch, out, n);
   DALI_CUDA_OK(ctx, cudaGetLastError());
   return DALI_OK;

@@ -600,10 +600,12 @@ int launch_rank_fused(dali_ctx *ctx, const dali_rank_plan *plan, const float *di
   const int64_t min_split = (G + (4ll << 20) - 1) / (4ll << 20);
   if (std::max<int64_t>(std::max<int64_t>(1, std::min(want, max_split)), min_split) != 1) return DALI_OK;
   // many thresholds per query (DeepChange: ~120): byte counters, which limit a thread to 255
-  // elements -- one 256-thread CTA then covers rows of up to 65280 columns
+  // elements.  A thread visits ceil(nvec / 256) float4 vectors plus at most one head and one tail
+  // element, so rows of up to 250 * 256 = 64000 columns are safe (63 vectors + 2 = 254 elements);
+  // wider rows take the split launch, which bounds its segments the same way.
   const bool bytec = plan->max_nv > 64;
   static const char *env_b = getenv("DALI_RANK_FUSED_BYTE");
-  if (bytec && (G > 255ll * 256 || (env_b && atoi(env_b) == 0))) return DALI_OK;
+  if (bytec && (G > 250ll * 256 || (env_b && atoi(env_b) == 0))) return DALI_OK;
   DALI_CUDA_OK(ctx, cudaMemsetAsync(cmc_cnt, 0, sizeof(int32_t) * (max_rank + 1), ctx->stream));
   FusedOut fo{ranks_sorted, ap, first_rank, cmc_cnt, max_rank};
   KTimer t(ctx, DALI_K_RANK_COUNT);

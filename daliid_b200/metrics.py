@@ -48,12 +48,19 @@ __all__ = [
 DEFAULT_PRECISION = "auto"  # fp32-class result on the tensor pipe, see _precision()
 
 
-def _precision(precision, normalize):
-    """"auto" = the fastest fp32-class tensor-core arithmetic the operands allow: the fp16 hi/lo
-    split (f16x3) for unit rows -- the reference's live cosine path -- and TF32 + bf16
-    corrections (tf32c) for un-normalised features."""
+F16X3_MAX_D = 4096  # above it the accumulator-truncation bound of f16x3 exceeds 1e-5
+
+
+def _precision(precision, normalize, D=None):
+    """"auto" = the fastest arithmetic that keeps distances within 1e-5 of the reference's fp32
+    expression: the fp16 hi/lo split (f16x3) for unit rows of up to 4096 elements -- the reference's
+    live cosine path at every feature size it has (512 .. 3840) -- the exact FP32 pipe for longer
+    unit rows, and TF32 + bf16 corrections (tf32c) for un-normalised features."""
     if precision == "auto":
-        precision = "f16x3" if normalize else "tf32c"
+        if normalize:
+            precision = "f16x3" if (D is None or D <= F16X3_MAX_D) else "fp32"
+        else:
+            precision = "tf32c"
     return _enum(PRECISIONS, precision, "precision")
 
 
@@ -214,7 +221,7 @@ def compute_distance_matrix(input1, input2, metric="cosine", precision=DEFAULT_P
     ctx.attach_torch_stream()
     if Q and G:
         ctx.check(ctx.lib.dali_distmat_f32(ctx.h, c_vp(a.ptr), Q, c_vp(b.ptr), G, D, m,
-                                           _precision(precision, normalize),
+                                           _precision(precision, normalize, D),
                                            1 if normalize else 0, c_vp(optr), max(ld, 1)))
     return out
 
@@ -314,7 +321,7 @@ def topk_features(qf, gf, k=20, metric="cosine", precision=DEFAULT_PRECISION, no
     if Q:
         ctx.check(ctx.lib.dali_topk_features_f32(
             ctx.h, c_vp(a.ptr), Q, c_vp(b.ptr), b.shape[0], a.shape[1], m,
-            _precision(precision, normalize), 1 if normalize else 0, int(k),
+            _precision(precision, normalize, a.shape[1]), 1 if normalize else 0, int(k),
             1 if largest else 0, int(g_base), c_vp(vptr), c_vp(iptr)))
     return vals, idx
 
@@ -378,7 +385,7 @@ def evaluate_features(qf, gf, q_pids, g_pids, q_camids, g_camids, metric="cosine
         dist, dptr = _alloc_out((Q, G), dev)
     rc = ctx.lib.dali_eval_features_f32(
         ctx.h, a.ptr, Q, b.ptr, G, D, p_i32(qp), p_i32(gp), p_i32(qc), p_i32(gc), m,
-        _precision(precision, normalize), 1 if normalize else 0, int(max_rank),
+        _precision(precision, normalize, D), 1 if normalize else 0, int(max_rank),
         _enum(ACCUMS, accum, "accumulation mode"), np_ptr(cmc), ctypes.byref(mAP), np_ptr(ap), np_ptr(first),
         ctypes.byref(nvalid), dptr, G)
     ctx.check(rc)

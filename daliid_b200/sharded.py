@@ -358,7 +358,7 @@ def _evaluate_features_one_call(ops, qf, gf_slab, g0, q_pids, g_pids_all, q_cami
         matches = ctypes.c_int64(0)
         rc = ctx.lib.dali_eval_features_sharded_f32(
             ctx.h, px.h, c_vp(a.ptr), Q, c_vp(b.ptr), Gs, D, int(g0), G, p_i32(qp), p_i32(gp), p_i32(qc),
-            p_i32(gc), metrics._enum(metrics.METRICS, metric, "metric"), metrics._precision(precision, normalize),
+            p_i32(gc), metrics._enum(metrics.METRICS, metric, "metric"), metrics._precision(precision, normalize, D),
             1 if normalize else 0, int(max_rank), ACCUMS[accum], cmc.ctypes.data_as(_lib.c_f32p),
             ctypes.byref(mAP), ap.ctypes.data_as(_lib.c_f64p), first.ctypes.data_as(_lib.c_i32p),
             ctypes.byref(nvalid), ctypes.byref(matches))

@@ -51,18 +51,21 @@ class validateModels:
         queries_fvs = self.feature_extractor(queries, self.img_height, self.img_width, model, 500, self.gpu_index)
         gallery_fvs = self.feature_extractor(gallery, self.img_height, self.img_width, model, 500, self.gpu_index)
 
-        if getattr(self, "rerank", False):
-            # the reference's commented-out hook, live here (validateModels.py:49-53): torchreid's
-            # "euclidean" is the squared distance; features are L2-normalised first (41-42)
+        # `rerank` (setParameters) is IGNORED, exactly like upstream: the reference keeps its
+        # re-ranking block commented out (validateModels.py:49-53), so the same setParameters call
+        # must give the same cmc / mAP here.  The hook is available as a separate opt-in,
+        # `enable_rerank = True`, which no reference caller sets.
+        if getattr(self, "enable_rerank", False):
             print('Applying person re-ranking ...')
+            # features are L2-normalised once (validateModels.py:41-42); the three matrices are then
+            # computed from the unit rows as they are (normalize=False: no second division).
+            # torchreid's "euclidean" is the squared distance.
             qn = metrics.normalize(queries_fvs)
             gn = metrics.normalize(gallery_fvs)
-            distmat = metrics.compute_distance_matrix(qn, gn, "cosine", precision=self.precision,
-                                                      normalize=True)
-            distmat_qq = metrics.compute_distance_matrix(qn, qn, "sqeuclidean", precision=self.precision,
-                                                         normalize=True)
-            distmat_gg = metrics.compute_distance_matrix(gn, gn, "sqeuclidean", precision=self.precision,
-                                                         normalize=True)
+            prec = "tf32c" if self.precision in ("auto", "f16x3", "f16") else self.precision
+            distmat = metrics.compute_distance_matrix(qn, gn, "cosine", precision=prec, normalize=False)
+            distmat_qq = metrics.compute_distance_matrix(qn, qn, "sqeuclidean", precision=prec, normalize=False)
+            distmat_gg = metrics.compute_distance_matrix(gn, gn, "sqeuclidean", precision=prec, normalize=False)
             distmat = metrics.re_ranking(distmat, distmat_qq, distmat_gg)
             del queries_fvs, gallery_fvs, distmat_qq, distmat_gg
             cmc, mAP = self.calculateMetrics(distmat, queries, gallery)

@@ -46,6 +46,8 @@ extern "C" {
 #define DALI_ERR_UNSUPPORTED (-4)
 #define DALI_ERR_NOMEM (-5)
 #define DALI_ERR_PEER_CAPACITY (-6) /* peer block smaller than the number of matches: re-create it */
+#define DALI_ERR_PEER_TIMEOUT (-7)  /* a peer exchange gave up waiting for another rank               */
+#define DALI_ERR_FUSED_FALLBACK (-8) /* internal: the fused path declined, the caller takes the matrix path */
 
 /* ---- enums --------------------------------------------------------------- */
 /* distance metric (a2 / a2') */
@@ -105,7 +107,9 @@ int dali_ctx_h2d_streams(const dali_ctx *ctx);
 #define DALI_K_RANK_GATHER 6
 #define DALI_K_RERANK 7
 #define DALI_K_MRFUSE 8
-#define DALI_K_COUNT_ 9
+#define DALI_K_PEER_EXCHANGE 9 /* includes the wait for the slowest rank */
+#define DALI_K_H2D 10          /* host -> device copies of operands (copy streams)  */
+#define DALI_K_COUNT_ 11
 int dali_ctx_timing_enable(dali_ctx *ctx, int on);
 int dali_ctx_timing_reset(dali_ctx *ctx);
 int dali_ctx_timing_read(dali_ctx *ctx, int which, int *launches, float *total_ms);
@@ -290,6 +294,10 @@ void dali_peer_destroy(dali_peer *peer);
 int64_t dali_peer_capacity(const dali_peer *peer);
 void *dali_peer_buffer(dali_peer *peer, int which);
 int dali_peer_allreduce_i32(dali_ctx *ctx, dali_peer *peer, int which, int32_t *out, int64_t n);
+/* DALI_OK, or DALI_ERR_PEER_TIMEOUT when an exchange since dali_peer_create gave up waiting for
+ * another rank (limit: DALI_PEER_TIMEOUT_MS, default 20000).  The kernel does not trap: the
+ * context stays usable, but results computed from that exchange are meaningless.  Synchronises. */
+int dali_peer_status(dali_peer *peer);
 /* The whole sharded evaluation of one rank in one call: slab contraction, plan, gather, exchange,
  * count, exchange, finalize (the sequence daliid_b200/sharded.py otherwise drives call by call).
  * q [Q,D] and g_slab [Gs,D]: host or device; g0 = first gallery index of the slab; labels of the

@@ -253,3 +253,61 @@ def test_property_random_cases_hypothesis():
             assert np.array_equal(ap, e_ap, equal_nan=True)
 
     run()
+
+
+def test_byte_counter_rows_at_the_boundary():
+    """the single-launch byte-counter path (more than 64 positives per query) must not
+    wrap its 8-bit private counters.  G in (64512, 65280] gives threads 0..191 256 elements; with a
+    worst-ranked positive nearly the whole row falls into one bucket.  Such rows now take the split
+    launch; G = 64000 is the widest single-launch row.  Both are checked against the oracle."""
+    from daliid_b200 import metrics
+    rng = np.random.default_rng(7)
+    for G in (64000, 65280):
+        Q, npos = 3, 90
+        d = rng.random((Q, G), dtype=np.float32) * 0.5          # negatives: 0 .. 0.5
+        g_pid = np.full(G, 1000, dtype=np.int32)
+        g_cam = np.ones(G, dtype=np.int32)
+        q_pid = np.arange(Q, dtype=np.int32)
+        q_cam = np.zeros(Q, dtype=np.int32)
+        for q in range(Q):
+            cols = rng.choice(G, npos, replace=False)
+            g_pid[cols] = q                                     # positives of query q ...
+            d[q, cols] = 0.9 + 0.001 * rng.random(npos, dtype=np.float32)   # ... ranked last
+        e = ro.eval_market1501_cy_f32(d, q_pid, g_pid, q_cam, g_cam, 50, return_details=True)
+        cmc, mAP, ap, first, _ = metrics.evaluate_rank_detailed(torch.from_numpy(d).cuda(), q_pid, g_pid,
+                                                                 q_cam, g_cam)
+        assert np.array_equal(first, e[3]) and mAP == e[1] and np.array_equal(cmc, e[0]), G
+
+
+def test_two_streams_share_the_context_safely():
+    """the context's workspaces are ordered on the stream of the previous call.  A second
+    call issued under another torch stream must wait for it (dali_ctx_set_stream hands over with an
+    event): the first matrix stays intact although the second call reuses the operand planes."""
+    from daliid_b200 import metrics
+    g = torch.Generator().manual_seed(11)
+    q = torch.randn(3000, 1024, generator=g).cuda()
+    g1 = torch.randn(9000, 1024, generator=g).cuda()
+    g2 = torch.randn(9000, 1024, generator=g).cuda()
+    ref1 = metrics.compute_distance_matrix(q, g1, "cosine").clone()
+    ref2 = metrics.compute_distance_matrix(q, g2, "cosine").clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(5):
+        with torch.cuda.stream(s1):
+            d1 = metrics.compute_distance_matrix(q, g1, "cosine")
+        with torch.cuda.stream(s2):
+            d2 = metrics.compute_distance_matrix(q, g2, "cosine")
+        torch.cuda.synchronize()
+        assert torch.equal(d1, ref1) and torch.equal(d2, ref2)
+
+
+def test_entry_points_restore_the_callers_device():
+    """an entry point switches to its context's device and puts the caller's back."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from daliid_b200 import metrics
+    torch.cuda.set_device(0)
+    x = torch.randn(64, 128, device="cuda:1")
+    metrics.compute_distance_matrix(x, x, "cosine")
+    assert torch.cuda.current_device() == 0
+    assert torch.empty(1, device="cuda").device.index == 0
