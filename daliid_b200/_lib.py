@@ -65,6 +65,8 @@ _SIGNATURES = {
     "dali_ctx_fallback_count": (i64, [c_vp]),
     "dali_ctx_plan_cache_enable": (ci, [c_vp, ci]),
     "dali_ctx_plan_cache_hits": (i64, [c_vp]),
+    "dali_ctx_fused_count_enable": (ci, [c_vp, ci]),
+    "dali_ctx_fused_count_calls": (i64, [c_vp]),
     "dali_normalize_f32": (ci, [c_vp, c_vp, i64, i64, i64, c_vp, i64, c_vp]),
     "dali_distmat_f32": (ci, [c_vp, c_vp, i64, c_vp, i64, i64, ci, ci, ci, c_vp, i64]),
     "dali_peer_create": (ci, [c_vp, ci, ci, i64, ctypes.POINTER(c_vp)]),
@@ -191,14 +193,20 @@ class Context:
     def launch_count(self):
         return int(self.lib.dali_ctx_launch_count(self.h))
 
-    def fallback_count(self):
-        return int(self.lib.dali_ctx_fallback_count(self.h))
-
     def plan_cache_enable(self, on=True):
         self.check(self.lib.dali_ctx_plan_cache_enable(self.h, 1 if on else 0))
 
     def plan_cache_hits(self):
         return int(self.lib.dali_ctx_plan_cache_hits(self.h))
+
+    def fused_count_enable(self, on=True):
+        self.check(self.lib.dali_ctx_fused_count_enable(self.h, 1 if on else 0))
+
+    def fused_count_calls(self):
+        return int(self.lib.dali_ctx_fused_count_calls(self.h))
+
+    def fallback_count(self):
+        return int(self.lib.dali_ctx_fallback_count(self.h))
 
 
 _tls = threading.local()

@@ -398,7 +398,8 @@ static int alloc_operand(dali_ctx *ctx, int ws_planes, int ws_p16, int ws_sq, in
 
 // Prepare rows [r0, r1) of an operand (r1 - r0 may include zero padding rows) from device rows xd.
 static int prep_rows(dali_ctx *ctx, const Prepared &o, const float *xd, int64_t ldx, int64_t D,
-                     int64_t r0, int64_t n_valid, int64_t r1, int precision, int normalize) {
+                     int64_t r0, int64_t n_valid, int64_t r1, int precision, int normalize,
+                     const int32_t *perm = nullptr) {
   char *p16 = static_cast<char *>(o.planes16);
   const int64_t off = r0 * o.Dp;
   return launch_prep(ctx, xd, n_valid, D, ldx, o.planes ? o.planes + off : nullptr,
@@ -407,19 +408,19 @@ static int prep_rows(dali_ctx *ctx, const Prepared &o, const float *xd, int64_t 
                      precision == DALI_PREC_FP32 ? 0 : precision == DALI_PREC_F16X3 ? 3 : precision == DALI_PREC_F16 ? 2 : 1,
                      nullptr,
                      o.sq ? o.sq + r0 : nullptr, p16 ? p16 + 2 * off : nullptr,
-                     p16 ? p16 + 2 * (o.rows_pad * o.Dp + off) : nullptr);
+                     p16 ? p16 + 2 * (o.rows_pad * o.Dp + off) : nullptr, perm);
 }
 
 static int prepare_operand(dali_ctx *ctx, int ws_in, int ws_planes, int ws_p16, int ws_sq, const float *x,
                            int64_t n, int64_t D, int metric, int precision, int normalize,
-                           Prepared *out) {
+                           Prepared *out, const int32_t *perm = nullptr) {
   const float *xd = nullptr;
   int64_t ldx = D;
   int rc = stage_in(ctx, ws_in, x, n, D, D, &xd, &ldx);
   if (rc) return rc;
   rc = alloc_operand(ctx, ws_planes, ws_p16, ws_sq, n, D, metric, precision, out);
   if (rc) return rc;
-  return prep_rows(ctx, *out, xd, ldx, D, 0, n, out->rows_pad, precision, normalize);
+  return prep_rows(ctx, *out, xd, ldx, D, 0, n, out->rows_pad, precision, normalize, perm);
 }
 
 // out[:, 0:Gs] = distances of all Q queries to gallery rows [g_row0, g_row0 + Gs)
@@ -481,6 +482,175 @@ static int rank_from_device(dali_ctx *ctx, const dali_rank_plan *plan, const flo
   return dali_rank_finalize(ctx, plan, static_cast<const uint32_t *>(keys),
                             static_cast<const int32_t *>(counts), max_rank, accum_mode, cmc, mAP,
                             ap_opt, first_rank_opt, num_valid_opt);
+}
+
+
+// ---------------------------------------------------------------------------
+// Fused distance + positive-rank counting (distmat_umma2.cu kBand / kCount): the Q x G matrix is
+// never written and never read back.
+// ---------------------------------------------------------------------------
+// Host part, once per plan: queries sorted by where their identity sits in the identity-sorted
+// gallery (`order`), so that the matches of 256 consecutive sorted queries fall into a contiguous
+// range of column tiles -- the band of that row tile; then the two tile lists.
+static int fused_plan_setup(dali_ctx *ctx, dali_rank_plan *plan) {
+  if (plan->fz_ready) return DALI_OK;
+  const int64_t Q = plan->Q, G = plan->G;
+  std::vector<int32_t> qorder(Q);
+  std::iota(qorder.begin(), qorder.end(), 0);
+  // key: start of the identity segment; queries without a match (empty segment) last
+  std::vector<int64_t> key(Q);
+  for (int64_t q = 0; q < Q; ++q)
+    key[q] = plan->h_off[q + 1] > plan->h_off[q] ? plan->h_lo[q] : G;
+  std::stable_sort(qorder.begin(), qorder.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+  const int64_t num_m = (Q + 255) / 256, num_n = (G + 255) / 256;
+  if (num_m > 65535 || num_n > 65535) return set_err(ctx, DALI_ERR_FUSED_FALLBACK, "too many tiles for the fused path");
+  std::vector<int32_t> n_lo(num_m, 1), n_hi(num_m, 0);  // empty band: lo > hi
+  std::vector<uint32_t> band, mainl;
+  for (int64_t m = 0; m < num_m; ++m) {
+    int64_t c_lo = INT64_MAX, c_hi = -1;
+    for (int64_t r = m * 256; r < std::min(Q, m * 256 + 256); ++r) {
+      const int32_t q = qorder[r];
+      const int64_t mq = plan->h_off[q + 1] - plan->h_off[q];
+      if (mq == 0) continue;
+      c_lo = std::min(c_lo, plan->h_lo[q]);
+      c_hi = std::max(c_hi, plan->h_lo[q] + mq - 1);
+    }
+    if (c_hi >= 0) {
+      n_lo[m] = static_cast<int32_t>(c_lo / 256);
+      n_hi[m] = static_cast<int32_t>(c_hi / 256);
+      for (int32_t n = n_lo[m]; n <= n_hi[m]; ++n) band.push_back(static_cast<uint32_t>(m << 16) | static_cast<uint32_t>(n));
+    }
+  }
+  // every other tile, query tile fastest (the 74 tiles in flight share a few gallery tiles)
+  mainl.reserve(static_cast<size_t>(num_m * num_n));
+  for (int64_t n = 0; n < num_n; ++n)
+    for (int64_t m = 0; m < num_m; ++m)
+      if (n < n_lo[m] || n > n_hi[m]) mainl.push_back(static_cast<uint32_t>(m << 16) | static_cast<uint32_t>(n));
+  // a band much wider than the matches (labels that do not cluster) defeats the purpose
+  if (band.size() > static_cast<size_t>(num_m * num_n) / 4 + 8)
+    return set_err(ctx, DALI_ERR_FUSED_FALLBACK, "band too wide for the fused path");
+  const size_t b_q = sizeof(int32_t) * std::max<int64_t>(Q, 1);
+  const size_t b_band = sizeof(uint32_t) * std::max<size_t>(band.size(), 1);
+  const size_t b_main = sizeof(uint32_t) * std::max<size_t>(mainl.size(), 1);
+  std::vector<char> host(b_q + b_band + b_main);
+  std::memcpy(host.data(), qorder.data(), sizeof(int32_t) * Q);
+  std::memcpy(host.data() + b_q, band.data(), sizeof(uint32_t) * band.size());
+  std::memcpy(host.data() + b_q + b_band, mainl.data(), sizeof(uint32_t) * mainl.size());
+  DALI_CUDA_OK(ctx, cudaMallocAsync(&plan->d_fz, host.size(), ctx->stream));
+  // pageable source: the copy is staged by the runtime before the call returns
+  DALI_CUDA_OK(ctx, cudaMemcpyAsync(plan->d_fz, host.data(), host.size(), cudaMemcpyHostToDevice, ctx->stream));
+  char *db = static_cast<char *>(plan->d_fz);
+  plan->d_qorder = reinterpret_cast<int32_t *>(db);
+  plan->d_band = reinterpret_cast<uint32_t *>(db + b_q);
+  plan->d_main = reinterpret_cast<uint32_t *>(db + b_q + b_band);
+  plan->n_band = static_cast<int>(band.size());
+  plan->n_main = static_cast<int>(mainl.size());
+  plan->fz_ready = true;
+  return DALI_OK;
+}
+
+// Most same-identity gallery items a query may have for the fused path.  The counting epilogue
+// holds 32 thresholds (valid positives) per pass and re-reads the accumulator for every further 32;
+// a pass of 32 thresholds over a 128 x 256 tile costs ~17 us of ALU-pipe time, the MMAs of a tile
+// 14 us at D = 768 and 37 us at D = 2048 -- beyond two (four) passes the matrix path is faster.
+static int fused_max_matches(int64_t Dp) {
+  static const char *env = getenv("DALI_FUSED_MAX_MATCHES");
+  if (env) return atoi(env);
+  return Dp >= 1536 ? 128 : 64;
+}
+
+// keys [M] and counts [M] (device) of one gallery slab through the fused path.  q, g: device or
+// (small) host features.  g0: global gallery id of slab row 0.  The plan must describe exactly the
+// slab's labels when g0 == 0 and Gs == plan->G (single GPU).
+static int fused_keys_counts(dali_ctx *ctx, dali_rank_plan *plan, const float *q, int64_t Q, const float *g,
+                             int64_t G, int64_t D, int metric, int precision, int normalize, uint32_t *keys,
+                             int32_t *counts, bool *flag_pending) {
+  int rc = fused_plan_setup(ctx, plan);
+  if (rc) return rc;
+  Prepared a, b;
+  rc = prepare_operand(ctx, WS_QIN, WS_QN, WS_QN16, WS_QNORM, q, Q, D, metric, precision, normalize, &a,
+                       plan->d_qorder);
+  if (rc) return rc;
+  rc = prepare_operand(ctx, WS_GIN, WS_GN, WS_GN16, WS_GNORM, g, G, D, metric, precision, normalize, &b,
+                       plan->d_order);
+  if (rc) return rc;
+  void *scratch = nullptr, *flag = nullptr;
+  rc = ws_ensure(ctx, WS_DIST, sizeof(float) * 256 * 256 * std::max(plan->n_band, 1), &scratch);
+  if (rc) return rc;
+  rc = ws_ensure(ctx, WS_FLAG, 256, &flag);
+  if (rc) return rc;
+  DALI_CUDA_OK(ctx, cudaMemsetAsync(flag, 0, 4 * sizeof(int32_t), ctx->stream));
+  DALI_CUDA_OK(ctx, cudaMemsetAsync(keys, 0, sizeof(uint32_t) * plan->M, ctx->stream));
+  DALI_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, sizeof(int32_t) * plan->M, ctx->stream));
+  FusedArgs fa;
+  fa.scratch = static_cast<float *>(scratch);
+  fa.qorder = plan->d_qorder;
+  fa.off = plan->d_off;
+  fa.lo = plan->d_lo;
+  fa.nv = plan->d_nv;
+  fa.gid = plan->d_gid;
+  fa.slot_of_seg = plan->d_slot;
+  fa.order = plan->d_order;
+  fa.keys = keys;
+  fa.counts = counts;
+  fa.flag = static_cast<int32_t *>(flag);
+  fa.gid_base = 0;
+  fa.tiles = plan->d_band;
+  fa.num_list = plan->n_band;
+  const float *gsq = b.sq;
+  rc = launch_distmat_band_umma(ctx, a.planes, b.planes, a.planes16, b.planes16, Q, G, a.Dp, a.rows_pad,
+                                b.rows_pad, 0, precision, metric, a.sq, gsq, fa);
+  if (rc) return rc;
+  // thresholds of every query sorted ascending (the counting epilogue searches them)
+  void *sthr = nullptr, *sslot = nullptr, *hist = nullptr;
+  const size_t mb = sizeof(int32_t) * std::max<int64_t>(plan->M, 1);
+  if ((rc = ws_ensure(ctx, WS_FZ_THR, mb, &sthr)) || (rc = ws_ensure(ctx, WS_FZ_SLOT, mb, &sslot)) ||
+      (rc = ws_ensure(ctx, WS_FZ_HIST, mb, &hist)))
+    return rc;
+  DALI_CUDA_OK(ctx, cudaMemsetAsync(hist, 0, mb, ctx->stream));
+  rc = launch_fused_sort_thresholds(ctx, plan, keys, static_cast<float *>(sthr), static_cast<int32_t *>(sslot),
+                                    static_cast<int32_t *>(flag));
+  if (rc) return rc;
+  fa.sorted_thr = static_cast<const float *>(sthr);
+  fa.sorted_slot = static_cast<const int32_t *>(sslot);
+  fa.hist = static_cast<int32_t *>(hist);
+  fa.tiles = plan->d_main;
+  fa.num_list = plan->n_main;
+  fa.band = plan->d_band;
+  fa.num_band = plan->n_band;
+  rc = launch_distmat_count_umma(ctx, a.planes, b.planes, a.planes16, b.planes16, Q, G, a.Dp, a.rows_pad,
+                                 b.rows_pad, 0, precision, metric, a.sq, gsq, fa);
+  if (rc) return rc;
+  rc = launch_fused_prefix(ctx, plan, static_cast<const int32_t *>(hist), static_cast<const int32_t *>(sslot),
+                           counts, 31);
+  if (rc) return rc;
+  {
+    static const char *env_dbg = getenv("DALI_FUSED_DBG");
+    if (env_dbg && (atoi(env_dbg) & 64)) {
+      int32_t h[4];
+      cudaMemcpyAsync(h, flag, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+      fprintf(stderr, "[dali fused dbg] flag %d tie groups %d\n", h[0], h[1]);
+    }
+  }
+  if (!ctx->pinned_flag) DALI_CUDA_OK(ctx, cudaMallocHost(reinterpret_cast<void **>(&ctx->pinned_flag), 64));
+  *ctx->pinned_flag = 0;
+  DALI_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned_flag, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  *flag_pending = true;
+  return DALI_OK;
+}
+
+static bool fused_eligible(dali_ctx *ctx, const dali_rank_plan *plan, const float *q, const float *g, int64_t Q,
+                           int64_t G, int64_t D, int precision, const float *distmat_opt) {
+  static const char *env = getenv("DALI_FUSED_COUNT");  // 1 / 0 override the context's switch
+  if (env ? atoi(env) == 0 : !ctx->fused_count) return false;
+  if (distmat_opt || !fused_count_supports(precision) || Q == 0 || G == 0 || plan->M == 0) return false;
+  if (plan->max_m > fused_max_matches(round_up(D, 32))) return false;
+  // a big host gallery is better served by the chunked copy / contraction pipeline (the copy
+  // bounds that path; the matrix path overlaps everything but its last chunk with it)
+  if (!is_device_ptr(g) && static_cast<int64_t>(sizeof(float)) * G * D >= (24ll << 20)) return false;
+  (void)ctx; (void)q;
+  return true;
 }
 
 }  // namespace dali
@@ -568,6 +738,7 @@ void dali_ctx_destroy(dali_ctx *ctx) {
   for (auto &b : ctx->ws)
     if (b.p) cudaFree(b.p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->pinned_flag) cudaFreeHost(ctx->pinned_flag);
   if (ctx->plan_stage) cudaFreeHost(ctx->plan_stage);
   if (ctx->plan_stage_done) cudaEventDestroy(ctx->plan_stage_done);
   if (ctx->h2d_ev0) cudaEventDestroy(ctx->h2d_ev0);
@@ -631,6 +802,12 @@ int dali_ctx_timing_read(dali_ctx *ctx, int which, int *launches, float *total_m
 int64_t dali_ctx_launch_count(dali_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int64_t dali_ctx_fallback_count(dali_ctx *ctx) { return ctx ? ctx->fallbacks : 0; }
 int64_t dali_ctx_plan_cache_hits(dali_ctx *ctx) { return ctx ? ctx->plan_cache_hits : 0; }
+int dali_ctx_fused_count_enable(dali_ctx *ctx, int on) {
+  if (!ctx) return DALI_ERR_INVALID;
+  ctx->fused_count = on != 0;
+  return DALI_OK;
+}
+int64_t dali_ctx_fused_count_calls(dali_ctx *ctx) { return ctx ? ctx->fused_calls : 0; }
 int dali_ctx_plan_cache_enable(dali_ctx *ctx, int on) {
   if (!ctx) return DALI_ERR_INVALID;
   ctx->plan_cache = on != 0;
@@ -1003,9 +1180,10 @@ int dali_rank_plan_create(dali_ctx *ctx, const int32_t *q_pid, const int32_t *g_
   p->M = M;
   p->max_nv = p->max_m;
   std::memcpy(p->h_off.data(), s_off, b_off);
+  p->h_lo.assign(s_lo, s_lo + Q);
   // ---- device image: upload the CSR, expand the per-query match lists on the GPU ---------
   const size_t b_gid = sizeof(int32_t) * std::max<int64_t>(M, 1);
-  const size_t total = b_off + b_lo + 3 * b_q32 + b_gid + 2 * b_g32 + 64;
+  const size_t total = b_off + b_lo + 3 * b_q32 + 2 * b_gid + 2 * b_g32 + 64;
   if (!ctx->pool_ready) {  // keep freed blocks in the default pool: allocation becomes ~free
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
@@ -1024,6 +1202,7 @@ int dali_rank_plan_create(dali_ctx *ctx, const int32_t *q_pid, const int32_t *g_
   p->d_nv = reinterpret_cast<int32_t *>(db + stage_bytes);
   p->d_njunk = reinterpret_cast<int32_t *>(db + stage_bytes + b_q32);
   p->d_gid = reinterpret_cast<int32_t *>(db + stage_bytes + 2 * b_q32);
+  p->d_slot = reinterpret_cast<int32_t *>(db + stage_bytes + 2 * b_q32 + b_gid);
   if ((e = cudaMemcpyAsync(p->d_block, hs, stage_bytes, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
     return fail(e, "upload");
   if ((e = cudaEventRecord(ctx->plan_stage_done, ctx->stream)) != cudaSuccess) return fail(e, "event record");
@@ -1057,6 +1236,7 @@ void dali_rank_plan_destroy(dali_rank_plan *plan) {
   if (!plan) return;
   if (--plan->refs > 0) return;
   if (plan->d_block) cudaFreeAsync(plan->d_block, plan->ctx->stream);
+  if (plan->d_fz) cudaFreeAsync(plan->d_fz, plan->ctx->stream);
   if (plan->ready) cudaEventDestroy(plan->ready);
   delete plan;
 }
@@ -1163,6 +1343,44 @@ int dali_eval_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float
   if (rc) return rc;
   if (metric == DALI_METRIC_DOT)
     return set_err(ctx, DALI_ERR_INVALID, "eval_features ranks distances; DOT is a similarity");
+  // Fused path (device-resident features, tensor-core arithmetic, no matrix requested, few matches
+  // per query): band tiles -> keys, every tile counted in the contraction's epilogue, finalize.
+  // The plan comes first here (the operands are written identity-sorted); with the plan cache
+  // that is a memcmp.
+  struct PlanHold {  // releases the call's reference on every way out
+    dali_rank_plan *p = nullptr;
+    ~PlanHold() { if (p) dali_rank_plan_destroy(p); }
+  } hold;
+  dali_rank_plan *&fplan = hold.p;  // built early for the fused path; reused by the matrix path
+  if (accum_mode == DALI_ACCUM_CY_F32 || accum_mode == DALI_ACCUM_PY_F64) {
+    bool try_fused = !distmat_opt && fused_count_supports(precision) && Q && G;
+    if (try_fused) {
+      rc = dali_rank_plan_create(ctx, q_pid, g_pid, q_cam, g_cam, Q, G, &fplan);
+      if (rc) return rc;
+      try_fused = fused_eligible(ctx, fplan, q, g, Q, G, D, precision, distmat_opt);
+    }
+    if (try_fused) {
+      void *keys = nullptr, *counts = nullptr;
+      bool pending = false;
+      rc = ws_ensure(ctx, WS_KEYS, sizeof(uint32_t) * std::max<int64_t>(fplan->M, 1), &keys);
+      if (!rc) rc = ws_ensure(ctx, WS_COUNTS, sizeof(int32_t) * std::max<int64_t>(fplan->M, 1), &counts);
+      if (!rc)
+        rc = fused_keys_counts(ctx, fplan, q, Q, g, G, D, metric, precision, normalize,
+                               static_cast<uint32_t *>(keys), static_cast<int32_t *>(counts), &pending);
+      if (!rc) {
+        rc = dali_rank_finalize(ctx, fplan, static_cast<const uint32_t *>(keys), static_cast<const int32_t *>(counts),
+                                max_rank, accum_mode, cmc, mAP, ap_opt, first_rank_opt, num_valid_opt);
+        // finalize synchronised the stream: the flag is on the host now
+        if ((rc == DALI_OK || rc == DALI_ERR_NO_VALID_QUERY) && pending && *ctx->pinned_flag) rc = DALI_ERR_FUSED_FALLBACK;
+      }
+      if (rc != DALI_ERR_FUSED_FALLBACK) {
+        ctx->fused_calls++;
+        return rc;
+      }
+      ctx->fallbacks++;  // not finite thresholds / labels that do not cluster: the matrix path below
+      rc = DALI_OK;
+    }
+  }
   const bool user_dev = distmat_opt && is_device_ptr(distmat_opt);
   float *dd = distmat_opt;
   int64_t ldd = ld_opt;
@@ -1183,13 +1401,14 @@ int dali_eval_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float
                                         sizeof(float) * G, Q, cudaMemcpyDeviceToHost, ctx->stream));
   // 2. ... so the host builds the rank plan (gallery CSR by identity) while the GPU works
   const double t_launched = since();
-  dali_rank_plan *plan = nullptr;
-  rc = dali_rank_plan_create(ctx, q_pid, g_pid, q_cam, g_cam, Q, G, &plan);
-  if (rc) return rc;
+  if (!fplan) {
+    rc = dali_rank_plan_create(ctx, q_pid, g_pid, q_cam, g_cam, Q, G, &fplan);
+    if (rc) return rc;
+  }
+  dali_rank_plan *plan = fplan;
   const double t_plan = since();
   rc = rank_from_device(ctx, plan, dd, ldd, max_rank, accum_mode, cmc, mAP, ap_opt,
                         first_rank_opt, num_valid_opt);
-  dali_rank_plan_destroy(plan);
   if (trace)
     fprintf(stderr, "[dali trace] eval_features host: contraction enqueued %.1f us, plan ready %.1f us, done %.1f us\n",
             t_launched, t_plan, since());

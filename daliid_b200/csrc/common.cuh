@@ -87,8 +87,42 @@ enum WsSlot {
   WS_MR_T,      // meta-recognition fusion: cleaned transpose [G,Q]
   WS_MR_MISC,   // kill / low lists, Weibull parameters
   WS_SORT,      // full row ordering: composite keys, payload, radix scratch
+  WS_FZ_THR,    // fused counting: per-query sorted thresholds [M] fp32
+  WS_FZ_SLOT,   // their match-list slots [M] int32
+  WS_FZ_HIST,   // bucket histogram [M] int32
   WS_COUNT_
 };
+
+// ---- fused distance + positive-rank counting (distmat_umma2.cu: kBand / kCount) ----------------
+// Operands of the fused path are written IDENTITY-SORTED by the preparation kernels (rows of the
+// query planes in `qorder`, rows of the gallery planes in the plan's `order`), so that the matches
+// of a 256-query tile sit in a handful of adjacent column tiles (the band).
+struct FusedArgs {
+  const uint32_t *tiles = nullptr;  // explicit tile list of this launch, (m << 16) | n
+  int num_list = 0;
+  const uint32_t *band = nullptr;   // kCount: the band tiles, whose distances wait in `scratch`
+  int num_band = 0;
+  float *scratch = nullptr;         // [num_band][256][256] fp32
+  const int32_t *qorder = nullptr;  // [Q] query index of sorted row r
+  const int64_t *off = nullptr;     // [Q + 1] match-list offsets (plan)
+  const int64_t *lo = nullptr;      // [Q] first sorted-gallery column of the query's identity
+  const int32_t *nv = nullptr;      // [Q] valid positives (they come first in the match list)
+  const int32_t *gid = nullptr;     // [M] global gallery id of a match
+  const int32_t *slot_of_seg = nullptr;  // [M] match-list slot of the i-th column of the segment
+  const int32_t *order = nullptr;   // [G] local gallery row of sorted column j
+  uint32_t *keys = nullptr;         // [M] order keys of the matches' distances (kBand writes them)
+  const float *sorted_thr = nullptr;   // [M] per query: distances of its valid positives, ascending
+  const int32_t *sorted_slot = nullptr;  // [M] match-list slot of the k-th smallest
+  int32_t *hist = nullptr;          // [M] per query and sorted position k: columns with exactly k
+                                    // thresholds (of the same pass of 31) <= them (red.add per tile)
+  int32_t *counts = nullptr;        // [M] match-list order: tie corrections (kCount), then the prefix
+                                    // sums of hist are added (launch_fused_prefix)
+  int32_t *flag = nullptr;          // set when a threshold is not finite: the caller redoes the
+                                    // evaluation through the materialised matrix
+  int32_t gid_base = 0;             // global gallery id of local row 0 (sharded slabs)
+  int dbg = 0;                      // DALI_FUSED_DBG (experiments): 1 skip the search, 2 skip the tile
+};
+
 
 }  // namespace dali
 
@@ -103,6 +137,7 @@ struct dali_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   dali::DevBuf ws[dali::WS_COUNT_];
+  int32_t *pinned_flag = nullptr;  // fused counting: "a threshold was not finite" read back here
   void *pinned = nullptr;  // small pinned scratch for results
   size_t pinned_cap = 0;
   void *plan_stage = nullptr;  // pinned staging of the rank plan (async upload)
@@ -137,6 +172,9 @@ struct dali_ctx {
   int64_t plan_cache_hits = 0;
   int64_t launches = 0;
   int64_t fallbacks = 0;  // fused calls that had to be redone through the materialised path
+  bool fused_count = false;  // evaluations may take the fused distance + counting path (opt-in:
+                             // measured slower than the matrix path at the Market shapes)
+  int64_t fused_calls = 0;   // evaluations that did
   // opt-in dynamic shared memory already granted per kernel on THIS device (the attribute is
   // per device, so it cannot be a process-wide static)
   std::unordered_map<const void *, size_t> func_smem;
@@ -166,6 +204,17 @@ struct dali_rank_plan {
   int32_t *d_gid = nullptr;   // [M] gallery id of each match (valid ascending, then junk)
   int32_t *d_order = nullptr;
   int32_t *d_gcam = nullptr;
+  int32_t *d_slot = nullptr;  // [M] match-list slot (relative to off[q]) of the i-th item of the query's
+                              // identity segment in `order` (written by the expansion kernel)
+  std::vector<int64_t> h_lo;  // [Q] host copy of lo
+  // fused distance + counting (built on first use, dali::fused_plan_setup): queries sorted by the
+  // position of their identity in `order`, the band tiles and all the other tiles
+  bool fz_ready = false;
+  void *d_fz = nullptr;
+  int32_t *d_qorder = nullptr;   // [Q]
+  uint32_t *d_band = nullptr;    // [n_band] (m << 16) | n
+  uint32_t *d_main = nullptr;    // [n_main]
+  int n_band = 0, n_main = 0;
 };
 
 namespace dali {
@@ -201,10 +250,11 @@ struct KTimer {
 
 // ---- kernel launchers (defined in the .cu files) ---------------------------
 // normalize.cu
+// perm (device, may be null): output row r is prepared from input row perm[r]
 int launch_prep(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx, float *plane0,
                 float *plane1, int64_t ldo, int64_t d_pad, int64_t rows_pad, int do_normalize,
                 int round_mode, float *norms, float *sq, void *hi16 = nullptr,
-                void *lo16 = nullptr);
+                void *lo16 = nullptr, const int32_t *perm = nullptr);
 float f16x3_hi_grid(int64_t d_pad);
 // distmat_simt.cu
 int launch_distmat_simt(dali_ctx *ctx, const float *qn, const float *gn, int64_t Q, int64_t G,
@@ -222,7 +272,20 @@ int launch_distmat_filter_umma(dali_ctx *ctx, const float *q32, const float *g32
                                int precision, int metric, const float *qsq, const float *gsq,
                                const float *thr, int32_t *cand_cnt, uint64_t *cand, int cap,
                                int largest, int direct, int32_t id_base);
+bool fused_count_supports(int precision);
+int launch_distmat_band_umma(dali_ctx *ctx, const float *q32, const float *g32, const void *q16,
+                             const void *g16, int64_t Q, int64_t G, int64_t Dp, int64_t q_rows_pad,
+                             int64_t g_rows_pad, int64_t g_row0, int precision, int metric,
+                             const float *qsq, const float *gsq, const FusedArgs &fa);
+int launch_distmat_count_umma(dali_ctx *ctx, const float *q32, const float *g32, const void *q16,
+                              const void *g16, int64_t Q, int64_t G, int64_t Dp, int64_t q_rows_pad,
+                              int64_t g_rows_pad, int64_t g_row0, int precision, int metric,
+                              const float *qsq, const float *gsq, const FusedArgs &fa);
 // rank.cu
+int launch_fused_sort_thresholds(dali_ctx *ctx, const dali_rank_plan *plan, const uint32_t *keys,
+                                 float *sorted_thr, int32_t *sorted_slot, int32_t *flag);
+int launch_fused_prefix(dali_ctx *ctx, const dali_rank_plan *plan, const int32_t *hist,
+                        const int32_t *sorted_slot, int32_t *counts, int pass);
 int launch_plan_expand(dali_ctx *ctx, const dali_rank_plan *plan);
 int launch_rank_gather(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist, int64_t ld,
                        int64_t g0, int64_t Gs, uint32_t *keys);

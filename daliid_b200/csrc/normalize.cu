@@ -59,6 +59,7 @@ struct PrepParams {
   float *sq;       // nullable: sum of squares of the OUTPUT row (fp32 values before tf32 rounding)
   __nv_bfloat16 *hi16;  // nullable: bf16 copy of plane0 (TF32C correction operand)
   __nv_bfloat16 *lo16;  // nullable: bf16 copy of the residual x - plane0
+  const int32_t *perm;  // nullable: output row r comes from input row perm[r]
 };
 
 __global__ void __launch_bounds__(kPrepThreads) prep_rows_kernel(PrepParams p) {
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_rows_kernel(PrepParams p) {
     }
     return;
   }
-  const float *xr = p.x + r * p.ldx;
+  const float *xr = p.x + (p.perm ? static_cast<int64_t>(__ldg(p.perm + r)) : r) * p.ldx;
   float nrm = 1.f;
   if (p.do_normalize || p.norms) {
     float acc = 0.f;
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_rows_vec_kernel(PrepParams 
     }
     return;
   }
-  const float4 *xr = reinterpret_cast<const float4 *>(p.x + r * p.ldx);
+  const float4 *xr = reinterpret_cast<const float4 *>(p.x + (p.perm ? static_cast<int64_t>(__ldg(p.perm + r)) : r) * p.ldx);
   const int nv = static_cast<int>(p.d >> 2);
   float4 cache[kVecCache];
   float acc = 0.f;
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_f16_kernel(PrepParams p) {
     }
     return;
   }
-  const float4 *xr = reinterpret_cast<const float4 *>(p.x + r * p.ldx);
+  const float4 *xr = reinterpret_cast<const float4 *>(p.x + (p.perm ? static_cast<int64_t>(__ldg(p.perm + r)) : r) * p.ldx);
   const int nv = static_cast<int>(p.d >> 2);
   float4 cache[NVEC];
   float acc = 0.f;
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_f16_warp_kernel(PrepParams 
     }
     return;
   }
-  const float4 *xr = reinterpret_cast<const float4 *>(p.x + r * p.ldx);
+  const float4 *xr = reinterpret_cast<const float4 *>(p.x + (p.perm ? static_cast<int64_t>(__ldg(p.perm + r)) : r) * p.ldx);
   const int nv = static_cast<int>(p.d >> 2);
   float4 cache[NV];
   float acc = 0.f;
@@ -353,7 +354,7 @@ float f16x3_hi_grid(int64_t) {
 
 int launch_prep(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx, float *plane0,
                 float *plane1, int64_t ldo, int64_t d_pad, int64_t rows_pad, int do_normalize,
-                int round_mode, float *norms, float *sq, void *hi16, void *lo16) {
+                int round_mode, float *norms, float *sq, void *hi16, void *lo16, const int32_t *perm) {
   if (rows_pad == 0) return DALI_OK;
   // round_mode 3 = round_mode 2 with the fixed-point hi plane of the three-pass fp16 arithmetic
   // (the single-pass F16 mode keeps plain fp16 rounding: it has no residual to absorb a coarser hi)
@@ -361,7 +362,7 @@ int launch_prep(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx
   if (round_mode == 3) round_mode = 2;
   PrepParams p{x, n, d, ldx, plane0, plane1, ldo, d_pad, rows_pad, do_normalize, round_mode,
                hgrid > 0.f ? 1.0f / hgrid : 0.f, hgrid, norms, sq,
-               static_cast<__nv_bfloat16 *>(hi16), static_cast<__nv_bfloat16 *>(lo16)};
+               static_cast<__nv_bfloat16 *>(hi16), static_cast<__nv_bfloat16 *>(lo16), perm};
   KTimer t(ctx, DALI_K_NORMALIZE);
   const bool vec = d % 4 == 0 && d_pad <= 4 * kPrepThreads * kVecCache && ldx % 4 == 0 && ldo % 4 == 0 &&
                    (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&

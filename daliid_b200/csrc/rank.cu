@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(128)
 plan_expand_kernel(int64_t Q, const int64_t *__restrict__ off, const int64_t *__restrict__ lo,
                    const int32_t *__restrict__ qcam, const int32_t *__restrict__ order,
                    const int32_t *__restrict__ gcam, int32_t *__restrict__ gid,
-                   int32_t *__restrict__ nv_out, int32_t *__restrict__ njunk_out) {
+                   int32_t *__restrict__ nv_out, int32_t *__restrict__ njunk_out,
+                   int32_t *__restrict__ slot_out) {
   const int64_t q = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
   if (q >= Q) return;
   const int lane = threadIdx.x & 31;
@@ -57,8 +58,16 @@ plan_expand_kernel(int64_t Q, const int64_t *__restrict__ off, const int64_t *__
     const unsigned bv = __ballot_sync(0xffffffffu, valid);
     const unsigned bj = __ballot_sync(0xffffffffu, junk);
     const unsigned below = (1u << lane) - 1u;
-    if (valid) gid[o + nv + __popc(bv & below)] = g;
-    if (junk) gid[o + (m - 1) - (nj + __popc(bj & below))] = g;  // filled from the back
+    if (valid) {
+      const int slot = nv + __popc(bv & below);
+      gid[o + slot] = g;
+      slot_out[o + i] = slot;
+    }
+    if (junk) {  // filled from the back
+      const int slot = (m - 1) - (nj + __popc(bj & below));
+      gid[o + slot] = g;
+      slot_out[o + i] = slot;
+    }
     nv += __popc(bv);
     nj += __popc(bj);
   }
@@ -490,11 +499,82 @@ rank_finalize_kernel(const int64_t *__restrict__ off, const int32_t *__restrict_
 
 }  // namespace
 
+// ------------------- fused distance + counting: threshold sort, prefix ---------------------
+// (the counting itself is the kCount epilogue of distmat_umma2.cu)
+namespace {
+constexpr int kFzThreads = 128;  // >= the most valid positives of a query on the fused path
+
+// One CTA per query: its valid positives' distances sorted ascending by (key, gallery id) -- a
+// rank sort, the composites are distinct -- with the match-list slot of each; a positive whose
+// distance is NaN or infinite raises the flag (the caller then takes the matrix path).
+__global__ void __launch_bounds__(kFzThreads)
+fused_sort_thresholds_kernel(const int64_t *__restrict__ off, const int32_t *__restrict__ nvalid,
+                             const int32_t *__restrict__ gid, const uint32_t *__restrict__ keys,
+                             float *__restrict__ sorted_thr, int32_t *__restrict__ sorted_slot,
+                             int32_t *__restrict__ flag) {
+  __shared__ uint64_t s_c[kFzThreads];
+  const int64_t q = blockIdx.x;
+  const int64_t o = off[q];
+  const int nv = min(nvalid[q], kFzThreads);
+  const int t = threadIdx.x;
+  uint64_t c = 0;
+  if (t < nv) {
+    const uint32_t k = keys[o + t];
+    c = composite(k, static_cast<uint32_t>(gid[o + t]));
+    s_c[t] = c;
+    if (k >= 0xFF800000u || k <= 0x007FFFFFu) *flag = 1;  // +inf, NaN / -inf
+  }
+  __syncthreads();
+  if (t < nv) {
+    int r = 0;
+    for (int u = 0; u < nv; ++u) r += s_c[u] < c ? 1 : 0;
+    sorted_thr[o + r] = key_to_dist(static_cast<uint32_t>(c >> 32));
+    sorted_slot[o + r] = t;
+  }
+}
+
+// counts[slot of the k-th smallest threshold] += sum of the buckets of its pass up to k
+__global__ void __launch_bounds__(kFzThreads)
+fused_prefix_kernel(const int64_t *__restrict__ off, const int32_t *__restrict__ nvalid,
+                    const int32_t *__restrict__ hist, const int32_t *__restrict__ sorted_slot,
+                    int32_t *__restrict__ counts, int pass) {
+  const int64_t q = blockIdx.x;
+  const int64_t o = off[q];
+  const int nv = min(nvalid[q], kFzThreads);
+  const int k = threadIdx.x;
+  if (k >= nv) return;
+  const int b0 = (k / pass) * pass;
+  int sum = 0;
+  for (int b = b0; b <= k; ++b) sum += hist[o + b];
+  counts[o + sorted_slot[o + k]] += sum;
+}
+}  // namespace
+
+int launch_fused_sort_thresholds(dali_ctx *ctx, const dali_rank_plan *plan, const uint32_t *keys,
+                                 float *sorted_thr, int32_t *sorted_slot, int32_t *flag) {
+  if (plan->Q == 0) return DALI_OK;
+  KTimer t(ctx, DALI_K_RANK_GATHER);
+  fused_sort_thresholds_kernel<<<static_cast<unsigned>(plan->Q), kFzThreads, 0, ctx->stream>>>(
+      plan->d_off, plan->d_nv, plan->d_gid, keys, sorted_thr, sorted_slot, flag);
+  DALI_CUDA_OK(ctx, cudaGetLastError());
+  return DALI_OK;
+}
+
+int launch_fused_prefix(dali_ctx *ctx, const dali_rank_plan *plan, const int32_t *hist,
+                        const int32_t *sorted_slot, int32_t *counts, int pass) {
+  if (plan->Q == 0) return DALI_OK;
+  KTimer t(ctx, DALI_K_RANK_COUNT);
+  fused_prefix_kernel<<<static_cast<unsigned>(plan->Q), kFzThreads, 0, ctx->stream>>>(
+      plan->d_off, plan->d_nv, hist, sorted_slot, counts, pass);
+  DALI_CUDA_OK(ctx, cudaGetLastError());
+  return DALI_OK;
+}
+
 int launch_plan_expand(dali_ctx *ctx, const dali_rank_plan *plan) {
   if (plan->Q == 0) return DALI_OK;
   plan_expand_kernel<<<static_cast<unsigned>((plan->Q + 3) / 4), 128, 0, ctx->stream>>>(
       plan->Q, plan->d_off, plan->d_lo, plan->d_qcam, plan->d_order, plan->d_gcam, plan->d_gid,
-      plan->d_nv, plan->d_njunk);
+      plan->d_nv, plan->d_njunk, plan->d_slot);
   DALI_CUDA_OK(ctx, cudaGetLastError());
   ctx->launches++;
   return DALI_OK;

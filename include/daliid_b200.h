@@ -126,6 +126,20 @@ int64_t dali_ctx_fallback_count(dali_ctx *ctx);
  * environment or dali_ctx_plan_cache_enable(ctx, 0) turn it off. */
 int dali_ctx_plan_cache_enable(dali_ctx *ctx, int on);
 int64_t dali_ctx_plan_cache_hits(dali_ctx *ctx);
+/* Fused distance + positive-rank counting (opt-in).  When enabled, dali_eval_features_f32 never
+ * writes the Q x G matrix if the features are device resident (or a small host array), the
+ * arithmetic is a tensor-core mode, no matrix is requested and no query has more than 64
+ * same-identity gallery items (128 from D = 1536 on): the operands are prepared identity-sorted, the
+ * few tiles holding the matches yield the positives' distances (kBand), and every tile is counted
+ * against each query's sorted thresholds in the contraction's epilogue (kCount: a binary search per
+ * column in shared memory).  Results are bit-identical to the matrix path of the same arithmetic.
+ * DISABLED by default: at the Market shapes the extra band wave and the epilogue cost more than the
+ * 0.1 ms the matrix read-back takes (DESIGN.md 4.9 has the measurements); DALI_FUSED_COUNT=1 / 0
+ * overrides this switch.  dali_ctx_fused_count_calls: evaluations that took the fused path; a call
+ * that found a non-finite positive distance is redone through the matrix and counted by
+ * dali_ctx_fallback_count instead. */
+int dali_ctx_fused_count_enable(dali_ctx *ctx, int on);
+int64_t dali_ctx_fused_count_calls(dali_ctx *ctx);
 
 /* ---- a1: row L2 normalisation -------------------------------------------- */
 /* out[i,:] = x[i,:] / ||x[i,:]||  (no eps: a zero row yields NaN, as the reference does)
