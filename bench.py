@@ -229,39 +229,188 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------
-def measure_c5(dev, rank, world, dist):
-    """BASELINE config 5 beside the headline: 100k queries x 125k gallery rows PER GPU (1M at 8
+def measure_tf32_peak(dev):
+    """cuBLAS TF32 8192^3, best of 5 (TFLOP/s): MEASURED_PEAKS.json holds no TF32 figure, so the
+    single-pass TF32 mode is rated against this, measured the way the driver measured bf16."""
+    n = 8192
+    a = torch.randn(n, n, device=dev)
+    b = torch.randn(n, n, device=dev)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        for _ in range(2):
+            a @ b
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    del a, b
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def measure_c5(dev, rank, world, dist, tf32_peak):
+    """BASELINE config 4 beside the headline: 100k queries x 125k gallery rows PER GPU (1M at 8
     GPUs), D=512, fused distance + top-20 (the Q x G matrix is never written), per-slab top-k
-    all-gathered and merged.  Device-resident synthetic features, 3 timed evaluations."""
+    all-gathered and merged.  Device-resident synthetic features, 3 timed evaluations per
+    arithmetic mode: the default fp32-class f16x3 (three fp16 passes) and the two single-pass
+    modes the 0.01 pp rule admits for identification (f16, tf32), each against ITS tensor peak."""
     from daliid_b200 import sharded
     Q, Gs, D, k = 100000, 125000, 512, 20
     gq = torch.Generator(device=dev).manual_seed(12)
     qf = torch.randn(Q, D, generator=gq, device=dev)
     gg = torch.Generator(device=dev).manual_seed(1000 + rank)
     gf = torch.randn(Gs, D, generator=gg, device=dev)
-    for _ in range(2):
-        sharded.topk_features_sharded(qf, gf, rank * Gs, k=k)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 3
-    e0.record()
-    for _ in range(n):
-        v, i = sharded.topk_features_sharded(qf, gf, rank * Gs, k=k)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    pk = peaks()
+    out = {"workload": f"Q={Q} x G={Gs}/GPU (global {Gs * world}) x D={D}, fused distance + top-{k}",
+           "scaling": "weak (one 125k slab per GPU)"}
+    ref_ids = None
+    for mode, passes, peak in (("f16x3", 3, pk["bf16"]), ("f16", 1, pk["bf16"]), ("tf32", 1, tf32_peak)):
+        for _ in range(2):
+            sharded.topk_features_sharded(qf, gf, rank * Gs, k=k, precision=mode)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 3
+        e0.record()
+        for _ in range(n):
+            v, i = sharded.topk_features_sharded(qf, gf, rank * Gs, k=k, precision=mode)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        tf = 2.0 * Q * Gs * D / (ms * 1e-3) / 1e12
+        blk = {"ms_per_eval": ms, "pairs_per_s": Q * Gs * world / (ms * 1e-3), "tflops_per_gpu": tf,
+               "tensor_passes": passes, "peak_tflops": peak,
+               # algorithmic FLOPs over the peak of the MMA kind used; the ceiling is 1 / passes
+               "frac_of_peak": tf / peak, "frac_of_own_ceiling": tf * passes / peak}
+        if mode == "f16x3":
+            ref_ids = i
+            blk["frac_of_bf16_peak"] = tf / pk["bf16"]
+        else:  # rank-1 agreement of the single-pass mode with the fp32-class result
+            blk["top1_agreement_with_f16x3"] = float((i[:, 0] == ref_ids[:, 0]).float().mean().item())
+        out[mode] = blk
+    out.update({kk: out["f16x3"][kk] for kk in ("ms_per_eval", "pairs_per_s", "tflops_per_gpu", "frac_of_bf16_peak")})
+    out["frac_ceiling"] = 1.0 / 3.0
     del qf, gf
-    tf = 2.0 * Q * Gs * D / (ms * 1e-3) / 1e12
-    return {"workload": f"Q={Q} x G={Gs}/GPU (global {Gs * world}) x D={D}, fused distance + top-{k}, f16x3",
-            "ms_per_eval": ms, "pairs_per_s": Q * Gs * world / (ms * 1e-3), "tflops_per_gpu": tf,
-            "frac_of_bf16_peak": tf / peaks()["bf16"], "frac_ceiling": 1.0 / 3.0,
-            "scaling": "weak (one 125k slab per GPU)"}
+    return out
+
+
+def measure_c1(dev, timed, ctx):
+    """BASELINE config 0, the north-star target shape: Market-1501, ViT D=768, full evaluation
+    (target: under 50 ms on one B200)."""
+    from daliid_b200 import metrics, synth
+    qf, gf, qp, gp, qc, gc = synth.make_config("market_vit", device=dev)
+    Q, G, D = qf.shape[0], gf.shape[0], qf.shape[1]
+
+    def step():
+        return metrics.evaluate_features(qf, gf, qp, gp, qc, gc, precision="f16x3")
+    for _ in range(3):
+        step()
+    ms, (cmc, mAP) = timed(step, 10)
+    ctx.timing_enable(True)
+    ctx.timing_reset()
+    for _ in range(4):
+        step()
+    kt = ctx.timing_read()
+    ctx.timing_enable(False)
+    n_dm, ms_dm = kt["distmat"]
+    tf = 2.0 * Q * G * D / (ms_dm / max(n_dm, 1) * 1e-3) / 1e12
+    return {"workload": f"market_vit: Q={Q} x G={G} x D={D}, cosine, f16x3", "ms_per_step": ms / 10,
+            "pairs_per_s": Q * G / (ms / 10 * 1e-3), "target_ms": 50.0, "under_target": ms / 10 < 50.0,
+            "kernel_ms_per_step": {k: v[1] / 4 for k, v in kt.items() if v[0]},
+            "contraction_tflops": tf, "contraction_frac_of_bf16_peak": tf / peaks()["bf16"],
+            "mAP": mAP, "rank1": float(cmc[0])}
+
+
+def measure_c3(dev, rank, world, dist, timed, ctx):
+    """BASELINE config 2: DeepChange shape (17527 x 62956, D=768), STRONG scaling at the run's N --
+    the gallery is split over the ranks, every rank holds all queries."""
+    from daliid_b200 import metrics, sharded, synth
+    qf, gf, qp, gp, qc, gc = synth.make_config("deepchange", device=dev)
+    Q, G, D = qf.shape[0], gf.shape[0], qf.shape[1]
+    g0, gs = sharded.slab_bounds(G, world, rank)
+    slab = gf[g0:g0 + gs].contiguous()
+    del gf
+
+    def step():
+        if world == 1:
+            return metrics.evaluate_features(qf, slab, qp, gp, qc, gc, precision="f16x3")
+        return sharded.evaluate_features_sharded(qf, slab, g0, qp, gp, qc, gc, precision="f16x3")
+    for _ in range(3):
+        step()
+    ms, (cmc, mAP) = timed(step, 5)
+    ctx.timing_enable(True)
+    ctx.timing_reset()
+    for _ in range(2):
+        step()
+    kt = ctx.timing_read()
+    ctx.timing_enable(False)
+    return {"workload": f"deepchange: Q={Q} x G={G} x D={D}, cosine, f16x3, gallery split over {world} GPU(s)",
+            "scaling": "strong", "ms_per_step": ms / 5, "pairs_per_s": Q * G / (ms / 5 * 1e-3),
+            "kernel_ms_per_step_rank0": {k: v[1] / 2 for k, v in kt.items() if v[0]}, "mAP": mAP,
+            "rank1": float(cmc[0])}
+
+
+def measure_c4(dev, timed, ctx):
+    """BASELINE config 3: three models' Market-shaped distance matrices (seeds 12, 13, 14) -> mean
+    fusion in the reference's operation order -> rank / CMC / mAP (evaluate.py:260-279)."""
+    from daliid_b200 import metrics, synth
+    sets = [synth.make_config("market_vit", seed=sd, device=dev) for sd in (12, 13, 14)]
+    _, _, qp, gp, qc, gc = sets[0]
+    Q, G = sets[0][0].shape[0], sets[0][1].shape[0]
+
+    def step():
+        ds = [metrics.compute_distance_matrix(q, g, "cosine", "f16x3") for q, g, *_ in sets]
+        return metrics.evaluate_rank(metrics.fuse_distmats(ds), qp, gp, qc, gc)
+    for _ in range(3):
+        step()
+    ms, (cmc, mAP) = timed(step, 10)
+    ctx.timing_enable(True)
+    ctx.timing_reset()
+    for _ in range(4):
+        step()
+    kt = ctx.timing_read()
+    ctx.timing_enable(False)
+    return {"workload": f"3 x market_vit (Q={Q} x G={G} x D=768) -> mean fusion -> rank", "ms_per_step": ms / 10,
+            "pairs_per_s": Q * G / (ms / 10 * 1e-3), "kernel_ms_per_step": {k: v[1] / 4 for k, v in kt.items() if v[0]},
+            "mAP": mAP, "rank1": float(cmc[0])}
+
+
+def measure_h2d_ceiling(dev, nbytes, world, dist):
+    """Raw pinned host -> device copy of one step's input bytes, all ranks at the same time: the
+    ceiling of the end-to-end number on this host (aggregate GB/s over the ranks)."""
+    h = torch.empty(nbytes // 4, dtype=torch.float32).pin_memory()
+    d = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+    best = 1e9
+    for it in range(4):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        d.copy_(h, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        if it:
+            best = min(best, ms)
+    del h, d
+    return {"bytes_per_rank": int(nbytes), "ms": best, "gbs_per_rank": nbytes / (best * 1e-3) / 1e9,
+            "gbs_aggregate": world * nbytes / (best * 1e-3) / 1e9}
 
 
 def stock_gpu_baseline(qf, gf, q_pid, g_pid, q_cam, g_cam, timed):
@@ -423,6 +572,44 @@ def run_ours(args):
         step_host()
     ms_e2e, _ = timed(step_host, args.steps)
     hits = ctx.plan_cache_hits() - hits
+    # the same end-to-end steps from PAGEABLE host memory: what the reference's producer hands over
+    # (getFeatures.py:62-67 concatenates per-batch .cpu() tensors; nothing is pinned there)
+    qf_p, gf_p = wl["qf"].clone(), wl["gf"].clone()
+    for _ in range(3):
+        step(qf_p, gf_p)
+    ms_pageable, _ = timed(lambda: step(qf_p, gf_p), max(4, args.steps // 2))
+    ms_pageable /= max(4, args.steps // 2)
+    del qf_p, gf_p
+    # host ceiling: the raw pinned copy of one step's input bytes, all ranks at once
+    in_bytes = int((-(-Q // world) + G) * D * 4)
+    h2d_ceiling = measure_h2d_ceiling(dev, in_bytes, world, dist)
+    # H2D and peer-exchange shares of the end-to-end step (events on the copy / compute streams)
+    ctx.timing_enable(True)
+    ctx.timing_reset()
+    for _ in range(4):
+        step_host()
+    kt_e2e = ctx.timing_read()
+    ctx.timing_enable(False)
+    # multi-GPU: the sharded result against the single-GPU evaluation of the WHOLE gallery
+    sharded_parity = None
+    if world > 1:
+        slabs = [torch.empty_like(gf_d) for _ in range(world)]
+        dist.all_gather(slabs, gf_d)
+        g_all = torch.cat(slabs)
+        del slabs
+        s_cmc, s_map, s_det = sharded.evaluate_features_sharded(qf_d, gf_d, wl["g0"], wl["q_pid"], g_pid, wl["q_cam"],
+                                                                g_cam, metric="cosine", precision=prec,
+                                                                return_details=True)
+        u_cmc, u_map, u_det = metrics.evaluate_features(qf_d, g_all, wl["q_pid"], g_pid, wl["q_cam"], g_cam,
+                                                        metric="cosine", precision=prec, return_details=True)
+        del g_all
+        same = bool(np.array_equal(s_cmc, u_cmc) and s_map == u_map and
+                    np.array_equal(s_det["first_rank"], u_det["first_rank"]) and
+                    np.array_equal(s_det["ap"], u_det["ap"], equal_nan=True))
+        flag = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        assert int(flag.item()) == 1, f"rank {rank}: sharded evaluation differs from the single-GPU one"
+        sharded_parity = "bit-identical"
     # the same steps with the rank plan rebuilt from the labels on every step
     ctx.plan_cache_enable(False)
     step(qf_d, gf_d)
@@ -508,9 +695,15 @@ def run_ours(args):
     if world == 1 and rank == 0 and not args.no_modes:
         stock = stock_gpu_baseline(qf_d, gf_d, wl["q_pid"], g_pid, wl["q_cam"], g_cam, timed)
 
-    c5 = None
+    c1 = c3 = c4 = c5 = None
+    if not args.no_side:
+        if world == 1:
+            c1 = measure_c1(dev, timed, ctx)
+            c4 = measure_c4(dev, timed, ctx)
+        c3 = measure_c3(dev, rank, world, dist, timed, ctx)
     if not args.no_c5:
-        c5 = measure_c5(dev, rank, world, dist)
+        tf32_peak = measure_tf32_peak(dev)
+        c5 = measure_c5(dev, rank, world, dist, tf32_peak)
 
     if rank != 0:
         if world > 1:
@@ -526,12 +719,11 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": "distmat_umma2_kernel" if prec != "fp32" else "distmat_simt_kernel",
                 "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
                 "frac": (achieved / pk["bf16"]) if achieved else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this
-                # shape, ncu --set full (profiles/r01f_full.md: 200.3 MB + 187.1 MB; r01d: 234.8 + 188.5);
-                # algorithmic minimum = 161 MB of fp16 operand planes + 214 MB of distance matrix (part of
-                # which is still in L2 when the kernel ends)
-                "traffic": 387.4e6 if (prec == "f16x3" and world == 1) else None,
-                "traffic_source": "profiles/r01f_full.md",
+                # dram__bytes_read.sum + dram__bytes_write.sum need ncu and are not measured in this run:
+                # see profiles/ (r02_c2_full.md: read + write per launch of this kernel at this shape);
+                # algorithmic minimum = 161 MB of fp16 operand planes + 214 MB of distance matrix
+                "traffic": None,
+                "traffic_source": "not measured live (ncu capture of the same command: profiles/r02_c2_full.md)",
                 "peak_source": pk["source"] + " bf16 burst; the fp32-class splits issue several tensor "
                                "passes per algorithmic FLOP: ceiling of frac = 1/3 for f16x3 (three 16-bit "
                                "passes), 1/2 for tf32, 1/4 for tf32c (1 TF32 + 2 bf16 passes), 1/6 for tf32x3",
@@ -539,7 +731,7 @@ def run_ours(args):
     roofline_rank = {"bound": "hbm", "kernel": "rank_count_v2_kernel (one launch: thresholds, counting, CMC/AP epilogue)"
                      if world == 1 else "rank_count_v2_kernel", "achieved": rank_gbs,
                      "peak": pk["hbm"], "unit": "GB/s", "frac": (rank_gbs / pk["hbm"]) if rank_gbs else None,
-                     "traffic": 218.3e6 if world == 1 else None,  # profiles/r01f_full.md: 214.8 + 3.5 MB
+                     "traffic": None,  # ncu only: profiles/r02_c2_full.md
                      "avg_launch_ms": ms_rc / max(n_rc, 1) if n_rc else None}
 
     line = {
@@ -561,6 +753,12 @@ def run_ours(args):
                 # sharded.share_queries) + its gallery slab, fp32, + the int32 label arrays
                 "h2d_bytes_per_step": int((-(-Q // world) + G) * D * 4 + (Q + G * world) * 8),
                 "d2h_bytes_per_step": int(Q * 8 + 51 * 4), "h2d_dma_streams": ctx.h2d_streams()},
+        "e2e_pageable": {"value": pairs_per_step / (ms_pageable * 1e-3), "unit": UNIT, "ms_per_step": ms_pageable,
+                         "note": "same call, features in pageable host memory (what the reference's "
+                                 "getFeatures.py hands over); the driver stages through its own pinned buffers"},
+        "h2d_ceiling": h2d_ceiling,
+        "e2e_kernel_ms_per_step": {k: v[1] / 4 for k, v in kt_e2e.items() if v[0]},
+        "sharded_parity": sharded_parity,
         "gpu_launches": int(launches),
         "numa_binding": numa,
         "rank_plan": {"note": "the plan (gallery index by identity, label-only) of the previous step is "
@@ -577,6 +775,12 @@ def run_ours(args):
         line["other_precisions"] = modes
     if stock:
         line["stock_gpu_baseline"] = stock
+    if c1:
+        line["c1_market_vit"] = c1
+    if c3:
+        line["c3_deepchange"] = c3
+    if c4:
+        line["c4_fusion3"] = c4
     if c5:
         line["c5_faceid_1toN"] = c5
     if world == 1 and not args.no_cpu_baseline:
@@ -608,6 +812,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-modes", action="store_true", help="skip the per-precision side measurements")
     ap.add_argument("--no-c5", action="store_true", help="skip the config-5 (1:N top-k) side measurement")
+    ap.add_argument("--no-side", action="store_true", help="skip the C1 / C3 / C4 side measurements")
     ap.add_argument("--breakdown", action="store_true", help="diagnostic per-phase host timing (stderr)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -153,8 +153,22 @@ static int h2d_parallel(dali_ctx *ctx, void *dst, const void *src, size_t bytes,
     const size_t b0 = per * i;
     if (b0 >= bytes) break;
     const size_t nb = std::min(per, bytes - b0);
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (ctx->timing) {  // DALI_K_H2D: events on the copy stream around this part of the copy
+      auto get = [&]() {
+        cudaEvent_t e;
+        if (!ctx->t_pool.empty()) { e = ctx->t_pool.back(); ctx->t_pool.pop_back(); } else { cudaEventCreate(&e); }
+        return e;
+      };
+      t0 = get(); t1 = get();
+      cudaEventRecord(t0, ctx->copy_streams[i]);
+    }
     DALI_CUDA_OK(ctx, cudaMemcpyAsync(static_cast<char *>(dst) + b0, static_cast<const char *>(src) + b0, nb,
                                       cudaMemcpyHostToDevice, ctx->copy_streams[i]));
+    if (t0) {
+      cudaEventRecord(t1, ctx->copy_streams[i]);
+      ctx->t_pending.push_back({DALI_K_H2D, {t0, t1}});
+    }
     int rc = next_event(ctx, &ev);
     if (rc) return rc;
     DALI_CUDA_OK(ctx, cudaEventRecord(ev, ctx->copy_streams[i]));

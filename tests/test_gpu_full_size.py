@@ -226,3 +226,56 @@ def test_deepchange_shape_vs_oracle_and_sharded():
     v, i = metrics.topk_identify(d, k=20)
     order = np.argsort(sub, axis=1, kind="stable")[:, :20]
     assert np.array_equal(i[selt].cpu().numpy(), order.astype(np.int32))
+
+
+def test_c2_resnet50_shape_full_size():
+    """BASELINE config 1 -- the shape bench.py measures: 3368 x 15913, D = 2048, default precision.
+    Distances of a row subset against the reference's CPU fp32 expression (1e-5), CMC / mAP /
+    per-query first rank of that subset bit-exact against the compiled oracle fed the SAME matrix,
+    the whole evaluation against the FP32-pipe arm (<= 0.01 pp mAP), and exact duplicates planted
+    in the gallery (the pairs where the tensor core's accumulator truncation shows) within 1e-5."""
+    from daliid_b200 import metrics, synth
+    qf, gf, qp, gp, qc, gc = synth.make_config("market_resnet50", device="cuda")
+    gf = gf.clone()
+    gf[:64] = qf[:64]                       # 64 exact duplicates and 64 near-duplicates
+    gf[64:128] = qf[64:128] + 0.01 * torch.randn(64, qf.shape[1], device="cuda")
+    sel = torch.cat([torch.arange(0, 128, device="cuda"), torch.arange(128, qf.shape[0], 23, device="cuda")])[:260]
+    seln = sel.cpu().numpy()
+    ref = do.cosine_distmat(qf[sel].cpu(), gf.cpu()).numpy()
+    cmc, mAP, d, det = metrics.evaluate_features(qf, gf, qp, gp, qc, gc, return_distmat=True, return_details=True)
+    sub = d[sel].cpu().numpy()
+    err = np.abs(sub.astype(np.float64) - ref) / np.maximum(1.0, np.abs(ref))
+    assert err.max() <= 1e-5, err.max()
+    dup = np.abs(sub[np.arange(128), np.arange(128)].astype(np.float64) - ref[np.arange(128), np.arange(128)])
+    assert dup.max() <= 1e-5 and ref[np.arange(64), np.arange(64)].max() < 1e-6, dup.max()
+    e = c_oracle.evaluate_rank_c(sub, qp[seln], gp, qc[seln], gc, return_details=True)
+    s_cmc, s_map, s_ap, s_first, _ = metrics.evaluate_rank_detailed(d[sel].contiguous(), qp[seln], gp, qc[seln], gc)
+    assert np.array_equal(s_cmc, e[0]) and s_map == e[1] and np.array_equal(s_first, e[3])
+    assert np.array_equal(det["first_rank"][seln], e[3])          # the fused call ranked the same rows alike
+    x_cmc, x_map = metrics.evaluate_features(qf, gf, qp, gp, qc, gc, precision="fp32")
+    assert abs(x_map - mAP) * 100 <= 0.01 and np.abs(x_cmc - cmc).max() <= 0.001
+
+
+def test_c5_slab_fused_topk_equals_materialised_topk():
+    """BASELINE config 4 (1:N identification), one gallery slab of the 8-GPU run: 100k queries x
+    125k gallery rows, D = 512.  The fused distance + top-20 (no matrix) of a query subset must equal
+    the top-20 of the materialised matrix of the same arithmetic bit for bit (values and ids), the
+    whole call must not fall back, and ids must respect g_base."""
+    from daliid_b200 import _lib, metrics
+    Q, G, D, k = 100_000, 125_000, 512, 20
+    gq = torch.Generator(device="cuda").manual_seed(12)
+    qf = torch.randn(Q, D, generator=gq, device="cuda")
+    gf = torch.randn(G, D, generator=gq, device="cuda")
+    gf[1000:1100] = qf[500:600]                     # planted matches: rank 1 at distance ~0
+    ctx = _lib.get_ctx(0)
+    f0 = ctx.fallback_count()
+    v, i = metrics.topk_features(qf, gf, k=k, g_base=3_000_000)
+    assert ctx.fallback_count() == f0
+    assert i.shape == (Q, k) and int(i.min()) >= 3_000_000 and int(i.max()) < 3_000_000 + G
+    assert torch.equal(i[500:600, 0].cpu(), torch.arange(1000, 1100, dtype=torch.int32) + 3_000_000)
+    assert float(v[500:600, 0].abs().max()) <= 1e-5
+    sel = torch.arange(0, Q, 97, device="cuda")[:1024]
+    d = metrics.compute_distance_matrix(qf[sel].contiguous(), gf, "cosine")
+    ev, ei = metrics.topk_identify(d, k=k)
+    assert torch.equal(v[sel], ev) and torch.equal(i[sel] - 3_000_000, ei)
+    assert bool((v[:, 1:] >= v[:, :-1]).all())        # ascending within every row
