@@ -93,53 +93,93 @@ __global__ void __launch_bounds__(256) fuse_kernel(FuseParams p) {
   }
 }
 
-// Contiguous matrices (ld == G, what numpy / torch hand over): the Q x G elements are one flat
-// array, so 128-bit accesses work for any G (15913 is odd); the (row, column) of an element is
-// only needed for the weighted form.
+// Flat form: the matrices are one array of Q * ld floats each (ld == G: what numpy / torch hand over,
+// 128-bit accesses then work for any G -- 15913 is odd; or rows padded to a multiple of four floats:
+// what compute_distance_matrix returns on CUDA, the padding columns are fused along and never read).
+// N is a compile-time constant (the 8-way predicated unroll over a run-time n cost a third of the
+// bandwidth), two float4 per matrix are in flight per thread, and the mean of 2 / 4 / 8 matrices
+// multiplies by the exact reciprocal instead of dividing.
+template <int N, bool WEIGHTED>
 __global__ void __launch_bounds__(256) fuse_flat_kernel(FuseParams p) {
-  const int64_t total = p.Q * p.G;
+  const int64_t total = p.Q * p.ld;
   const int64_t nvec = (total + 3) >> 2;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  auto one = [&](const float (&v)[N], int64_t q, int64_t col) -> float {
+    if (!WEIGHTED) {
+      float acc = v[0];
+#pragma unroll
+      for (int m = 1; m < N; ++m) acc = __fadd_rn(acc, v[m]);
+      if (N == 1) return acc;
+      if (N == 2 || N == 4 || N == 8) return __fmul_rn(acc, 1.0f / N);  // exact: a power of two
+      return __fdiv_rn(acc, static_cast<float>(N));
+    }
+    if (col >= p.G) return 0.f;  // padding column
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      const float a = __ldg(p.wq[m] + q), g = __ldg(p.wg[m] + col);
+      float w = fmaxf(a, g);
+      if (a != a || g != g) w = NAN;  // torch.maximum propagates NaN; fmaxf does not
+      num = m == 0 ? __fmul_rn(w, v[0]) : __fadd_rn(num, __fmul_rn(w, v[m]));
+      den = m == 0 ? w : __fadd_rn(den, w);
+    }
+    return __fdiv_rn(num, den);
+  };
+  auto body = [&](int64_t i) {
     const int64_t e0 = i << 2;
-    int64_t q = 0, col = e0;
-    if (p.weighted) {
-      q = e0 / p.G;
-      col = e0 - q * p.G;
-    }
-    float xs[kMaxFuse][4];
-    const bool full = e0 + 3 < total;
+    if (e0 + 3 < total) {
+      float4 x[N];
 #pragma unroll
-    for (int m = 0; m < kMaxFuse; ++m) {
-      if (m < p.n) {
-        if (full) {
-          const float4 x = __ldcs(reinterpret_cast<const float4 *>(p.d[m] + e0));
-          xs[m][0] = x.x; xs[m][1] = x.y; xs[m][2] = x.z; xs[m][3] = x.w;
-        } else {
+      for (int m = 0; m < N; ++m) x[m] = __ldcs(reinterpret_cast<const float4 *>(p.d[m] + e0));
+      int64_t q = 0, col = 0;
+      if (WEIGHTED) { q = e0 / p.ld; col = e0 - q * p.ld; }  // ld % 4 == 0 or ld == G: see the launcher
+      float v[N];
+      float4 o;
 #pragma unroll
-          for (int t = 0; t < 4; ++t) xs[m][t] = e0 + t < total ? __ldg(p.d[m] + e0 + t) : 0.f;
-        }
-      }
-    }
-    float o[4];
+      for (int m = 0; m < N; ++m) v[m] = x[m].x;
+      o.x = one(v, q, col);
+      if (WEIGHTED && ++col == p.ld) { col = 0; ++q; }
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      float v[kMaxFuse], wqv[kMaxFuse];
+      for (int m = 0; m < N; ++m) v[m] = x[m].y;
+      o.y = one(v, q, col);
+      if (WEIGHTED && ++col == p.ld) { col = 0; ++q; }
 #pragma unroll
-      for (int m = 0; m < kMaxFuse; ++m) {
-        v[m] = (m < p.n) ? xs[m][t] : 0.f;
-        wqv[m] = (p.weighted && m < p.n && e0 + t < total) ? __ldg(p.wq[m] + q) : 0.f;
-      }
-      o[t] = (e0 + t < total) ? fuse_one(p, v, wqv, col) : 0.f;
-      if (++col == p.G) { col = 0; ++q; }
-    }
-    if (full) {
-      *reinterpret_cast<float4 *>(p.out + e0) = make_float4(o[0], o[1], o[2], o[3]);
+      for (int m = 0; m < N; ++m) v[m] = x[m].z;
+      o.z = one(v, q, col);
+      if (WEIGHTED && ++col == p.ld) { col = 0; ++q; }
+#pragma unroll
+      for (int m = 0; m < N; ++m) v[m] = x[m].w;
+      o.w = one(v, q, col);
+      __stcs(reinterpret_cast<float4 *>(p.out + e0), o);
     } else {
+      for (int64_t e = e0; e < total; ++e) {
+        float v[N];
 #pragma unroll
-      for (int t = 0; t < 4; ++t)
-        if (e0 + t < total) p.out[e0 + t] = o[t];
+        for (int m = 0; m < N; ++m) v[m] = __ldg(p.d[m] + e);
+        const int64_t q = e / p.ld;
+        p.out[e] = one(v, q, e - q * p.ld);
+      }
     }
+  };
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  for (; i + stride < nvec; i += 2 * stride) {  // two independent vectors per trip
+    body(i);
+    body(i + stride);
+  }
+  if (i < nvec) body(i);
+}
+
+template <bool WEIGHTED>
+static void launch_flat(int n, int blocks, cudaStream_t st, const FuseParams &p) {
+  switch (n) {
+    case 1: fuse_flat_kernel<1, WEIGHTED><<<blocks, 256, 0, st>>>(p); break;
+    case 2: fuse_flat_kernel<2, WEIGHTED><<<blocks, 256, 0, st>>>(p); break;
+    case 3: fuse_flat_kernel<3, WEIGHTED><<<blocks, 256, 0, st>>>(p); break;
+    case 4: fuse_flat_kernel<4, WEIGHTED><<<blocks, 256, 0, st>>>(p); break;
+    case 5: fuse_flat_kernel<5, WEIGHTED><<<blocks, 256, 0, st>>>(p); break;
+    case 6: fuse_flat_kernel<6, WEIGHTED><<<blocks, 256, 0, st>>>(p); break;
+    case 7: fuse_flat_kernel<7, WEIGHTED><<<blocks, 256, 0, st>>>(p); break;
+    default: fuse_flat_kernel<8, WEIGHTED><<<blocks, 256, 0, st>>>(p); break;
   }
 }
 
@@ -161,12 +201,16 @@ int launch_fuse(dali_ctx *ctx, const float *const *d, int n, const float *const 
   p.out = out; p.n = n; p.weighted = (wq && wg) ? 1 : 0; p.Q = Q; p.G = G; p.ld = ld;
   bool base_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   for (int m = 0; m < n; ++m) base_aligned = base_aligned && (reinterpret_cast<uintptr_t>(d[m]) & 15) == 0;
-  if ((ld == G || Q == 1) && base_aligned) {
+  // flat form: contiguous matrices, or rows padded to whole float4 (then a vector never straddles
+  // two rows and the padding columns are simply fused along)
+  if ((ld == G || Q == 1 || ld % 4 == 0) && base_aligned) {
+    if (Q == 1) p.ld = G;
     KTimer t(ctx, DALI_K_FUSE);
-    const int64_t nvec = (Q * G + 3) / 4;
-    const int64_t want = (nvec + 255) / 256;
-    const int blocks = static_cast<int>(std::min<int64_t>(want, 8ll * ctx->num_sms));
-    fuse_flat_kernel<<<blocks, 256, 0, ctx->stream>>>(p);
+    const int64_t nvec = (p.Q * p.ld + 3) / 4;
+    const int64_t want = (nvec + 511) / 512;
+    const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, 16ll * ctx->num_sms)));
+    if (p.weighted) launch_flat<true>(n, blocks, ctx->stream, p);
+    else launch_flat<false>(n, blocks, ctx->stream, p);
     DALI_CUDA_OK(ctx, cudaGetLastError());
     return DALI_OK;
   }
