@@ -1705,7 +1705,15 @@ static int topk_features_fused(dali_ctx *ctx, const Prepared &b, const float *q,
   float *dd = static_cast<float *>(dd_v);
   int32_t *ii = static_cast<int32_t *>(ii_v);
   DALI_CUDA_OK(ctx, cudaMemsetAsync(flag, 0, sizeof(int32_t), ctx->stream));
-  const int64_t growth = std::max<int64_t>(1, std::min<int64_t>(8, kCapList / (8 * k)));
+  // Chunk schedule.  After `seen` exchangeable columns the row's threshold is its k-th best, so a
+  // chunk of c further columns yields about c * k / seen survivors; the list holds kCapList.  Growth
+  // factors 4 .. 20 were measured on a 100k x 125k x 512 slab (tests/probes/c5_probe.py): larger
+  // chunks save launches and compaction passes but append more survivors per row in the epilogue,
+  // and 4 (about 80 survivors per row and chunk at k = 20) was the fastest: 28.2 ms against 29.0 at
+  // 8 and 29.7 at 12.  DALI_TOPK_GROWTH overrides.
+  static const char *env_growth = getenv("DALI_TOPK_GROWTH");
+  const int64_t growth = env_growth ? std::max(1, atoi(env_growth))
+                                    : std::max<int64_t>(1, std::min<int64_t>(8, kCapList / (12 * k)));
   for (int64_t q0 = 0; q0 < Q; q0 += band) {
     const int64_t qc = std::min(band, Q - q0);
     Prepared a;
@@ -1717,7 +1725,7 @@ static int topk_features_fused(dali_ctx *ctx, const Prepared &b, const float *q,
       const bool first = seen == 0;
       // first chunk: every column becomes a candidate, so keep it as narrow as k allows (the
       // compaction sorts it whole); later chunks start on a tile edge
-      const int64_t first_cols = std::min<int64_t>(kCapList, round_up(std::max<int64_t>(2 * k, 256), 256));
+      const int64_t first_cols = std::min<int64_t>(kCapList, round_up(std::max<int64_t>(2 * k, G >= 65536 ? 512 : 256), 256));
       int64_t chunk = first ? std::min<int64_t>(G, first_cols)
                             : std::min<int64_t>(G - seen, std::max<int64_t>(256, growth * seen / 256 * 256));
       rc = launch_distmat_filter_umma(ctx, a.planes, b.planes, a.planes16, b.planes16, qc, chunk, a.Dp,

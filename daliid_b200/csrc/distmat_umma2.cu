@@ -204,12 +204,17 @@ __device__ __forceinline__ void filter_cols(const uint32_t (&v)[32], const Filte
   }
   if (lim < 32) mask &= (1u << lim) - 1u;
   if (!fr.row_ok) mask = 0;
-  while (mask) {  // rare, divergent
-    const int j = __ffs(mask) - 1;
-    mask &= mask - 1;
-    const float d = dist_of(pick32(v, j), j);
-    const int pos = atomicAdd(fr.cnt, 1);
-    if (pos < fr.cap) fr.list[pos] = composite(dist_key(d) ^ fr.flip, id0 + j);
+  if (mask) {  // rare, divergent: ONE counter round trip for all survivors of these 32 columns (a
+               // returning atomic per survivor paced the short early chunks, where a row keeps ~10
+               // of a tile's 256 columns)
+    int pos = atomicAdd(fr.cnt, __popc(mask));
+    while (mask) {
+      const int j = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float d = dist_of(pick32(v, j), j);
+      if (pos < fr.cap) fr.list[pos] = composite(dist_key(d) ^ fr.flip, id0 + j);
+      ++pos;
+    }
   }
   // the next tcgen05.ld is .sync.aligned: lanes that took the loop above must have rejoined
   // (without this the lanes with no survivor ran ahead and the load landed in registers the
