@@ -84,6 +84,8 @@ _SIGNATURES = {
     "dali_fuse_f32": (ci, [c_vp, ctypes.POINTER(c_vp), ci, ctypes.POINTER(c_vp),
                            ctypes.POINTER(c_vp), c_vp, i64, i64, i64]),
     "dali_argsort_f32": (ci, [c_vp, c_vp, i64, i64, i64, ci, c_vp]),
+    "dali_roc_hist_f32": (ci, [c_vp, c_vp, i64, i64, i64, c_i32p, c_i32p, ci, ctypes.c_float, ctypes.c_float,
+                               c_vp, c_vp]),
     "dali_mrfuse_f32": (ci, [c_vp, ctypes.POINTER(c_vp), ci, i64, i64, i64, ci, ci, ctypes.c_float, c_vp, i64,
                              c_vp, c_vp, c_vp]),
     "dali_eval_rank_f32": (ci, [c_vp, c_vp, i64, i64, i64, c_i32p, c_i32p, c_i32p, c_i32p, ci, ci,

@@ -1549,6 +1549,36 @@ int dali_argsort_f32(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int
   return DALI_OK;
 }
 
+int dali_roc_hist_f32(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t ld, const int32_t *q_pid,
+                      const int32_t *g_pid, int nbins, float lo, float hi, uint64_t *pos_hist,
+                      uint64_t *neg_hist) {
+  DeviceGuard dg;
+  int rc = dg.enter(ctx);
+  if (rc) return rc;
+  if (Q < 0 || G < 0 || ld < G || nbins < 2 || nbins > (1 << 24) || !(hi > lo) || !pos_hist || !neg_hist ||
+      (Q && G && (!dist || !q_pid || !g_pid)))
+    return set_err(ctx, DALI_ERR_INVALID, "roc_hist: bad arguments (2 <= nbins <= 2^24, hi > lo)");
+  std::memset(pos_hist, 0, sizeof(uint64_t) * nbins);
+  std::memset(neg_hist, 0, sizeof(uint64_t) * nbins);
+  if (Q == 0 || G == 0) return DALI_OK;
+  const float *dd;
+  int64_t ldd;
+  if ((rc = stage_in(ctx, WS_STAGE_A, dist, Q, G, ld, &dd, &ldd))) return rc;
+  void *lab = nullptr, *hist = nullptr;
+  if ((rc = ws_ensure(ctx, WS_STAGE_B, sizeof(int32_t) * (Q + G), &lab))) return rc;
+  if ((rc = ws_ensure(ctx, WS_STAGE_C, sizeof(uint64_t) * 2 * nbins, &hist))) return rc;
+  int32_t *dq = static_cast<int32_t *>(lab), *dgp = dq + Q;
+  DALI_CUDA_OK(ctx, cudaMemcpyAsync(dq, q_pid, sizeof(int32_t) * Q, cudaMemcpyHostToDevice, ctx->stream));
+  DALI_CUDA_OK(ctx, cudaMemcpyAsync(dgp, g_pid, sizeof(int32_t) * G, cudaMemcpyHostToDevice, ctx->stream));
+  DALI_CUDA_OK(ctx, cudaMemsetAsync(hist, 0, sizeof(uint64_t) * 2 * nbins, ctx->stream));
+  unsigned long long *ph = static_cast<unsigned long long *>(hist), *nh = ph + nbins;
+  if ((rc = launch_roc_hist(ctx, dd, Q, G, ldd, dq, dgp, nbins, lo, hi, ph, nh))) return rc;
+  DALI_CUDA_OK(ctx, cudaMemcpyAsync(pos_hist, ph, sizeof(uint64_t) * nbins, cudaMemcpyDeviceToHost, ctx->stream));
+  DALI_CUDA_OK(ctx, cudaMemcpyAsync(neg_hist, nh, sizeof(uint64_t) * nbins, cudaMemcpyDeviceToHost, ctx->stream));
+  DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return DALI_OK;
+}
+
 int dali_mrfuse_f32(dali_ctx *ctx, const float *const *scores, int n, int64_t Q, int64_t G,
                     int64_t ld, int topk, int use_columns, float killscale, double *fused,
                     int64_t ld_out, double *fit_opt, float *small_opt, double *weights_opt) {

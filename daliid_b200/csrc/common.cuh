@@ -315,6 +315,10 @@ int launch_mrfuse(dali_ctx *ctx, const float *const *s, int n, int64_t Q, int64_
 // sortrows.cu
 int launch_argsort_rows(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t ld,
                         int descending, int32_t *idx_out);
+// roc.cu
+int launch_roc_hist(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t ld, const int32_t *qpid,
+                    const int32_t *gpid, int nbins, float lo, float hi, unsigned long long *pos_hist,
+                    unsigned long long *neg_hist);
 // fuse.cu
 int launch_fuse(dali_ctx *ctx, const float *const *d_ptrs_dev, int n, const float *const *wq_dev,
                 const float *const *wg_dev, float *out, int64_t Q, int64_t G, int64_t ld);

@@ -1,9 +1,12 @@
 """Verification metric of the reference's dead ROC branch (SURVEY 8f row N3,
 evaluateCleanATModels.py:276-292).
 
-NOT part of the hot path and NOT a hand-written kernel: the ROC over all Q x G pairs is the
-stock-library formulation on the device (``torch.sort`` over the scores + cumulative sums).  It is
-kept in its own module so that ``metrics.py`` stays "ctypes only, no arithmetic".
+``roc_curve_binned`` is the kernel path (``csrc/roc.cu`` through ``dali_roc_hist_f32``): one
+streaming pass over the distance matrix histograms the scores of the two classes; the suffix sums
+are exact points of the ROC at ``bins`` thresholds -- no sort, no Q x G temporaries.
+``roc_curve_pairs`` is the stock-library formulation (``torch.sort`` + cumulative sums) that
+reproduces scikit-learn's output element for element; it is the checker of the kernel path, not a
+kernel.
 """
 from __future__ import annotations
 
@@ -11,7 +14,7 @@ import numpy as np
 
 from .metrics import canonicalize_labels
 
-__all__ = ["roc_curve_pairs"]
+__all__ = ["roc_curve_pairs", "roc_curve_binned"]
 
 
 def roc_curve_pairs(distmat, q_pids, g_pids, device=None):
@@ -55,3 +58,35 @@ def roc_curve_pairs(distmat, q_pids, g_pids, device=None):
     fpr = fps / fps[-1]
     tpr = tps / tps[-1]
     return fpr.cpu().numpy(), tpr.cpu().numpy(), thr.cpu().numpy()
+
+
+def roc_curve_binned(distmat, q_pids, g_pids, bins=65536, lo=0.0, hi=1.0):
+    """ROC of evaluateCleanATModels.py:276-292 (label = same identity, score = ``1.0 - distmat/2.0``)
+    at ``bins`` thresholds, by the histogram kernel (``dali_roc_hist_f32``).
+
+    Returns ``(fpr, tpr, thresholds)`` with ``bins + 1`` points, thresholds descending like
+    scikit-learn's: point 0 is ``(0, 0, inf)``, point ``i`` counts the scores in bins ``>= bins - i``.
+    Every point lies exactly on the curve ``sklearn.metrics.roc_curve`` returns (its counts are the
+    exact numbers of positives / negatives at that threshold); ``thresholds[i]`` is the lower edge
+    of the bin, ``lo + (bins - i) * (hi - lo) / bins``.  Scores outside ``[lo, hi]`` fall into the
+    end bins (cosine distances in [0, 2] give scores in [0, 1])."""
+    import ctypes
+
+    from . import _lib
+    from ._lib import as_matrix, c_vp, p_i32
+    d = as_matrix(distmat, np.float32, "distmat")
+    Q, G = d.shape
+    qp, gp = canonicalize_labels(q_pids, g_pids)
+    if qp.shape[0] != Q or gp.shape[0] != G:
+        raise ValueError("label arrays do not match the distance matrix shape")
+    ctx = _lib.get_ctx(d.device)
+    ctx.attach_torch_stream()
+    pos = np.zeros(bins, dtype=np.uint64)
+    neg = np.zeros(bins, dtype=np.uint64)
+    ctx.check(ctx.lib.dali_roc_hist_f32(ctx.h, c_vp(d.ptr), Q, G, max(d.ld, 1), p_i32(qp), p_i32(gp), int(bins),
+                                        ctypes.c_float(lo), ctypes.c_float(hi), c_vp(pos.ctypes.data),
+                                        c_vp(neg.ctypes.data)))
+    tps = np.concatenate([[0.0], np.cumsum(pos[::-1].astype(np.float64))])
+    fps = np.concatenate([[0.0], np.cumsum(neg[::-1].astype(np.float64))])
+    thr = np.concatenate([[np.inf], lo + np.arange(bins - 1, -1, -1, dtype=np.float64) * ((hi - lo) / bins)])
+    return fps / max(fps[-1], 1.0), tps / max(tps[-1], 1.0), thr

@@ -259,6 +259,17 @@ int dali_mrfuse_f32(dali_ctx *ctx, const float *const *scores, int n, int64_t Q,
                     int64_t ld, int topk, int use_columns, float killscale, double *fused,
                     int64_t ld_out, double *fit_opt, float *small_opt, double *weights_opt);
 
+/* ROC over all Q x G pairs without a sort: the verification branch of
+ * evaluateCleanATModels.py:276-292 (label = same identity, score = 1.0 - distmat / 2.0 in fp32,
+ * sklearn.metrics.roc_curve).  One streaming pass histograms the scores of the two classes over
+ * nbins uniform bins of [lo, hi] (bin = floor((score - lo) * nbins / (hi - lo)), clamped; NaN -> bin
+ * 0); the suffix sums of pos_hist / neg_hist are exact points (tps, fps) of the curve at the nbins
+ * thresholds "smallest score of bin b".  dist: fp32 [Q, ld], host or device; labels: HOST int32;
+ * pos_hist, neg_hist: HOST uint64 [nbins]. */
+int dali_roc_hist_f32(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t ld,
+                      const int32_t *q_pid, const int32_t *g_pid, int nbins, float lo, float hi,
+                      uint64_t *pos_hist, uint64_t *neg_hist);
+
 /* ---- (e) gallery-sharded building blocks ------------------------------------ */
 /* One process per GPU holds all Q queries and a contiguous gallery slab
  * [g0, g0+Gs).  Labels of the WHOLE gallery are replicated (small).  The host side

@@ -238,3 +238,39 @@ def test_rank_by_similarity_matches_reference_arithmetic():
         topK = int(N * 0.1)
         assert len(set(order[:topK].tolist()) ^ set(ref[:topK].tolist())) <= 4
         assert (lab[order[:200]] == 7).float().mean() > 0.9
+
+
+def test_roc_histogram_kernel_lies_on_the_exact_curve():
+    """csrc/roc.cu: the binned ROC (one streaming pass, no sort) against (1) numpy's histogram of the
+    same fp32 scores -- bit-exact counts -- and (2) the exact curve of the stock formulation that
+    equals scikit-learn's: every binned point is a point of the exact step curve."""
+    from daliid_b200 import metrics, synth, verification
+    qf, gf, qp, gp, qc, gc = synth.make_config("small", device="cuda")
+    d = metrics.compute_distance_matrix(qf, gf, "cosine")
+    bins = 4096
+    fpr, tpr, thr = verification.roc_curve_binned(d, qp, gp, bins=bins)
+    dn = d.cpu().numpy()
+    score = (np.float32(1.0) - dn * np.float32(0.5)).astype(np.float32)
+    y = (qp[:, None] == gp[None, :])
+    b = np.clip(np.floor(score.astype(np.float32) * np.float32(bins)).astype(np.int64), 0, bins - 1)
+    pos = np.bincount(b[y], minlength=bins)
+    neg = np.bincount(b[~y], minlength=bins)
+    assert np.array_equal(np.cumsum(pos[::-1]) / max(pos.sum(), 1), tpr[1:])
+    assert np.array_equal(np.cumsum(neg[::-1]) / max(neg.sum(), 1), fpr[1:])
+    assert fpr[0] == 0 and tpr[0] == 0 and fpr[-1] == 1 and tpr[-1] == 1 and np.isinf(thr[0])
+    # on the exact curve: at the smallest score of a bin, the exact (fpr, tpr) equals the binned point
+    efpr, etpr, ethr = verification.roc_curve_pairs(d, qp, gp)
+    for i in (bins // 2 + 7, bins // 2 + 40, bins // 2 + 200):
+        sel = b >= bins - i
+        if not sel.any():
+            continue
+        t = score[sel].min()
+        exact_tpr = (y & (score >= t)).sum() / y.sum()
+        exact_fpr = (~y & (score >= t)).sum() / (~y).sum()
+        assert exact_tpr == tpr[i] and exact_fpr == fpr[i]
+    # and host matrices give the same histogram
+    f2, t2, _ = verification.roc_curve_binned(dn, qp, gp, bins=bins)
+    assert np.array_equal(f2, fpr) and np.array_equal(t2, tpr)
+    auc_b = np.trapezoid(tpr, fpr)
+    auc_e = np.trapezoid(etpr, efpr)
+    assert abs(auc_b - auc_e) < 1e-3
