@@ -94,6 +94,7 @@ _SIGNATURES = {
                                     c_i32p, ci, ci, ci, ci, ci, c_f32p, c_f64p, c_f64p, c_i32p,
                                     c_i64p, c_vp, i64]),
     "dali_topk_f32": (ci, [c_vp, c_vp, i64, i64, i64, ci, ci, c_vp, c_vp, c_vp]),
+    "dali_topk_merge_f32": (ci, [c_vp, c_vp, c_vp, ci, i64, ci, ci, c_vp, c_vp]),
     "dali_topk_features_f32": (ci, [c_vp, c_vp, i64, c_vp, i64, i64, ci, ci, ci, ci, ci,
                                     ctypes.c_int32, c_vp, c_vp]),
     "dali_rank_plan_create": (ci, [c_vp, c_i32p, c_i32p, c_i32p, c_i32p, i64, i64,

@@ -1487,6 +1487,18 @@ int dali_topk_f32(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_
   return topk_out(ctx, dd, Q, G, ldd, k, largest, ids, 0, d_out, i_out);
 }
 
+int dali_topk_merge_f32(dali_ctx *ctx, const float *vals, const int32_t *ids, int parts, int64_t Q, int k,
+                        int largest, float *d_out, int32_t *i_out) {
+  DeviceGuard dg;
+  int rc = dg.enter(ctx);
+  if (rc) return rc;
+  if (!vals || !ids || !d_out || !i_out || parts < 1 || Q < 0 || k < 1 || k > 32)
+    return set_err(ctx, DALI_ERR_INVALID, "topk_merge: bad arguments (1 <= k <= 32)");
+  if (!is_device_ptr(vals) || !is_device_ptr(ids) || !is_device_ptr(d_out) || !is_device_ptr(i_out))
+    return set_err(ctx, DALI_ERR_INVALID, "topk_merge: device buffers only");
+  return launch_topk_merge(ctx, vals, ids, parts, Q, k, largest, d_out, i_out);
+}
+
 // a7 from features, materialised: the gallery is processed in one slab through an internal
 // [band, G] matrix per query band (bounded workspace); each band owns its rows.
 int dali_rerank_f32(dali_ctx *ctx, const float *qg, int64_t ld_qg, const float *qq, int64_t ld_qq,

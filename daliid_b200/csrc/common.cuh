@@ -301,6 +301,8 @@ int launch_rank_finalize(dali_ctx *ctx, const dali_rank_plan *plan, const uint32
 int launch_topk(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t ld, int k,
                 int largest, const int32_t *col_ids, int32_t id_base, float *d_out,
                 int32_t *i_out);
+int launch_topk_merge(dali_ctx *ctx, const float *vals, const int32_t *ids, int parts, int64_t Q, int k,
+                      int largest, float *d_out, int32_t *i_out);
 int launch_topk_compact(dali_ctx *ctx, uint64_t *cand, int32_t *cand_cnt, float *thr, int64_t Q,
                         int cap, int k, int largest, int fixed_cnt, int32_t *overflow, float *d_out,
                         int32_t *i_out, int32_t *row_flags = nullptr);

@@ -311,7 +311,66 @@ topk_compact_warp_kernel(uint64_t *__restrict__ cand, int32_t *__restrict__ cnt,
   }
 }
 
+// Merge of per-shard top-k lists (gallery-sharded 1:N identification): vals / ids are
+// [parts][Q][k] as torch.distributed.all_gather_into_tensor leaves them; one warp per query row
+// streams its parts * k candidates through the same register-resident insertion as above.  Padded
+// entries (id -1) lose against every real candidate.
+__global__ void __launch_bounds__(256)
+topk_merge_warp_kernel(const float *__restrict__ vals, const int32_t *__restrict__ ids, int parts, int64_t Q,
+                       int k, int largest, float *__restrict__ d_out, int32_t *__restrict__ i_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  const uint32_t flip = largest ? 0xFFFFFFFFu : 0u;
+  constexpr uint64_t kNone = ~0ull;
+  uint64_t best = kNone, kth = kNone;
+  const int n = parts * k;
+  for (int base = 0; base < n; base += 32) {
+    uint64_t x = kNone;
+    if (base + lane < n) {
+      const int part = (base + lane) / k, j = (base + lane) - part * k;
+      const int64_t at = (static_cast<int64_t>(part) * Q + q) * k + j;
+      const int32_t id = __ldg(ids + at);
+      if (id >= 0) x = composite(dist_key(__ldg(vals + at)) ^ flip, static_cast<uint32_t>(id));
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, x < kth);
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const uint64_t v = __shfl_sync(0xffffffffu, x, src);
+      if (v < kth) {
+        const int pos = __popc(__ballot_sync(0xffffffffu, best <= v));
+        const uint64_t up = __shfl_up_sync(0xffffffffu, best, 1);
+        if (lane == pos) best = v;
+        else if (lane > pos && lane < k) best = up;
+        kth = __shfl_sync(0xffffffffu, best, k - 1);
+      }
+    }
+  }
+  if (lane < k) {
+    float dv = largest ? -INFINITY : INFINITY;
+    int32_t iv = -1;
+    if (best != kNone) {
+      dv = key_to_dist(static_cast<uint32_t>(best >> 32) ^ flip);
+      iv = static_cast<int32_t>(static_cast<uint32_t>(best));
+    }
+    d_out[q * k + lane] = dv;
+    i_out[q * k + lane] = iv;
+  }
+}
+
 }  // namespace
+
+int launch_topk_merge(dali_ctx *ctx, const float *vals, const int32_t *ids, int parts, int64_t Q, int k,
+                      int largest, float *d_out, int32_t *i_out) {
+  if (Q == 0) return DALI_OK;
+  if (k < 1 || k > 32 || parts < 1) return set_err(ctx, DALI_ERR_INVALID, "top-k merge: 1 <= k <= 32");
+  KTimer t(ctx, DALI_K_TOPK);
+  topk_merge_warp_kernel<<<static_cast<unsigned>((Q + 7) / 8), 256, 0, ctx->stream>>>(vals, ids, parts, Q, k, largest,
+                                                                                      d_out, i_out);
+  DALI_CUDA_OK(ctx, cudaGetLastError());
+  return DALI_OK;
+}
 
 int launch_topk_compact(dali_ctx *ctx, uint64_t *cand, int32_t *cand_cnt, float *thr, int64_t Q,
                         int cap, int k, int largest, int fixed_cnt, int32_t *overflow, float *d_out,

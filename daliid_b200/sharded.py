@@ -384,12 +384,27 @@ def topk_features_sharded(qf, gf_slab, g0, k=20, metric="cosine", precision=metr
     world, _ = _world(group)
     if world == 1:
         return vals, ids
-    vals = torch.as_tensor(vals)
-    ids = torch.as_tensor(ids)
+    vals = torch.as_tensor(vals).contiguous()
+    ids = torch.as_tensor(ids).contiguous()
+    if isinstance(ops, CudaOps) and k <= 32 and vals.is_cuda:
+        # one all-gather per array straight into [world, Q, k], merged by one warp per query
+        # (dali_topk_merge_f32): no concatenation copies, no one-CTA-per-row selection over 8 k columns
+        Q = vals.shape[0]
+        gv = torch.empty((world, Q, k), dtype=vals.dtype, device=vals.device)
+        gi = torch.empty((world, Q, k), dtype=ids.dtype, device=ids.device)
+        dist.all_gather_into_tensor(gv, vals, group=group)
+        dist.all_gather_into_tensor(gi, ids, group=group)
+        out_v = torch.empty_like(vals)
+        out_i = torch.empty_like(ids)
+        ctx = ops.ctx
+        ctx.attach_torch_stream()
+        ctx.check(ctx.lib.dali_topk_merge_f32(ctx.h, c_vp(gv.data_ptr()), c_vp(gi.data_ptr()), world, Q, int(k),
+                                              1 if largest else 0, c_vp(out_v.data_ptr()), c_vp(out_i.data_ptr())))
+        return out_v, out_i
     vs = [torch.empty_like(vals) for _ in range(world)]
     js = [torch.empty_like(ids) for _ in range(world)]
-    dist.all_gather(vs, vals.contiguous(), group=group)
-    dist.all_gather(js, ids.contiguous(), group=group)
+    dist.all_gather(vs, vals, group=group)
+    dist.all_gather(js, ids, group=group)
     cand_v = torch.cat(vs, dim=1).contiguous()
     cand_i = torch.cat(js, dim=1).contiguous()
     # padded entries (id -1, value +-inf) lose every comparison against real candidates

@@ -217,6 +217,13 @@ int dali_topk_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float
                            int64_t D, int metric, int precision, int normalize, int k,
                            int largest, int32_t g_base, float *d_out, int32_t *i_out);
 
+/* Merge of per-shard top-k lists (gallery-sharded identification): vals / ids are DEVICE arrays
+ * [parts][Q][k] (the layout an all-gather of the per-rank [Q,k] results produces), ids global
+ * gallery ids (-1 = padding).  d_out / i_out: DEVICE [Q,k], the k best over all parts in the same
+ * order as dali_topk_f32 (value, then id).  k <= 32.  Stream-ordered, no host synchronisation. */
+int dali_topk_merge_f32(dali_ctx *ctx, const float *vals, const int32_t *ids, int parts, int64_t Q,
+                        int k, int largest, float *d_out, int32_t *i_out);
+
 /* ---- next row N1: k-reciprocal re-ranking ------------------------------------- */
 /* out[Q,G] = torchreid.utils.re_ranking(qg, qq, gg, k1, k2, lambda_value): the hook the
  * reference keeps commented out at validateModels.py:49-53, evaluate.py:294-298,

@@ -274,3 +274,29 @@ def test_roc_histogram_kernel_lies_on_the_exact_curve():
     auc_b = np.trapezoid(tpr, fpr)
     auc_e = np.trapezoid(etpr, efpr)
     assert abs(auc_b - auc_e) < 1e-3
+
+
+def test_topk_merge_of_gallery_parts_equals_whole_topk():
+    """dali_topk_merge_f32 (the merge step of the gallery-sharded 1:N identification): per-part fused
+    top-k lists stacked as an all-gather leaves them, merged by one warp per query, equal the top-k
+    over the whole gallery bit for bit -- including duplicated gallery rows (ties by gallery id)
+    and a part shorter than k (padding ids -1)."""
+    import ctypes
+    from daliid_b200 import _lib, metrics
+    from daliid_b200._lib import c_vp
+    g = torch.Generator().manual_seed(4)
+    qf = torch.randn(500, 96, generator=g).cuda()
+    gf = torch.randn(3007, 96, generator=g).cuda()
+    gf[2000:2100] = gf[100:200]                    # exact ties across parts
+    k = 20
+    ev, ei = metrics.topk_features(qf, gf, k=k)
+    bounds = [(0, 1500), (1500, 2995), (2995, 3007)]   # the last part has 12 < k rows
+    vs, js = zip(*[metrics.topk_features(qf, gf[a:b].contiguous(), k=k, g_base=a) for a, b in bounds])
+    gv, gi = torch.stack(vs).contiguous(), torch.stack(js).contiguous()
+    assert int((gi[2] == -1).sum()) == 500 * (k - 12)
+    out_v, out_i = torch.empty_like(ev), torch.empty_like(ei)
+    ctx = _lib.get_ctx(0)
+    ctx.attach_torch_stream()
+    ctx.check(ctx.lib.dali_topk_merge_f32(ctx.h, c_vp(gv.data_ptr()), c_vp(gi.data_ptr()), 3, 500, k, 0,
+                                          c_vp(out_v.data_ptr()), c_vp(out_i.data_ptr())))
+    assert torch.equal(out_i, ei) and torch.equal(out_v, ev)
