@@ -127,6 +127,7 @@ struct FusedArgs {
 }  // namespace dali
 
 struct dali_rank_plan;
+namespace dali { struct HostStager; }
 
 struct dali_ctx {
   int device = 0;
@@ -158,6 +159,7 @@ struct dali_ctx {
   cudaEvent_t h2d_ev0 = nullptr, h2d_ev1 = nullptr;
   int h2d_ev_streams = 0;        // setting the pending event pair was recorded with (0: none)
   cudaEvent_t handover = nullptr;  // dali_ctx_set_stream: the new stream waits for the old one
+  dali::HostStager *stager = nullptr;  // pageable host operands: threaded copy into pinned slots
   // timing
   bool timing = false;
   int t_launches[DALI_K_COUNT_] = {0};
