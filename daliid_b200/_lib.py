@@ -13,7 +13,8 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdaliid_b200.so")
+# DALIID_B200_LIB: another build of the same library (kernel-variant probes under tests/probes)
+LIB_PATH = os.environ.get("DALIID_B200_LIB") or os.path.join(_HERE, "csrc", "libdaliid_b200.so")
 
 # ---- constants mirrored from include/daliid_b200.h -------------------------------
 ABI_VERSION = 1

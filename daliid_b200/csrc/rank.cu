@@ -9,6 +9,7 @@
 // label reads in the hot loop (junk items are all inside the query's match list).
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -446,6 +447,402 @@ rank_count_v2_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
   }
 }
 
+// ------------------------------ count, v3 -----------------------------------
+// Register-resident counting for queries with few positives (<= 64 thresholds per CTA; the Market
+// shapes).  What bounded v2 was the shared-memory pipe: a random 16-bit table lookup (~3.4
+// wavefronts per warp and element) plus the read and the write of a private counter (2 + 2).  v3
+// keeps the lookup and drops the counters:
+//   * the table bin of an element is ONE fused multiply-add on the fp32 distance: t = d * (-scale)
+//     + C lands in [2^23, 2^24), where the low mantissa bits ARE the rounded bin, two FMNMX clamp it
+//     (and send NaN above every threshold), one LEA forms the shared-memory address.  The map is
+//     monotone in d and the thresholds are binned by the same expression, so an element in a bin
+//     without thresholds is ordered exactly against all of them; an element that shares its bin with
+//     a threshold takes the exact path (64-bit composite compares, ties by gallery id);
+//   * the table entry is base = #{thresholds <= element}; the element must be counted for the
+//     thresholds base..n-1, i.e. it contributes the bit mask ~0 << base.  The masks of 8 elements are
+//     added into BIT-SLICED per-thread counters (plane k holds bit k of 32 / 64 counters) with a
+//     carry-save adder tree: 14 LOP3 + 2 per further plane for 8 elements and 32 thresholds, all in
+//     registers, no shared-memory traffic;
+//   * at the end a warp transposes its planes (lane i then holds the bits of threshold i of all 32
+//     lanes: popc) and adds 32 / 64 totals to the CTA's histogram; hist[i] is count_below(T[i])
+//     directly, no prefix sum.
+// A CTA whose thresholds are not all finite (NaN rows, infinite distances) counts its row with the
+// generic compare loop instead: same results, slow, rare.
+constexpr int kV3Chunk = 64;
+#ifndef DALI_V3_PREFETCH
+#define DALI_V3_PREFETCH 1
+#endif
+#ifndef DALI_V3_MINB
+#define DALI_V3_MINB 5  // resident 256-thread CTAs per SM the tight variant is compiled for
+#endif
+constexpr uint32_t kV3Magic = 0x4B000000u;  // 2^23 as fp32 bits
+
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t a, uint32_t s) {  // s >= 32 -> 0
+  uint32_t d;
+  asm("shl.b32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(s));
+  return d;
+}
+
+// 32 x 32 bit transpose across the lanes of a warp: on return bit j of lane i = bit i of lane j
+__device__ __forceinline__ uint32_t warp_bit_transpose(uint32_t x, int lane) {
+#pragma unroll
+  for (int j = 16; j >= 1; j >>= 1) {
+    const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu
+                     : j == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+    x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y & m) << j));
+  }
+  return x;
+}
+
+template <int NW, int PL>
+struct SlicedCounters {
+  uint32_t p[PL][NW];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int k = 0; k < PL; ++k)
+#pragma unroll
+      for (int w = 0; w < NW; ++w) p[k][w] = 0u;
+  }
+  // adds eight 0/1 vectors (one bit per threshold)
+  __device__ __forceinline__ void add8(const uint32_t (&m)[8][NW]) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      uint32_t ones = p[0][w], twos = p[1][w], fours = p[2][w];
+      const uint32_t tA = lop3_maj(ones, m[0][w], m[1][w]);
+      ones = lop3_xor3(ones, m[0][w], m[1][w]);
+      const uint32_t tB = lop3_maj(ones, m[2][w], m[3][w]);
+      ones = lop3_xor3(ones, m[2][w], m[3][w]);
+      const uint32_t fA = lop3_maj(twos, tA, tB);
+      twos = lop3_xor3(twos, tA, tB);
+      const uint32_t tC = lop3_maj(ones, m[4][w], m[5][w]);
+      ones = lop3_xor3(ones, m[4][w], m[5][w]);
+      const uint32_t tD = lop3_maj(ones, m[6][w], m[7][w]);
+      ones = lop3_xor3(ones, m[6][w], m[7][w]);
+      const uint32_t fB = lop3_maj(twos, tC, tD);
+      twos = lop3_xor3(twos, tC, tD);
+      uint32_t carry = lop3_maj(fours, fA, fB);
+      fours = lop3_xor3(fours, fA, fB);
+      p[0][w] = ones; p[1][w] = twos; p[2][w] = fours;
+#pragma unroll
+      for (int k = 3; k < PL; ++k) {
+        const uint32_t t = p[k][w] & carry;
+        p[k][w] ^= carry;
+        carry = t;
+      }
+    }
+  }
+};
+
+template <int LOG2NB, int THREADS, int PL, bool FUSED, bool TIGHT = false>
+__global__ void __launch_bounds__(THREADS, TIGHT ? DALI_V3_MINB * 256 / THREADS : 1)
+rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int64_t Gs,
+                     const int64_t *__restrict__ off, const int32_t *__restrict__ nvalid,
+                     const int32_t *__restrict__ gid, const uint32_t *__restrict__ keys,
+                     int32_t *__restrict__ counts, int nsplit, FusedOut fo) {
+  constexpr int NB = 1 << LOG2NB;  // bins 0 .. NB; thresholds fall into 2 .. NB-2
+  constexpr int NE = NB + 8;       // table entries (a multiple of 8)
+  constexpr int kJunkCap = 64;
+  __shared__ uint64_t Tu[kV3Chunk + kJunkCap];  // unsorted thresholds, then the junk composites
+  __shared__ uint64_t T[kV3Chunk + 1];          // sorted, T[n] = sentinel above every composite
+  __shared__ float Tf[kV3Chunk + 1];            // sorted thresholds as distances, Tf[n] = +inf
+  __shared__ uint32_t Tg[kV3Chunk + 1];         // their gallery ids
+  __shared__ uint32_t hist[kV3Chunk + 1];
+  __shared__ uint16_t orig[kV3Chunk];
+  __shared__ uint16_t tb[kV3Chunk + 2];
+  __shared__ double s_term[FUSED ? kV3Chunk : 1];
+  __shared__ __align__(16) uint16_t lut[NE];
+
+  const int64_t q = blockIdx.x;
+  const int chunk = blockIdx.y;
+  const int tid = threadIdx.x;
+  const float *row = dist + q * ld;
+
+  // column range of this split, in multiples of 4 columns; [cv0, cv0 + 4 nvec) is its 16-byte
+  // aligned part, dealt out as float4 vectors: iteration `it` gives a thread the vectors
+  // tid + 2 it THREADS and that + THREADS.  Vectors beyond the range read as NaN, which sorts above
+  // every threshold and so counts for none.
+  const int64_t per = nsplit == 1 ? ((Gs + 3) & ~int64_t(3)) : ((((Gs + nsplit - 1) / nsplit) + 3) & ~int64_t(3));
+  const int64_t c0r = per * static_cast<int64_t>(blockIdx.z);
+  const int64_t c0 = c0r < Gs ? c0r : Gs;
+  const int64_t c1 = (c0 + per) < Gs ? (c0 + per) : Gs;
+  const int mis = static_cast<int>((reinterpret_cast<uintptr_t>(row + c0) >> 2) & 3);
+  int head = (4 - mis) & 3;
+  if (head > c1 - c0) head = static_cast<int>(c1 - c0);
+  const int64_t cv0 = c0 + head;
+  const int nvec = static_cast<int>((c1 - cv0) >> 2);
+  const int tail = static_cast<int>(c1 - cv0) & 3;
+  const int niter = (nvec + 2 * THREADS - 1) / (2 * THREADS);
+  const float qnan = __int_as_float(0x7FFFFFFF);
+  const float *pv = row + cv0 + 4 * tid;  // this thread's next pair of vectors
+  int rem = nvec - tid;                   // vectors left from pv on, in steps of THREADS
+  auto load2 = [&](float4 &x0, float4 &x1) {
+    x0 = rem > 0 ? ld_stream_f4(pv) : make_float4(qnan, qnan, qnan, qnan);
+    x1 = rem > THREADS ? ld_stream_f4(pv + 4 * THREADS) : make_float4(qnan, qnan, qnan, qnan);
+    pv += 8 * THREADS;
+    rem -= 2 * THREADS;
+  };
+  // the first vectors are requested before anything else: the prologue below (three dependent
+  // global loads, a sort, the table) runs under their latency
+  float4 xa0, xa1, xb0, xb1;
+  load2(xa0, xa1);
+
+  const int nv = nvalid[q];
+  if (FUSED && nv == 0) {
+    if (tid == 0) {
+      fo.ap[q] = 0.f;
+      fo.first_rank[q] = -1;
+    }
+    return;
+  }
+  if (chunk * kV3Chunk >= nv) return;  // uniform exit
+  const int n = min(kV3Chunk, nv - chunk * kV3Chunk);
+  const int64_t o = off[q] + static_cast<int64_t>(chunk) * kV3Chunk;
+  // FUSED: the junk matches (same identity, same camera) follow the valid ones in the match list
+  const int m = FUSED ? static_cast<int>(off[q + 1] - off[q]) : n;
+  const int nj = min(m - n, kJunkCap);  // staged; more than that are read from global memory later
+
+  // 1. thresholds, sorted by counting (composites are distinct: gallery ids differ)
+  if (tid < n + nj) {
+    const uint32_t g = static_cast<uint32_t>(__ldg(gid + o + tid));
+    const uint32_t k = FUSED ? dist_key(__ldg(row + g)) : __ldg(keys + o + tid);
+    Tu[tid] = composite(k, g);
+  }
+  if (tid <= kV3Chunk) hist[tid] = 0u;
+  __syncthreads();
+  {
+    constexpr int TPT = THREADS / kV3Chunk;  // threads per threshold (4 or 2), adjacent lanes
+    const int i = tid / TPT, part = tid % TPT;
+    const uint64_t c = Tu[i < n ? i : 0];
+    int pos = 0;
+    for (int u = part; u < n; u += TPT) pos += (Tu[u] < c) ? 1 : 0;
+#pragma unroll
+    for (int x = 1; x < TPT; x <<= 1) pos += __shfl_xor_sync(0xffffffffu, pos, x);
+    if (i < n && part == 0) {
+      T[pos] = c;
+      Tf[pos] = key_to_dist(static_cast<uint32_t>(c >> 32));
+      Tg[pos] = static_cast<uint32_t>(c);
+      orig[pos] = static_cast<uint16_t>(i);
+    }
+  }
+  if (tid == 0) {
+    T[n] = ~0ull;
+    Tf[n] = __int_as_float(0x7F800000);
+    Tg[n] = 0xFFFFFFFFu;
+  }
+  __syncthreads();
+
+  // 2. the bin map: u = sat(C - d s) in [0, 1] (NaN -> 0: above every threshold), bin = round(u NB)
+  // read off the mantissa of u NB + 2^23.  hi -> bin 2, lo -> bin NB - 2; monotone in d whatever s
+  // is, so only the bins' fineness depends on the approximate reciprocals.  s is capped so that C
+  // keeps a few bits below one bin (thresholds that nearly coincide relative to their size then
+  // share bins, which is slower, not wrong).
+  const uint32_t klo = static_cast<uint32_t>(T[0] >> 32);
+  const uint32_t khi = static_cast<uint32_t>(T[n - 1] >> 32);
+  const float lo = Tf[0], hi = Tf[n - 1];
+  float sc = fminf(__fdividef(static_cast<float>(NB - 4) / static_cast<float>(NB), hi - lo),
+                   __fdividef(524288.0f / static_cast<float>(NB), fabsf(hi)));
+  sc = fminf(fmaxf(sc, 1.0e-30f), 1.0e30f);
+  const float nsc = -sc;
+  const float C = fmaf(hi, sc, 2.0f / static_cast<float>(NB));
+  // all thresholds finite (key images of -inf / +inf bound the finite range)
+  const bool fast = klo > 0x007FFFFFu && khi < 0xFF800000u;
+  auto bin_bits = [&](float d) -> uint32_t {  // fp32 bits of 2^23 + bin
+    float u;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(u) : "f"(d), "f"(nsc), "f"(C));
+    return __float_as_uint(fmaf(u, static_cast<float>(NB), 8388608.0f));
+  };
+  const uint32_t gbase = static_cast<uint32_t>(g0);
+
+  if (fast) {
+    // 3. table: entry(b) = #{thresholds in higher bins (= smaller distances)}, | 0x8000 if bin b
+    // holds thresholds itself.  tb[i] = bin of T[i], non-increasing; tb[-1] := NE, tb[n] := -1.
+    uint16_t *tbs = tb + 1;
+    if (tid < n) tbs[tid] = static_cast<uint16_t>(bin_bits(Tf[tid]) - kV3Magic);
+    __syncthreads();
+    // (a) every block of eight entries as if no threshold fell inside it: #{tb >= block start}
+    for (int blk = tid; blk < NE / 8; blk += THREADS) {
+      const int b0 = blk * 8;
+      int l = 0, h = n;  // first index with tb < b0
+      while (l < h) {
+        const int mid = (l + h) >> 1;
+        if (static_cast<int>(tbs[mid]) >= b0) l = mid + 1; else h = mid;
+      }
+      const uint32_t w = static_cast<uint32_t>(l) * 0x00010001u;
+      *reinterpret_cast<uint4 *>(lut + b0) = make_uint4(w, w, w, w);
+    }
+    __syncthreads();
+    // (b) the blocks that do hold thresholds, patched by the thresholds' threads: threshold i (the
+    // first of a run sharing its bin) writes its bin and the pure bins above it up to the next
+    // threshold's bin or the block's end; the last threshold of a block also the bins below it
+    if (tid < n) {
+      const int i = tid;
+      const int b = tbs[i];
+      const int up = i > 0 ? static_cast<int>(tbs[i - 1]) : NE;        // bin of the next smaller distance
+      const int dn = i + 1 < n ? static_cast<int>(tbs[i + 1]) : -1;    // bin of the next larger distance
+      const int bs = b & ~7, be = bs + 8;
+      if (up != b) {
+        lut[b] = static_cast<uint16_t>(i | 0x8000);
+        for (int x = b + 1; x < min(up, be); ++x) lut[x] = static_cast<uint16_t>(i);
+      }
+      if (dn < bs)
+        for (int x = bs; x < b; ++x) lut[x] = static_cast<uint16_t>(i + 1);
+    }
+    __syncthreads();
+
+    uint32_t lut_s = static_cast<uint32_t>(__cvta_generic_to_shared(lut)) - (kV3Magic << 1);
+    asm volatile("mov.u32 %0, %0;" : "+r"(lut_s));  // keep the constant folded into the base register
+    // table entry of an element: #{thresholds <= element}, bit 15 = "exact compare needed"
+    auto entry_of = [&](float d) -> uint32_t {
+      uint32_t e;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(lut_s + (bin_bits(d) << 1)));
+      return e;
+    };
+    // rare: the bin holds thresholds.  Thresholds and the element are finite here (NaN and the
+    // infinities never share a bin with a finite threshold), so (distance, gallery id) compares as
+    // floats; -0 == +0 as in dist_key.
+    auto exact = [&](uint32_t e, float d, uint32_t g) -> uint32_t {
+      uint32_t b = e & 0x7FFFu;
+      while (true) {
+        const float t = Tf[b];
+        if (t < d || (t == d && Tg[b] <= g)) ++b; else break;
+      }
+      return b;
+    };
+
+    auto run = [&](auto nw_tag) {
+      constexpr int NW = decltype(nw_tag)::value;
+      SlicedCounters<NW, PL> scnt;
+      scnt.clear();
+      uint32_t mk[8][NW];
+      auto to_mask = [&](int s, uint32_t b) {
+        mk[s][0] = shl_clamp(0xFFFFFFFFu, b);
+        if (NW == 2) mk[s][NW - 1] = shl_clamp(0xFFFFFFFFu, max(b, 32u) - 32u);
+      };
+      // eight elements: the vector at gallery id ga and the one THREADS vectors further on
+      auto group = [&](const float4 &x0, const float4 &x1, uint32_t ga) {
+        const float d[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        uint32_t e[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) e[s] = entry_of(d[s]);
+        if ((e[0] | e[1] | e[2] | e[3] | e[4] | e[5] | e[6] | e[7]) & 0x8000u) {
+#pragma unroll
+          for (int s = 0; s < 8; ++s)
+            if (e[s] & 0x8000u) e[s] = exact(e[s], d[s], ga + (s < 4 ? 0u : 4u * THREADS) + (s & 3));
+        }
+#pragma unroll
+        for (int s = 0; s < 8; ++s) to_mask(s, e[s]);
+        scnt.add8(mk);
+      };
+      uint32_t ga = gbase + static_cast<uint32_t>(cv0) + 4u * tid;
+#pragma unroll 1
+      for (int it = 0; it < niter; it += 2) {
+        load2(xb0, xb1);
+        group(xa0, xa1, ga);
+        load2(xa0, xa1);
+        if (it + 1 < niter) group(xb0, xb1, ga + 8u * THREADS);  // uniform
+        ga += 16u * THREADS;
+      }
+      // the unaligned head and the tail of the range (<= 3 columns each, one per thread)
+      if (head | tail) {  // uniform
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+#pragma unroll
+          for (int w = 0; w < NW; ++w) mk[s][w] = 0u;
+        auto put = [&](int s, float d, uint32_t g) {
+          uint32_t e = entry_of(d);
+          if (e & 0x8000u) e = exact(e, d, g);
+          to_mask(s, e);
+        };
+        if (tid < head) put(0, __ldg(row + c0 + tid), gbase + static_cast<uint32_t>(c0 + tid));
+        const int64_t ct0 = cv0 + 4 * static_cast<int64_t>(nvec);
+        if (tid < tail) put(1, __ldg(row + ct0 + tid), gbase + static_cast<uint32_t>(ct0 + tid));
+        scnt.add8(mk);
+      }
+
+      // 4. totals: transpose every plane across the warp, lane i then owns threshold 32 w + i
+      const int lane = tid & 31;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int k = 0; k < PL; ++k) total += static_cast<uint32_t>(__popc(warp_bit_transpose(scnt.p[k][w], lane))) << k;
+        if (32 * w + lane < n && total) atomicAdd(&hist[32 * w + lane], total);
+      }
+    };
+    if (n <= 32) run(std::integral_constant<int, 1>{}); else run(std::integral_constant<int, 2>{});
+  } else {
+    // generic: bucket histogram with exact compares, then a prefix sum
+    __shared__ uint32_t bh[kV3Chunk + 1];
+    if (tid <= kV3Chunk) bh[tid] = 0u;
+    __syncthreads();
+    for (int64_t c = c0 + tid; c < c1; c += THREADS) {
+      const uint64_t cc = composite(dist_key(__ldg(row + c)), gbase + static_cast<uint32_t>(c));
+      int b = 0;
+      while (T[b] <= cc) ++b;
+      atomicAdd(&bh[b], 1u);
+    }
+    __syncthreads();
+    if (tid < n) {
+      uint32_t sum = 0;
+      for (int b = 0; b <= tid; ++b) sum += bh[b];
+      hist[tid] = sum;
+    }
+  }
+  __syncthreads();
+
+  // 5. hist[i] = count_below(T[i]); scatter back to plan order
+  if (!FUSED) {
+    if (tid < n) {
+      const uint32_t below = hist[tid];
+      int32_t *dst = counts + o + orig[tid];
+      if (nsplit > 1) {
+        if (below) atomicAdd(dst, static_cast<int32_t>(below));
+      } else {
+        *dst = static_cast<int32_t>(below);
+      }
+    }
+    return;
+  }
+  // 6. FUSED: finish the query (as rank_count_v2_kernel / rank_finalize_kernel do).  T[] is sorted
+  // by rank; the junk matches ahead of a positive are subtracted; the AP terms k / rank_k are formed
+  // in double by the positives' threads, thread 0 then only runs torchreid's sequential float sum.
+  __shared__ int32_t s_first;
+  if (tid < n) {
+    const uint64_t ck = T[tid];
+    int below_junk = 0;
+    for (int u = 0; u < nj; ++u) below_junk += Tu[n + u] < ck ? 1 : 0;
+    for (int u = n + nj; u < m; ++u) {
+      const uint32_t g = static_cast<uint32_t>(__ldg(gid + o + u));
+      below_junk += composite(dist_key(__ldg(row + g)), g) < ck ? 1 : 0;
+    }
+    const int r = static_cast<int>(hist[tid]) - below_junk + 1;  // 1-based rank among kept items
+    if (tid == 0) s_first = r;
+    fo.ranks_sorted[o + tid] = r;
+    s_term[tid] = static_cast<double>(tid + 1) / static_cast<double>(r);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float sum = 0.f;  // torchreid Cython accumulation: float running sum, each term formed in double
+    for (int k = 0; k < n; ++k) sum = static_cast<float>(static_cast<double>(sum) + s_term[k]);
+    fo.ap[q] = sum / static_cast<float>(n);
+    const int fr = s_first;
+    fo.first_rank[q] = fr;
+    if (fr <= fo.max_rank) atomicAdd(fo.cmc_cnt + (fr - 1), 1);
+    atomicAdd(fo.cmc_cnt + fo.max_rank, 1);  // num_valid_q
+  }
+}
+
 // ------------------------------ finalize -----------------------------------
 constexpr int kFinThreads = 128;
 constexpr int kFinCap = 2048;  // matches staged in shared memory
@@ -616,6 +1013,45 @@ static int launch_v2(dali_ctx *ctx, dim3 grid, size_t smem, const dali_rank_plan
   return DALI_OK;
 }
 
+// v3 (register-resident bit-sliced counters): queries with <= 64 valid positives.  PL = number of
+// counter planes: a thread must see fewer than 2^PL elements.
+static bool v3_enabled() {
+  static const char *env = getenv("DALI_RANK_V3");
+  return !(env && atoi(env) == 0);
+}
+static int v3_threads() {
+  static const char *env = getenv("DALI_RANK_V3_THREADS");
+  return env && atoi(env) == 128 ? 128 : 256;
+}
+template <int THREADS, bool FUSED>
+static int launch_v3(dali_ctx *ctx, dim3 grid, const dali_rank_plan *plan, const float *dist, int64_t ld,
+                     int64_t g0, int64_t Gs, const uint32_t *keys, int32_t *counts, int nsplit, FusedOut fo) {
+  const int64_t per = (((Gs + nsplit - 1) / nsplit) + 3) & ~int64_t(3);
+  const int64_t per_thread = ((per / 4 + THREADS - 1) / THREADS) * 4 + 2;
+  static const char *env_nb = getenv("DALI_RANK_V3_LOG2NB");
+  const int lnb = env_nb ? atoi(env_nb) : 11;
+#define DALI_V3_LAUNCH(LNB, PL)                                                                      \
+  rank_count_v3_kernel<LNB, THREADS, PL, FUSED><<<grid, THREADS, 0, ctx->stream>>>(                  \
+      dist, ld, g0, Gs, plan->d_off, plan->d_nv, plan->d_gid, keys, counts, nsplit, fo)
+  // rows of the Market shapes (a thread sees < 128 elements): the variant compiled for five resident
+  // 256-thread CTAs per SM (48 registers) -- occupancy is worth 25 % here (0.094 -> 0.072 ms at C2)
+  static const char *env_tight = getenv("DALI_RANK_V3_TIGHT");
+  if (per_thread < (1 << 7)) {
+    if (!(env_tight && atoi(env_tight) == 0) && lnb == 11)
+      rank_count_v3_kernel<11, THREADS, 7, FUSED, true><<<grid, THREADS, 0, ctx->stream>>>(
+          dist, ld, g0, Gs, plan->d_off, plan->d_nv, plan->d_gid, keys, counts, nsplit, fo);
+    else if (lnb == 12) DALI_V3_LAUNCH(12, 7); else DALI_V3_LAUNCH(11, 7);
+  } else if (per_thread < (1 << 10)) {
+    if (lnb == 12) DALI_V3_LAUNCH(12, 10); else DALI_V3_LAUNCH(11, 10);
+  } else if (per_thread < (1 << 14)) {
+    if (lnb == 12) DALI_V3_LAUNCH(12, 14); else DALI_V3_LAUNCH(11, 14);
+  } else {
+    return set_err(ctx, DALI_ERR_UNSUPPORTED, "row segment too long for the counting kernel");
+  }
+#undef DALI_V3_LAUNCH
+  return DALI_OK;
+}
+
 int launch_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist, int64_t ld,
                       int64_t g0, int64_t Gs, const uint32_t *keys, int32_t *counts) {
   if (plan->M == 0 || plan->Q == 0) return DALI_OK;
@@ -647,7 +1083,12 @@ int launch_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *di
   const int nsplit = static_cast<int>(ns);
   dim3 grid(static_cast<unsigned>(plan->Q), nchunk, nsplit);
   KTimer t(ctx, DALI_K_RANK_COUNT);
-  if (use_v1) {
+  if (!use_v1 && !env_c && !env_t && plan->max_nv <= kV3Chunk && v3_enabled()) {
+    const int rc = v3_threads() == 128
+        ? launch_v3<128, false>(ctx, grid, plan, dist, ld, g0, Gs, keys, counts, nsplit, FusedOut{})
+        : launch_v3<256, false>(ctx, grid, plan, dist, ld, g0, Gs, keys, counts, nsplit, FusedOut{});
+    if (rc) return rc;
+  } else if (use_v1) {
     rank_count_kernel<<<grid, kCountThreads, 0, ctx->stream>>>(dist, ld, g0, Gs, plan->d_off,
                                                               plan->d_nv, plan->d_gid, keys, counts,
                                                               nsplit);
@@ -699,7 +1140,12 @@ int launch_rank_fused(dali_ctx *ctx, const dali_rank_plan *plan, const float *di
   FusedOut fo{ranks_sorted, ap, first_rank, cmc_cnt, max_rank};
   KTimer t(ctx, DALI_K_RANK_COUNT);
   const dim3 grid(static_cast<unsigned>(plan->Q), 1, 1);
-  if (bytec) {
+  if (plan->max_nv <= kV3Chunk && v3_enabled()) {
+    const int rc = v3_threads() == 128
+        ? launch_v3<128, true>(ctx, grid, plan, dist, ld, 0, G, nullptr, nullptr, 1, fo)
+        : launch_v3<256, true>(ctx, grid, plan, dist, ld, 0, G, nullptr, nullptr, 1, fo);
+    if (rc) return rc;
+  } else if (bytec) {
     const size_t smem = v2_smem_bytes(12, plan->max_nv, 256, true);
     if (int rc = ensure_dyn_smem(ctx, reinterpret_cast<const void *>(&rank_count_v2_kernel<12, 256, true, true>), smem))
       return rc;

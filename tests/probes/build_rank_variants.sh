@@ -1,0 +1,20 @@
+#!/bin/bash
+# Builds variants of the library that differ in rank.cu compile-time switches (probe only).
+# usage: build_rank_variants.sh name:"-DFLAG=.. -DFLAG=.." ...
+set -e
+cd "$(dirname "$0")/../../daliid_b200/csrc"
+make -s
+OUT=../../tests/probes/_variants; mkdir -p $OUT
+NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden -cudart static --threads 0"
+for spec in "$@"; do
+  name=${spec%%:*}; flags=${spec#*:}
+  $NV $flags -c rank.cu -o $OUT/rank_$name.o &
+done
+wait
+for spec in "$@"; do
+  name=${spec%%:*}
+  objs=$(ls _obj/*.o | grep -v "_obj/rank.o")
+  /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o $OUT/lib_$name.so $objs $OUT/rank_$name.o -lpthread
+  rm $OUT/rank_$name.o
+  echo built $name
+done
