@@ -469,11 +469,11 @@ rank_count_v2_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
 // A CTA whose thresholds are not all finite (NaN rows, infinite distances) counts its row with the
 // generic compare loop instead: same results, slow, rare.
 constexpr int kV3Chunk = 64;
-#ifndef DALI_V3_PREFETCH
-#define DALI_V3_PREFETCH 1
+#ifndef DALI_V3_DEPTH
+#define DALI_V3_DEPTH 2  // row vectors in flight per thread: ring slots of two float4
 #endif
 #ifndef DALI_V3_MINB
-#define DALI_V3_MINB 5  // resident 256-thread CTAs per SM the tight variant is compiled for
+#define DALI_V3_MINB 8  // resident 256-thread CTAs per SM the tight variant is compiled for (32 registers)
 #endif
 constexpr uint32_t kV3Magic = 0x4B000000u;  // 2^23 as fp32 bits
 
@@ -562,6 +562,12 @@ rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
   __shared__ uint16_t tb[kV3Chunk + 2];
   __shared__ double s_term[FUSED ? kV3Chunk : 1];
   __shared__ __align__(16) uint16_t lut[NE];
+  // the row is streamed through a per-thread ring in shared memory with cp.async: the loads of the
+  // first DEPTH iterations are in flight while the prologue runs, and no registers are held for them
+  constexpr int DEPTH = DALI_V3_DEPTH;
+  __shared__ float4 ring[DEPTH][2][THREADS];
+  constexpr int kPartPlanes = PL + 3;
+  __shared__ uint32_t part[2 * kPartPlanes * 32];  // [threshold word][plane][partial sum]
 
   const int64_t q = blockIdx.x;
   const int chunk = blockIdx.y;
@@ -585,19 +591,33 @@ rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
   const int niter = (nvec + 2 * THREADS - 1) / (2 * THREADS);
   const float qnan = __int_as_float(0x7FFFFFFF);
   const float *pv = row + cv0 + 4 * tid;  // this thread's next pair of vectors
-  int rem = nvec - tid;                   // vectors left from pv on, in steps of THREADS
-  auto load2 = [&](float4 &x0, float4 &x1) {
-    x0 = rem > 0 ? ld_stream_f4(pv) : make_float4(qnan, qnan, qnan, qnan);
-    x1 = rem > THREADS ? ld_stream_f4(pv + 4 * THREADS) : make_float4(qnan, qnan, qnan, qnan);
+  const int nfull = nvec / (2 * THREADS);  // iterations in which every thread has both its vectors
+  const uint32_t ring_s = static_cast<uint32_t>(__cvta_generic_to_shared(&ring[0][0][tid]));
+  // requests the thread's two vectors of iteration `itx` into ring[slot]; always one commit group
+  auto issue = [&](int slot, int itx) {
+    if (itx < nfull) {  // uniform
+      const uint32_t dst = ring_s + static_cast<uint32_t>(slot * 2 * THREADS * 16);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(pv) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + THREADS * 16), "l"(pv + 4 * THREADS) : "memory");
+    } else if (itx < niter) {
+      const int rem = nvec - tid - itx * (2 * THREADS);  // vectors left from pv on, in steps of THREADS
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t dst = ring_s + static_cast<uint32_t>((slot * 2 + j) * THREADS * 16);
+        if (rem > j * THREADS)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(pv + 4 * j * THREADS) : "memory");
+        else
+          asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "f"(qnan) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     pv += 8 * THREADS;
-    rem -= 2 * THREADS;
   };
-  // the first vectors are requested before anything else: the prologue below (three dependent
-  // global loads, a sort, the table) runs under their latency
-  float4 xa0, xa1, xb0, xb1;
-  load2(xa0, xa1);
+#pragma unroll
+  for (int sl = 0; sl < DEPTH; ++sl) issue(sl, sl);
 
-  const int nv = nvalid[q];
+  const int nv = __ldg(nvalid + q);
+  const int64_t off_q = __ldg(off + q), off_q1 = __ldg(off + q + 1);  // with nv: one latency, not two
   if (FUSED && nv == 0) {
     if (tid == 0) {
       fo.ap[q] = 0.f;
@@ -607,9 +627,9 @@ rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
   }
   if (chunk * kV3Chunk >= nv) return;  // uniform exit
   const int n = min(kV3Chunk, nv - chunk * kV3Chunk);
-  const int64_t o = off[q] + static_cast<int64_t>(chunk) * kV3Chunk;
+  const int64_t o = off_q + static_cast<int64_t>(chunk) * kV3Chunk;
   // FUSED: the junk matches (same identity, same camera) follow the valid ones in the match list
-  const int m = FUSED ? static_cast<int>(off[q + 1] - off[q]) : n;
+  const int m = FUSED ? static_cast<int>(off_q1 - off_q) : n;
   const int nj = min(m - n, kJunkCap);  // staged; more than that are read from global memory later
 
   // 1. thresholds, sorted by counting (composites are distinct: gallery ids differ)
@@ -745,13 +765,18 @@ rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
         scnt.add8(mk);
       };
       uint32_t ga = gbase + static_cast<uint32_t>(cv0) + 4u * tid;
+      int slot = 0;
 #pragma unroll 1
-      for (int it = 0; it < niter; it += 2) {
-        load2(xb0, xb1);
-        group(xa0, xa1, ga);
-        load2(xa0, xa1);
-        if (it + 1 < niter) group(xb0, xb1, ga + 8u * THREADS);  // uniform
-        ga += 16u * THREADS;
+      for (int it = 0; it < niter; ++it) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+        float4 x0, x1;
+        const uint32_t src = ring_s + static_cast<uint32_t>(slot * 2 * THREADS * 16);
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x0.x), "=f"(x0.y), "=f"(x0.z), "=f"(x0.w) : "r"(src) : "memory");
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x1.x), "=f"(x1.y), "=f"(x1.z), "=f"(x1.w) : "r"(src + THREADS * 16) : "memory");
+        issue(slot, it + DEPTH);  // the slot is this thread's own: no barrier between its read and its refill
+        group(x0, x1, ga);
+        ga += 8u * THREADS;
+        slot = slot + 1 == DEPTH ? 0 : slot + 1;
       }
       // the unaligned head and the tail of the range (<= 3 columns each, one per thread)
       if (head | tail) {  // uniform
@@ -770,14 +795,43 @@ rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
         scnt.add8(mk);
       }
 
-      // 4. totals: transpose every plane across the warp, lane i then owns threshold 32 w + i
-      const int lane = tid & 31;
+      // 4. totals.  Neighbouring lanes first add their counters in bit-sliced form (a ripple-carry
+      // adder per stage: 2 LOP3 and a shuffle per plane) until the CTA is down to 32 partial sums;
+      // those go to shared memory, and ONE warp per 32 thresholds transposes them (lane i then holds
+      // the bits of threshold i of all 32 partials: popc).  Transposing every warp's seven planes
+      // directly cost 300 instructions per warp -- a sixth of the kernel at the Market row length.
+      constexpr int ST = THREADS == 256 ? 3 : 2;  // (THREADS / 32) * (32 >> ST) == 32 partials
+      constexpr int PLR = PL + ST;
+      const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
       for (int w = 0; w < NW; ++w) {
+        uint32_t r[PLR];
+#pragma unroll
+        for (int k2 = 0; k2 < PLR; ++k2) r[k2] = k2 < PL ? scnt.p[k2][w] : 0u;
+#pragma unroll
+        for (int st = 0; st < ST; ++st) {
+          uint32_t carry = 0u;
+#pragma unroll
+          for (int k2 = 0; k2 < PL + st; ++k2) {
+            const uint32_t o2 = __shfl_xor_sync(0xffffffffu, r[k2], 1 << st);
+            const uint32_t sum = lop3_xor3(r[k2], o2, carry);
+            carry = lop3_maj(r[k2], o2, carry);
+            r[k2] = sum;
+          }
+          r[PL + st] = carry;
+        }
+        if ((lane & ((1 << ST) - 1)) == 0) {
+#pragma unroll
+          for (int k2 = 0; k2 < PLR; ++k2) part[(w * kPartPlanes + k2) * 32 + warp * (32 >> ST) + (lane >> ST)] = r[k2];
+        }
+      }
+      __syncthreads();
+      if (warp < NW) {
         uint32_t total = 0;
 #pragma unroll
-        for (int k = 0; k < PL; ++k) total += static_cast<uint32_t>(__popc(warp_bit_transpose(scnt.p[k][w], lane))) << k;
-        if (32 * w + lane < n && total) atomicAdd(&hist[32 * w + lane], total);
+        for (int k2 = 0; k2 < PLR; ++k2)
+          total += static_cast<uint32_t>(__popc(warp_bit_transpose(part[(warp * kPartPlanes + k2) * 32 + lane], lane))) << k2;
+        hist[32 * warp + lane] = total;
       }
     };
     if (n <= 32) run(std::integral_constant<int, 1>{}); else run(std::integral_constant<int, 2>{});

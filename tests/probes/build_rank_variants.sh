@@ -4,7 +4,7 @@
 set -e
 cd "$(dirname "$0")/../../daliid_b200/csrc"
 make -s
-OUT=../../tests/probes/_variants; mkdir -p $OUT
+OUT=../../tests/probes/_variants; mkdir -p $OUT; find $OUT -name "lib_*.so" -delete
 NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden -cudart static --threads 0"
 for spec in "$@"; do
   name=${spec%%:*}; flags=${spec#*:}
