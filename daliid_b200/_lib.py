@@ -70,6 +70,8 @@ _SIGNATURES = {
     "dali_ctx_fused_count_calls": (i64, [c_vp]),
     "dali_normalize_f32": (ci, [c_vp, c_vp, i64, i64, i64, c_vp, i64, c_vp]),
     "dali_distmat_f32": (ci, [c_vp, c_vp, i64, c_vp, i64, i64, ci, ci, ci, c_vp, i64]),
+    "dali_selftest_mean_division": (ci, [c_vp, ci, ctypes.POINTER(ctypes.c_uint64)]),
+    "dali_distmat_fuse_mean_f32": (ci, [c_vp, c_vp, i64, c_vp, i64, i64, ci, ci, ci, c_vp, i64, c_vp, i64, ci, ci]),
     "dali_peer_create": (ci, [c_vp, ci, ci, i64, ctypes.POINTER(c_vp)]),
     "dali_peer_ipc_handle": (ci, [c_vp, c_vp]),
     "dali_peer_connect": (ci, [c_vp, c_vp]),

@@ -591,13 +591,17 @@ static int prepare_operand(dali_ctx *ctx, int ws_in, int ws_planes, int ws_p16, 
 
 // out[:, 0:Gs] = distances of all Q queries to gallery rows [g_row0, g_row0 + Gs)
 static int contract(dali_ctx *ctx, const Prepared &a, const Prepared &b, int64_t Q, int64_t g_row0,
-                    int64_t Gs, int metric, int precision, float *out, int64_t ld) {
+                    int64_t Gs, int metric, int precision, float *out, int64_t ld, float *acc = nullptr,
+                    int64_t ld_acc = 0, int acc_mode = 0, float acc_div = 1.0f) {
   const float *gsq = b.sq ? b.sq + g_row0 : nullptr;
-  if (precision == DALI_PREC_FP32)
+  if (precision == DALI_PREC_FP32) {
+    if (acc_mode) return set_err(ctx, DALI_ERR_UNSUPPORTED, "the fused mean runs in the tensor-core contraction only");
     return launch_distmat_simt(ctx, a.planes, b.planes + g_row0 * b.Dp, Q, Gs, a.Dp, a.Dp, b.Dp, metric,
                                a.sq, gsq, out, ld);
+  }
   return launch_distmat_umma(ctx, a.planes, b.planes, a.planes16, b.planes16, Q, Gs, a.Dp, a.rows_pad,
-                             b.rows_pad, g_row0, precision, metric, a.sq, gsq, out, ld);
+                             b.rows_pad, g_row0, precision, metric, a.sq, gsq, out, ld, acc, ld_acc, acc_mode,
+                             acc_div);
 }
 
 static int check_metric_prec(dali_ctx *ctx, int metric, int precision, int normalize) {
@@ -1158,6 +1162,52 @@ int dali_distmat_f32(dali_ctx *ctx, const float *q, int64_t Q, const float *g, i
     DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return DALI_OK;  // device output: stream-ordered, no host synchronisation
+}
+
+int dali_selftest_mean_division(dali_ctx *ctx, int n, uint64_t *mismatches) {
+  DeviceGuard dg;
+  int rc = dg.enter(ctx);
+  if (rc) return rc;
+  if (n < 1 || n > 64 || !mismatches) return set_err(ctx, DALI_ERR_INVALID, "selftest_mean_division: n in 1..64");
+  void *d = nullptr;
+  rc = ws_ensure(ctx, WS_COUNTS, sizeof(unsigned long long), &d);
+  if (rc) return rc;
+  DALI_CUDA_OK(ctx, cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->stream));
+  rc = launch_selftest_div(ctx, n, static_cast<unsigned long long *>(d));
+  if (rc) return rc;
+  unsigned long long h = 0;
+  DALI_CUDA_OK(ctx, cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  DALI_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  *mismatches = h;
+  return DALI_OK;
+}
+
+int dali_distmat_fuse_mean_f32(dali_ctx *ctx, const float *q, int64_t Q, const float *g, int64_t G,
+                               int64_t D, int metric, int precision, int normalize, float *out_opt,
+                               int64_t ld_out, float *acc, int64_t ld_acc, int step, int n_models) {
+  DeviceGuard dg;
+  int rc = dg.enter(ctx);
+  if (rc) return rc;
+  if (Q < 0 || G < 0 || D <= 0 || !acc || ld_acc < G || (out_opt && ld_out < G) || (!q && Q) || (!g && G) ||
+      n_models < 1 || step < 0 || step >= n_models)
+    return set_err(ctx, DALI_ERR_INVALID, "distmat_fuse_mean: bad shape, step or null pointer");
+  rc = check_metric_prec(ctx, metric, precision, normalize);
+  if (rc) return rc;
+  if (precision == DALI_PREC_FP32 || !is_device_ptr(acc) || (out_opt && !is_device_ptr(out_opt)) ||
+      ld_acc % 4 != 0 || (reinterpret_cast<uintptr_t>(acc) & 15) != 0 ||
+      (out_opt && (ld_out % 4 != 0 || (reinterpret_cast<uintptr_t>(out_opt) & 15) != 0)))
+    return set_err(ctx, DALI_ERR_UNSUPPORTED,
+                   "distmat_fuse_mean: tensor-core precisions and device matrices with 16-byte aligned rows only");
+  if (Q == 0 || G == 0) return DALI_OK;
+  Prepared a, b;
+  rc = prepare_operand(ctx, WS_QIN, WS_QN, WS_QN16, WS_QNORM, q, Q, D, metric, precision, normalize, &a);
+  if (rc) return rc;
+  rc = prepare_operand(ctx, WS_GIN, WS_GN, WS_GN16, WS_GNORM, g, G, D, metric, precision, normalize, &b);
+  if (rc) return rc;
+  // 1: acc = d; 2: acc += d; 3: acc = (acc + d) / n.  One model: the mean is the matrix itself, divided by 1.
+  const int mode = step == 0 ? 1 : (step == n_models - 1 ? 3 : 2);
+  return contract(ctx, a, b, Q, 0, G, metric, precision, out_opt, ld_out, acc, ld_acc, mode,
+                  static_cast<float>(n_models));  // stream-ordered, no host synchronisation
 }
 
 // ---------------------------------------------------------------------------

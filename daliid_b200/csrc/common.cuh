@@ -38,6 +38,22 @@ __host__ __device__ __forceinline__ float key_to_dist(uint32_t k) {
 #endif
 }
 
+// x / n for a small integer n (the mean of n matrices), correctly rounded like __fdiv_rn: for
+// |x| in [2^-100, 2^100) two FMAs refine x * RN(1/n) -- q0 is faithful, r = x - q0 n is exact, and
+// RN(q0 + r RN(1/n)) is then the correctly rounded quotient (Markstein); checked against
+// __fdiv_rn over all 2^32 operands for n = 2 .. 8 by dali_selftest_mean_division.  Zero,
+// subnormal-range, huge, infinite and NaN operands take the IEEE division.  ~6 instructions
+// instead of ~20 with a call: the fused-mean epilogue and fuse.cu divide every element.
+__device__ __forceinline__ float div_small_int(float x, float n, float rn) {
+  const float ax = fabsf(x);
+  if (ax >= 7.888609052210118e-31f && ax < 1.2676506002282294e30f) {
+    const float q0 = __fmul_rn(x, rn);
+    const float r = __fmaf_rn(-q0, n, x);
+    return __fmaf_rn(r, rn, q0);
+  }
+  return __fdiv_rn(x, n);
+}
+
 __host__ __device__ __forceinline__ uint64_t composite(uint32_t key, uint32_t gid) {
   return (static_cast<uint64_t>(key) << 32) | gid;
 }
@@ -258,6 +274,7 @@ int launch_prep(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx
                 int round_mode, float *norms, float *sq, void *hi16 = nullptr,
                 void *lo16 = nullptr, const int32_t *perm = nullptr);
 float f16x3_hi_grid(int64_t d_pad);
+int launch_selftest_div(dali_ctx *ctx, int n, unsigned long long *bad_dev);  // fuse.cu
 // distmat_simt.cu
 int launch_distmat_simt(dali_ctx *ctx, const float *qn, const float *gn, int64_t Q, int64_t G,
                         int64_t D, int64_t ldq, int64_t ldg, int metric, const float *qsq,
@@ -266,7 +283,8 @@ int launch_distmat_simt(dali_ctx *ctx, const float *qn, const float *gn, int64_t
 int launch_distmat_umma(dali_ctx *ctx, const float *q32, const float *g32, const void *q16,
                         const void *g16, int64_t Q, int64_t G, int64_t Dp, int64_t q_rows_pad,
                         int64_t g_rows_pad, int64_t g_row0, int precision, int metric,
-                        const float *qsq, const float *gsq, float *out, int64_t ld);
+                        const float *qsq, const float *gsq, float *out, int64_t ld, float *acc = nullptr,
+                        int64_t ld_acc = 0, int acc_mode = 0, float acc_div = 1.0f);
 // distmat_umma2.cu
 int launch_distmat_filter_umma(dali_ctx *ctx, const float *q32, const float *g32, const void *q16,
                                const void *g16, int64_t Q, int64_t G, int64_t Dp,

@@ -71,7 +71,7 @@ static_assert(8 * (2 * kSlots + 4) + 8 <= kBarBytes, "barrier block too small");
 //   kCount  every other tile straight from TMEM, and the band tiles from the scratch: each
 //           epilogue thread owns a query row, holds that query's thresholds (the distances of its
 //           valid positives) in registers and counts the columns below each of them
-enum Epi { kStore = 0, kFilter = 1, kBand = 2, kCount = 3 };
+enum Epi { kStore = 0, kFilter = 1, kBand = 2, kCount = 3, kAccum = 4 };  // kAccum: kStore + running mean
 
 // mean accumulator loss per MMA in units of 2^-24 * s with the fixed-point hi plane, fitted to
 // tests/probes/trunc_probe.py on B200 (constant over D = 512 .. 4096 to +-0.01)
@@ -89,6 +89,12 @@ struct Umma2Params {
   float *out;
   int64_t ld;
   int tma_out;          // 1: rows of `out` are 16-byte aligned, tiles leave through TMA stores
+  // kStore, mean fusion over several launches (fuse.cu's operation order, ((d0+d1)+d2)/n):
+  float *acc;           // running sum matrix (16-byte aligned rows, written through tmAcc)
+  int64_t ld_acc;
+  int acc_mode;         // 0 none; 1 acc = d; 2 acc = acc + d; 3 acc = (acc + d) / acc_div
+  float acc_div;
+  int store_out;        // 0: only `acc` is written
   // kFilter
   const float *thr;     // [Q] running k-th best distance of the row (+inf / -inf: accept all)
   int32_t *cand_cnt;    // [Q] entries appended to the row's list
@@ -370,7 +376,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmA16,
                      const __grid_constant__ CUtensorMap tmB16,
-                     const __grid_constant__ CUtensorMap tmOut, const Umma2Params p) {
+                     const __grid_constant__ CUtensorMap tmOut,
+                     const __grid_constant__ CUtensorMap tmAcc, const Umma2Params p) {
   extern __shared__ uint8_t smem_raw[];
   // the dynamic window starts at the same offset in both CTAs, so this rounding is identical
   // in the pair (the MMA applies the leader's operand offsets to the peer's shared memory)
@@ -694,6 +701,19 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       int m, n;
       tile_mn(t, m, n);
       const int as = it & 1;
+      if (EPI == kAccum && p.acc_mode >= 2 && t + num_pairs < num_tiles) {
+        // mean fusion: this thread's row of the NEXT tile's running sums into L2, a whole tile ahead
+        int m2, n2;
+        tile_mn(t + num_pairs, m2, n2);
+        const int64_t r2 = static_cast<int64_t>(m2) * PM + rank * UM + quarter * 32 + lane;
+        const int64_t c2 = static_cast<int64_t>(n2) * BN;
+        if (r2 < p.Q) {
+          const float *src = p.acc + r2 * p.ld_acc + c2;
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j)
+            if (c2 + 32 * j < p.G) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 32 * j));
+        }
+      }
       mbar_wait(tfull_bar(as), (it >> 1) & 1u);
       tc_fence_after();
       const int64_t colt = static_cast<int64_t>(n) * BN;
@@ -718,7 +738,7 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             count_tile<2, 0>(p, cr, wmax, tbase, nullptr, colt, alpha, beta, qs, sT, sC, lane);
           else
             count_tile<0, 0>(p, cr, wmax, tbase, nullptr, colt, alpha, beta, qs, sT, sC, lane);
-        } else if (EPI == kStore || EPI == kBand) {
+        } else if (EPI == kStore || EPI == kBand || EPI == kAccum) {
           // one thread per query row: metric in registers, then either
           //   - the 32 x 32 block goes to a 128B-swizzled staging tile (conflict-free 16-byte
           //     stores) and leaves through one TMA store (rows / columns beyond Q / G clipped by
@@ -731,6 +751,30 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const float alpha = (p.metric == DALI_METRIC_COSINE ? -1.0f : 1.0f) * p.acc_scale;
           const float beta = p.metric == DALI_METRIC_COSINE ? 1.0f : 0.0f;
           const int kind = p.metric == DALI_METRIC_SQEUCLIDEAN ? 1 : p.metric == DALI_METRIC_EUCLIDEAN ? 2 : 0;
+          // mean fusion: 32 columns of this row of the running sum (rows are 16-byte aligned)
+          float nxt[32];
+          const bool acc32 = (p.ld_acc & 7) == 0 && (reinterpret_cast<uintptr_t>(p.acc) & 31) == 0;
+          const float acc_rdiv = __frcp_rn(p.acc_div);
+          auto load_prev = [&](int64_t col, float (&dst)[32]) {
+            const float *src = p.acc + (r_own < p.Q ? r_own : 0) * p.ld_acc + col;
+            if (p.G - col >= 32 && acc32) {  // whole 32-byte sectors per request
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=f"(dst[8 * j]), "=f"(dst[8 * j + 1]), "=f"(dst[8 * j + 2]), "=f"(dst[8 * j + 3]),
+                               "=f"(dst[8 * j + 4]), "=f"(dst[8 * j + 5]), "=f"(dst[8 * j + 6]), "=f"(dst[8 * j + 7])
+                             : "l"(src + 8 * j) : "memory");
+            } else if (p.G - col >= 32) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 x = *reinterpret_cast<const float4 *>(src + 4 * j);
+                dst[4 * j] = x.x; dst[4 * j + 1] = x.y; dst[4 * j + 2] = x.z; dst[4 * j + 3] = x.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) dst[j] = col + j < p.G ? src[j] : 0.f;
+            }
+          };
           // kBand: this row's identity segment [seg_lo, seg_lo + seg_m) in sorted-gallery columns
           int64_t seg_lo = 0, seg_o = 0;
           int seg_m = 0;
@@ -740,14 +784,23 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             seg_m = static_cast<int>(__ldg(p.f.off + q + 1) - seg_o);
             seg_lo = __ldg(p.f.lo + q);
           }
+          if (EPI == kAccum && p.acc_mode >= 2 && colt < p.G) load_prev(colt, nxt);
 #pragma unroll 1
           for (int c = 0; c < BN / 32; ++c) {
             const int64_t col0 = colt + c * 32;
             if (col0 >= p.G) break;
             uint32_t v[32];
+            const int lim = p.G - col0 < 32 ? static_cast<int>(p.G - col0) : 32;
+            // mean fusion: the running sum of this row's 32 columns was requested one block ago;
+            // the next block's is requested now, a block of epilogue work ahead of its use
+            float prev[32];
+            if (EPI == kAccum && p.acc_mode >= 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) prev[j] = nxt[j];
+              if (c + 1 < BN / 32 && col0 + 32 < p.G) load_prev(col0 + 32, nxt);
+            }
             tc_ld_32x32(tbase + c * 32, v);
             tc_wait_ld();
-            const int lim = p.G - col0 < 32 ? static_cast<int>(p.G - col0) : 32;
             const float *gs = p.gsq ? p.gsq + col0 : nullptr;
             if (kind == 0) apply_metric<0>(v, alpha, beta, p.acc_scale, qs, gs, lim);
             else if (kind == 1) apply_metric<1>(v, alpha, beta, p.acc_scale, qs, gs, lim);
@@ -766,23 +819,68 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               __syncwarp();
             }
             if (p.tma_out) {
-              const uint32_t buf = stg_base + static_cast<uint32_t>(((nstore++) & 1) * 4096);
-              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-              __syncwarp();
-              const uint32_t rowaddr = buf + static_cast<uint32_t>(lane * 128);
+              if (EPI != kAccum || p.store_out) {
+                const uint32_t buf = stg_base + static_cast<uint32_t>(((nstore++) & 1) * 4096);
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                const uint32_t rowaddr = buf + static_cast<uint32_t>(lane * 128);
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                sts128(rowaddr + static_cast<uint32_t>(((j ^ (lane & 7)) << 4)),
-                       __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-              __syncwarp();
-              if (lane == 0) {
-                if (EPI == kBand)  // tile t of the list -> rows [256 t, 256 t + 256) of the scratch
-                  tma_store_2d(&tmOut, buf, c * 32, t * PM + static_cast<int>(rank) * UM + quarter * 32);
-                else
-                  tma_store_2d(&tmOut, buf, static_cast<int32_t>(col0), static_cast<int32_t>(row0));
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                for (int j = 0; j < 8; ++j)
+                  sts128(rowaddr + static_cast<uint32_t>(((j ^ (lane & 7)) << 4)),
+                         __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                         __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                  if (EPI == kBand)  // tile t of the list -> rows [256 t, 256 t + 256) of the scratch
+                    tma_store_2d(&tmOut, buf, c * 32, t * PM + static_cast<int>(rank) * UM + quarter * 32);
+                  else
+                    tma_store_2d(&tmOut, buf, static_cast<int32_t>(col0), static_cast<int32_t>(row0));
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+              }
+              if (EPI == kAccum) {
+                // the running sum in fuse.cu's order and rounding: acc + d, the last launch divides
+                if (p.acc_mode >= 2) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__fadd_rn(prev[j], __uint_as_float(v[j])));
+                }
+                if (p.acc_mode == 3) {
+                  // one range test for the 32 columns, then the branch-free refinement (a test and a
+                  // branch per element serialised the block: 5 us per tile at D = 768)
+                  bool fast = true;
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) {
+                    const float ax = fabsf(__uint_as_float(v[j]));
+                    fast = fast && ax >= 7.888609052210118e-31f && ax < 1.2676506002282294e30f;
+                  }
+                  if (fast) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                      const float x = __uint_as_float(v[j]);
+                      const float q0 = __fmul_rn(x, acc_rdiv);
+                      v[j] = __float_as_uint(__fmaf_rn(__fmaf_rn(-q0, p.acc_div, x), acc_rdiv, q0));
+                    }
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(div_small_int(__uint_as_float(v[j]), p.acc_div, acc_rdiv));
+                  }
+                }
+                const uint32_t buf = stg_base + static_cast<uint32_t>(((nstore++) & 1) * 4096);
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                const uint32_t rowaddr = buf + static_cast<uint32_t>(lane * 128);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  sts128(rowaddr + static_cast<uint32_t>(((j ^ (lane & 7)) << 4)),
+                         __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                         __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_2d(&tmAcc, buf, static_cast<int32_t>(col0), static_cast<int32_t>(row0));
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
               }
             } else {
 #pragma unroll
@@ -850,7 +948,7 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_bar(as), 0);
     }
-    if ((EPI == kStore || EPI == kBand) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if ((EPI == kStore || EPI == kBand || EPI == kAccum) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -864,7 +962,8 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
 template <int MODE, int EPI>
 int launch_t(dali_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmA16,
-             const CUtensorMap &tmB16, const CUtensorMap &tmOut, const Umma2Params &p) {
+             const CUtensorMap &tmB16, const CUtensorMap &tmOut, const Umma2Params &p,
+             const CUtensorMap *tmAcc = nullptr) {
   if (int rc = ensure_dyn_smem(ctx, reinterpret_cast<const void *>(&distmat_umma2_kernel<MODE, EPI>), kSmemBytes))
     return rc;
   const int tiles = p.f.tiles ? std::max(p.f.num_list, p.f.num_band) : p.num_m_pairs * p.num_n_tiles;
@@ -873,7 +972,8 @@ int launch_t(dali_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, cons
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   KTimer t(ctx, DALI_K_DISTMAT);
   distmat_umma2_kernel<MODE, EPI><<<2 * pairs, kThreads, kSmemBytes, ctx->stream>>>(tmA, tmB, tmA16,
-                                                                                   tmB16, tmOut, p);
+                                                                                   tmB16, tmOut,
+                                                                                   tmAcc ? *tmAcc : tmOut, p);
   DALI_CUDA_OK(ctx, cudaGetLastError());
   return DALI_OK;
 }
@@ -881,13 +981,13 @@ int launch_t(dali_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, cons
 template <int EPI>
 int launch_prec(dali_ctx *ctx, int precision, const CUtensorMap &tmA, const CUtensorMap &tmB,
                 const CUtensorMap &tmA16, const CUtensorMap &tmB16, const CUtensorMap &tmOut,
-                const Umma2Params &p) {
+                const Umma2Params &p, const CUtensorMap *tmAcc = nullptr) {
   switch (precision) {
-    case DALI_PREC_TF32: return launch_t<kTf32, EPI>(ctx, tmA, tmB, tmA16, tmB16, tmOut, p);
-    case DALI_PREC_TF32X3: return launch_t<kTf32x3, EPI>(ctx, tmA, tmB, tmA16, tmB16, tmOut, p);
-    case DALI_PREC_TF32C: return launch_t<kTf32c, EPI>(ctx, tmA, tmB, tmA16, tmB16, tmOut, p);
-    case DALI_PREC_F16X3: return launch_t<kF16x3, EPI>(ctx, tmA, tmB, tmA16, tmB16, tmOut, p);
-    case DALI_PREC_F16: return launch_t<kF16, EPI>(ctx, tmA, tmB, tmA16, tmB16, tmOut, p);
+    case DALI_PREC_TF32: return launch_t<kTf32, EPI>(ctx, tmA, tmB, tmA16, tmB16, tmOut, p, tmAcc);
+    case DALI_PREC_TF32X3: return launch_t<kTf32x3, EPI>(ctx, tmA, tmB, tmA16, tmB16, tmOut, p, tmAcc);
+    case DALI_PREC_TF32C: return launch_t<kTf32c, EPI>(ctx, tmA, tmB, tmA16, tmB16, tmOut, p, tmAcc);
+    case DALI_PREC_F16X3: return launch_t<kF16x3, EPI>(ctx, tmA, tmB, tmA16, tmB16, tmOut, p, tmAcc);
+    case DALI_PREC_F16: return launch_t<kF16, EPI>(ctx, tmA, tmB, tmA16, tmB16, tmOut, p, tmAcc);
     default: return set_err(ctx, DALI_ERR_INVALID, "not a tensor-core precision");
   }
 }
@@ -1012,10 +1112,11 @@ int setup(dali_ctx *ctx, const float *q32, const float *g32, const void *q16, co
 int launch_distmat_umma(dali_ctx *ctx, const float *q32, const float *g32, const void *q16,
                         const void *g16, int64_t Q, int64_t G, int64_t Dp, int64_t q_rows_pad,
                         int64_t g_rows_pad, int64_t g_row0, int precision, int metric,
-                        const float *qsq, const float *gsq, float *out, int64_t ld) {
+                        const float *qsq, const float *gsq, float *out, int64_t ld, float *acc,
+                        int64_t ld_acc, int acc_mode, float acc_div) {
   if (Q == 0 || G == 0) return DALI_OK;
   static const char *env = getenv("DALI_UMMA_2CTA");
-  if (env && atoi(env) == 0 && precision != DALI_PREC_F16X3 && precision != DALI_PREC_F16)
+  if (env && atoi(env) == 0 && precision != DALI_PREC_F16X3 && precision != DALI_PREC_F16 && !acc_mode)
     return launch_distmat_umma1(ctx, q32, g32, q16, g16, Q, G, Dp, q_rows_pad, g_rows_pad, g_row0,
                                 precision, metric, qsq, gsq, out, ld);
   CUtensorMap tmA, tmB, tmA16, tmB16;
@@ -1028,11 +1129,26 @@ int launch_distmat_umma(dali_ctx *ctx, const float *q32, const float *g32, const
   // leading dimension is a multiple of 4; a caller's contiguous [Q, G] with odd G is not)
   static const char *env_tma = getenv("DALI_UMMA_TMA_STORE");
   CUtensorMap tmOut = tmA;
-  p.tma_out = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+  p.tma_out = out && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
               !(env_tma && atoi(env_tma) == 0) && Q <= INT32_MAX && G <= INT32_MAX;
   if (p.tma_out) {
     rc = make_out_map(ctx, &tmOut, out, Q, G, ld);
     if (rc) return rc;
+  }
+  p.store_out = 1;
+  if (acc_mode) {
+    // the running sum leaves (and its previous value is read) in 16-byte pieces
+    if (!acc || ld_acc % 4 != 0 || (reinterpret_cast<uintptr_t>(acc) & 15) != 0 || Q > INT32_MAX || G > INT32_MAX)
+      return set_err(ctx, DALI_ERR_UNSUPPORTED, "fused mean needs a sum matrix with 16-byte aligned rows");
+    CUtensorMap tmAcc;
+    rc = make_out_map(ctx, &tmAcc, acc, Q, G, ld_acc);
+    if (rc) return rc;
+    p.acc = acc; p.ld_acc = ld_acc; p.acc_mode = acc_mode; p.acc_div = acc_div;
+    p.store_out = out != nullptr && p.tma_out;
+    if (out && !p.tma_out)
+      return set_err(ctx, DALI_ERR_UNSUPPORTED, "fused mean with an individual matrix needs 16-byte aligned rows there too");
+    p.tma_out = 1;
+    return launch_prec<kAccum>(ctx, precision, tmA, tmB, tmA16, tmB16, p.store_out ? tmOut : tmAcc, p, &tmAcc);
   }
   return launch_prec<kStore>(ctx, precision, tmA, tmB, tmA16, tmB16, tmOut, p);
 }

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) fuse_flat_kernel(FuseParams p) {
       for (int m = 1; m < N; ++m) acc = __fadd_rn(acc, v[m]);
       if (N == 1) return acc;
       if (N == 2 || N == 4 || N == 8) return __fmul_rn(acc, 1.0f / N);  // exact: a power of two
-      return __fdiv_rn(acc, static_cast<float>(N));
+      return div_small_int(acc, static_cast<float>(N), __frcp_rn(static_cast<float>(N)));
     }
     if (col >= p.G) return 0.f;  // padding column
     float num = 0.f, den = 0.f;
@@ -228,6 +228,27 @@ int launch_fuse(dali_ctx *ctx, const float *const *d, int n, const float *const 
     fuse_kernel<4><<<grid, 256, 0, ctx->stream>>>(p);
   else
     fuse_kernel<1><<<grid, 256, 0, ctx->stream>>>(p);
+  DALI_CUDA_OK(ctx, cudaGetLastError());
+  return DALI_OK;
+}
+
+// ---- exhaustive check of div_small_int against the IEEE division (test hook) -------------------
+namespace {
+__global__ void __launch_bounds__(256) selftest_div_kernel(float n, unsigned long long *bad) {
+  const float rn = __frcp_rn(n);
+  unsigned long long mine = 0;
+  for (uint64_t b = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; b < (1ull << 32);
+       b += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const float x = __uint_as_float(static_cast<uint32_t>(b));
+    const float a = div_small_int(x, n, rn), e = __fdiv_rn(x, n);
+    if (__float_as_uint(a) != __float_as_uint(e) && !(a != a && e != e)) ++mine;
+  }
+  if (mine) atomicAdd(bad, mine);
+}
+}  // namespace
+
+int launch_selftest_div(dali_ctx *ctx, int n, unsigned long long *bad_dev) {
+  selftest_div_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(static_cast<float>(n), bad_dev);
   DALI_CUDA_OK(ctx, cudaGetLastError());
   return DALI_OK;
 }

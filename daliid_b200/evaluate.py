@@ -58,11 +58,11 @@ def evaluate_single_model(queries_fvs, gallery_fvs, queries, gallery, precision=
 def evaluate_multiple_output(q_feats, g_feats, queries, gallery, precision=metrics.DEFAULT_PRECISION):
     """3-exit branch of evaluate.py (244-279): one distmat per exit, metrics per exit, then the
     mean ``(d_backbone + d_head01 + d_head02)/3`` (278) and its metrics (279)."""
-    distmats = [metrics.compute_distance_matrix(q, g, "cosine", precision=precision)
-                for q, g in zip(q_feats, g_feats)]
+    # the three contractions add their tiles to the running mean in their epilogues: no fusion pass
+    distmats, distmat_ensemble = metrics.ensemble_distance_matrices(q_feats, g_feats, "cosine",
+                                                                    precision=precision)
     for d in distmats:
         calculate_metrics(d, queries, gallery)
-    distmat_ensemble = metrics.fuse_distmats(distmats)
     calculate_metrics(distmat_ensemble, queries, gallery)
     return distmats, distmat_ensemble
 
@@ -70,11 +70,10 @@ def evaluate_multiple_output(q_feats, g_feats, queries, gallery, precision=metri
 def evaluate_ensembled_models(q_feats01, g_feats01, q_feats02, g_feats02, queries, gallery,
                               precision=metrics.DEFAULT_PRECISION):
     """evaluate_ensembled_models.py:274-314: two models, ``(distmat01+distmat02)/2``."""
-    distmat01 = metrics.compute_distance_matrix(q_feats01, g_feats01, "cosine", precision=precision)
+    (distmat01, distmat02), distmat_ensemble = metrics.ensemble_distance_matrices(
+        [q_feats01, q_feats02], [g_feats01, g_feats02], "cosine", precision=precision)
     calculate_metrics(distmat01, queries, gallery)
-    distmat02 = metrics.compute_distance_matrix(q_feats02, g_feats02, "cosine", precision=precision)
     calculate_metrics(distmat02, queries, gallery)
-    distmat_ensemble = metrics.fuse_distmats([distmat01, distmat02])
     calculate_metrics(distmat_ensemble, queries, gallery)
     return distmat01, distmat02, distmat_ensemble
 

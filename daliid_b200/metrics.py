@@ -226,6 +226,62 @@ def compute_distance_matrix(input1, input2, metric="cosine", precision=DEFAULT_P
     return out
 
 
+def ensemble_distance_matrices(q_feats, g_feats, metric="cosine", precision=DEFAULT_PRECISION,
+                               normalize=None, individual=True, device=None):
+    """The distance matrices of an N-model ensemble and their mean ``((d0+d1)+..)/N`` in one sweep:
+    every model's contraction adds its tile to the running sum in its epilogue, so the separate
+    fusion pass over N+1 matrices (evaluate.py:278, evaluate_ensembled_models.py:313) disappears.
+
+    Returns ``(distmats, mean)``; ``distmats`` is ``None`` with ``individual=False`` (then only the
+    mean is written).  The mean is bit-identical to ``fuse_distmats`` of the separate matrices.
+    Shapes the fused epilogue does not take (FP32-pipe precision, host-resident results) go through
+    ``compute_distance_matrix`` + ``fuse_distmats`` -- same values."""
+    n = len(q_feats)
+    if n < 1 or n > 8 or len(g_feats) != n:
+        raise ValueError("between 1 and 8 (query, gallery) feature pairs")
+    a = [as_matrix(x, np.float32, "q_feats") for x in q_feats]
+    b = [as_matrix(x, np.float32, "g_feats") for x in g_feats]
+    Q, G = a[0].shape[0], b[0].shape[0]
+    for x, y in zip(a, b):
+        if x.shape[0] != Q or y.shape[0] != G or x.shape[1] != y.shape[1]:
+            raise ValueError("all models must share the query and gallery sets")
+        if x.ld != x.shape[1] or y.ld != y.shape[1]:
+            raise ValueError("feature matrices must be contiguous")
+    m = _enum(METRICS, metric, "metric")
+    if normalize is None:
+        normalize = m == METRICS["cosine"]
+    dev = _device_of(*a, *b)
+    if dev is None and device is not None:
+        dev = int(device)
+
+    def unfused():
+        ds = [compute_distance_matrix(x, y, metric, precision, normalize, device=device)
+              for x, y in zip(q_feats, g_feats)]
+        return (ds if individual else None), fuse_distmats(ds)
+    if dev is None or not Q or not G:
+        return unfused()
+    ctx = get_ctx(dev)
+    ctx.attach_torch_stream()
+    ld = (G + 3) // 4 * 4
+    lda = (G + 7) // 8 * 8  # the running sum is re-read in 32-byte pieces
+    acc_buf, acc_ptr = _alloc_out((Q, lda), dev)
+    outs = []
+    for i, (x, y) in enumerate(zip(a, b)):
+        if individual:
+            o_buf, o_ptr = _alloc_out((Q, ld), dev)
+            outs.append(o_buf[:, :G])
+        else:
+            o_ptr = None
+        rc = ctx.lib.dali_distmat_fuse_mean_f32(ctx.h, c_vp(x.ptr), Q, c_vp(y.ptr), G, x.shape[1], m,
+                                                _precision(precision, normalize, x.shape[1]),
+                                                1 if normalize else 0, c_vp(o_ptr), ld, c_vp(acc_ptr), lda,
+                                                i, n)
+        if rc == _lib.ERR_UNSUPPORTED:
+            return unfused()
+        ctx.check(rc)
+    return (outs if individual else None), acc_buf[:, :G]
+
+
 def fuse_distmats(distmats, q_weights=None, g_weights=None):
     """Fuse N distance matrices.
 

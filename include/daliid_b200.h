@@ -161,6 +161,27 @@ int dali_distmat_f32(dali_ctx *ctx, const float *q, int64_t Q, const float *g, i
                      int64_t D, int metric, int precision, int normalize, float *out,
                      int64_t ld);
 
+/* ---- a2 + a4: one model's distance matrix folded into the running mean -------------------- */
+/* The n_models matrices of an ensemble, one call per model (step = 0 .. n_models-1, in the
+ * reference's order of addition), summed in the contraction's epilogue instead of by a separate
+ * pass over n_models + 1 matrices:
+ *   step 0: acc = d;   0 < step < n_models-1: acc = acc + d;   last step: acc = (acc + d) / n_models
+ * with the roundings of dali_fuse_f32's mean, so acc ends bit-identical to fusing the separately
+ * materialised matrices.  out_opt (may be NULL) also receives this model's own matrix (the
+ * reference ranks every model before the ensemble).  acc and out_opt: DEVICE buffers, rows 16-byte
+ * aligned (ld multiple of 4); tensor-core precisions only -- otherwise DALI_ERR_UNSUPPORTED, and
+ * the caller takes dali_distmat_f32 + dali_fuse_f32.
+ * replaces  (distmat01 + distmat02)/2  evaluate_ensembled_models.py:313,
+ *           (d_backbone + d_head01 + d_head02)/3  evaluate.py:260-278. */
+int dali_distmat_fuse_mean_f32(dali_ctx *ctx, const float *q, int64_t Q, const float *g, int64_t G,
+                               int64_t D, int metric, int precision, int normalize, float *out_opt,
+                               int64_t ld_out, float *acc, int64_t ld_acc, int step, int n_models);
+
+/* Test hook: the mean's division x / n_models is carried out as a multiplication by RN(1/n) refined
+ * by two FMAs (correctly rounded, i.e. what numpy / torch compute); this compares it with the IEEE
+ * division over ALL 2^32 fp32 operands on the device and reports the number of differing results. */
+int dali_selftest_mean_division(dali_ctx *ctx, int n, uint64_t *mismatches);
+
 /* ---- a4: multi-model distance fusion -------------------------------------- */
 /* wq == NULL: out = ((d[0]+d[1])+...+d[n-1]) / n   fp32, left to right, true division
  *   replaces evaluate.py:278, evaluate_ensembled_models.py:313, evaluateCleanATModels.py:127.

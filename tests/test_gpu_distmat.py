@@ -228,6 +228,61 @@ def test_fusion_bit_exact():
         assert np.array_equal(get(w), z["weighted"])
 
 
+@pytest.mark.parametrize("shape", [(37, 95, 64), (300, 1000, 768), (513, 777, 96)])
+@pytest.mark.parametrize("nmodels", [1, 2, 3, 5])
+@pytest.mark.parametrize("precision", ["f16x3", "tf32", "tf32c"])
+def test_ensemble_mean_in_the_epilogue_is_bit_identical(shape, nmodels, precision):
+    """evaluate.py:260-278 / evaluate_ensembled_models.py:313: the mean formed in the contractions'
+    epilogues equals fuse_distmats of the separately materialised matrices bit for bit, and the
+    individual matrices equal compute_distance_matrix's."""
+    from daliid_b200 import metrics
+    Q, G, D = shape
+    rng = np.random.default_rng(Q + nmodels)
+    qs = [torch.from_numpy(rng.standard_normal((Q, D)).astype(np.float32)).cuda() for _ in range(nmodels)]
+    gs = [torch.from_numpy(rng.standard_normal((G, D)).astype(np.float32)).cuda() for _ in range(nmodels)]
+    sep = [metrics.compute_distance_matrix(q, g, "cosine", precision) for q, g in zip(qs, gs)]
+    ref = metrics.fuse_distmats(sep)
+    ds, mean = metrics.ensemble_distance_matrices(qs, gs, "cosine", precision)
+    assert mean.shape == (Q, G) and len(ds) == nmodels
+    assert torch.equal(mean, ref)
+    for a, b in zip(ds, sep):
+        assert torch.equal(a, b)
+    none, mean_only = metrics.ensemble_distance_matrices(qs, gs, "cosine", precision, individual=False)
+    assert none is None and torch.equal(mean_only, ref)
+    # the reference's own expression on the CPU (the matrices themselves are the contraction's)
+    cpu = sep[0].cpu().numpy().copy()
+    for d in sep[1:]:
+        cpu = cpu + d.cpu().numpy()
+    assert np.array_equal(mean.cpu().numpy(), cpu / np.float32(nmodels))
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 6, 7, 8])
+def test_mean_division_is_the_ieee_division_for_every_operand(n):
+    """The mean's x / n (fuse.cu, fused-mean epilogue) is a reciprocal multiplication refined by two
+    FMAs; exhaustively equal to the IEEE division numpy and torch perform (all 2^32 operands)."""
+    import ctypes
+    from daliid_b200 import _lib
+    ctx = _lib.get_ctx(0)
+    bad = ctypes.c_uint64(123)
+    ctx.check(ctx.lib.dali_selftest_mean_division(ctx.h, n, ctypes.byref(bad)))
+    assert bad.value == 0
+
+
+def test_ensemble_falls_back_for_the_fp32_pipe_and_host_results():
+    from daliid_b200 import metrics
+    rng = np.random.default_rng(3)
+    qs = [rng.standard_normal((20, 48)).astype(np.float32) for _ in range(2)]
+    gs = [rng.standard_normal((33, 48)).astype(np.float32) for _ in range(2)]
+    ds, mean = metrics.ensemble_distance_matrices(qs, gs, "cosine", "fp32")
+    assert isinstance(mean, np.ndarray) and np.array_equal(mean, metrics.fuse_distmats(ds))
+    qc, gc = [torch.from_numpy(x).cuda() for x in qs], [torch.from_numpy(x).cuda() for x in gs]
+    ds, mean = metrics.ensemble_distance_matrices(qc, gc, "cosine", "fp32")
+    assert torch.equal(mean, metrics.fuse_distmats(ds))
+    ds, mean = metrics.ensemble_distance_matrices(qc, gc, "sqeuclidean", "tf32c")
+    sep = [metrics.compute_distance_matrix(q, g, "sqeuclidean", "tf32c") for q, g in zip(qc, gc)]
+    assert torch.equal(mean, metrics.fuse_distmats(sep))
+
+
 def test_fusion_unaligned_shape():
     from daliid_b200 import metrics
     rng = np.random.default_rng(1)
