@@ -469,6 +469,7 @@ rank_count_v2_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
 // A CTA whose thresholds are not all finite (NaN rows, infinite distances) counts its row with the
 // generic compare loop instead: same results, slow, rare.
 constexpr int kV3Chunk = 64;
+constexpr int kV3MaxChunks = 1;  // threshold chunks per query the split launch takes before v2's byte counters
 #ifndef DALI_V3_DEPTH
 #define DALI_V3_DEPTH 2  // row vectors in flight per thread: ring slots of two float4
 #endif
@@ -1119,7 +1120,13 @@ int launch_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *di
   // limits the number of resident warps
   int tchunk = kV2Chunk;
   if (env_c) tchunk = std::max(8, std::min(kV2Chunk, atoi(env_c)));
-  const int per_cta = use_v1 ? kChunk : tchunk;
+  // v3 (register-resident counters, 64 thresholds per CTA): queries with more positives are counted
+  // by several CTAs that each stream the row (DALI_RANK_V3_CHUNKED, default on up to kV3MaxChunks)
+  static const char *env_ck = getenv("DALI_RANK_V3_CHUNKED");
+  const int v3_max_chunks = env_ck ? atoi(env_ck) : kV3MaxChunks;
+  const bool use_v3 = !use_v1 && !env_c && !env_t && v3_enabled() &&
+                      plan->max_nv <= static_cast<int64_t>(kV3Chunk) * std::max(1, v3_max_chunks);
+  const int per_cta = use_v1 ? kChunk : use_v3 ? kV3Chunk : tchunk;
   const int nchunk = (plan->max_nv + per_cta - 1) / per_cta;
   if (nchunk > 65535) return set_err(ctx, DALI_ERR_UNSUPPORTED, "too many positives for one query");
   // enough CTAs for >= 4 per SM; never split a row below 4096 columns; a v2 CTA counts in
@@ -1131,13 +1138,13 @@ int launch_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *di
   ns = std::max(ns, min_split);
   // many thresholds per query: byte counters, so a thread may see at most 255 elements
   static const char *env_b = getenv("DALI_RANK_BYTE");
-  const bool bytec = !use_v1 && std::min(plan->max_nv, tchunk) > 64 && !(env_b && atoi(env_b) == 0);
+  const bool bytec = !use_v1 && !use_v3 && std::min(plan->max_nv, tchunk) > 64 && !(env_b && atoi(env_b) == 0);
   if (bytec) ns = std::max<int64_t>(ns, (Gs + 250ll * 128 - 1) / (250ll * 128));
   if (ns > 65535) return set_err(ctx, DALI_ERR_UNSUPPORTED, "slab too wide for one launch");
   const int nsplit = static_cast<int>(ns);
   dim3 grid(static_cast<unsigned>(plan->Q), nchunk, nsplit);
   KTimer t(ctx, DALI_K_RANK_COUNT);
-  if (!use_v1 && !env_c && !env_t && plan->max_nv <= kV3Chunk && v3_enabled()) {
+  if (use_v3) {
     const int rc = v3_threads() == 128
         ? launch_v3<128, false>(ctx, grid, plan, dist, ld, g0, Gs, keys, counts, nsplit, FusedOut{})
         : launch_v3<256, false>(ctx, grid, plan, dist, ld, g0, Gs, keys, counts, nsplit, FusedOut{});
@@ -1188,6 +1195,9 @@ int launch_rank_fused(dali_ctx *ctx, const dali_rank_plan *plan, const float *di
   // element, so rows of up to 250 * 256 = 64000 columns are safe (63 vectors + 2 = 254 elements);
   // wider rows take the split launch, which bounds its segments the same way.
   const bool bytec = plan->max_nv > 64;
+  static const char *env_ck = getenv("DALI_RANK_V3_CHUNKED");
+  if (bytec && v3_enabled() && plan->max_nv <= static_cast<int64_t>(kV3Chunk) * (env_ck ? atoi(env_ck) : kV3MaxChunks))
+    return DALI_OK;  // gather + chunked v3 count + finalize
   static const char *env_b = getenv("DALI_RANK_FUSED_BYTE");
   if (bytec && (G > 250ll * 256 || (env_b && atoi(env_b) == 0))) return DALI_OK;
   DALI_CUDA_OK(ctx, cudaMemsetAsync(cmc_cnt, 0, sizeof(int32_t) * (max_rank + 1), ctx->stream));
