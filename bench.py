@@ -732,15 +732,15 @@ def run_ours(args):
                 # see profiles/ (r02_c2_full.md: read + write per launch of this kernel at this shape);
                 # algorithmic minimum = 161 MB of fp16 operand planes + 214 MB of distance matrix
                 "traffic": None,
-                "traffic_source": "not measured live (ncu capture of the same command: profiles/r02_c2_full.md)",
+                "traffic_source": "not measured live (ncu capture of the same command: profiles/r02b_c2_full.md)",
                 "peak_source": pk["source"] + " bf16 burst; the fp32-class splits issue several tensor "
                                "passes per algorithmic FLOP: ceiling of frac = 1/3 for f16x3 (three 16-bit "
                                "passes), 1/2 for tf32, 1/4 for tf32c (1 TF32 + 2 bf16 passes), 1/6 for tf32x3",
                 "avg_launch_ms": ms_dm / max(n_dm, 1) if n_dm else None}
-    roofline_rank = {"bound": "hbm", "kernel": "rank_count_v2_kernel (one launch: thresholds, counting, CMC/AP epilogue)"
-                     if world == 1 else "rank_count_v2_kernel", "achieved": rank_gbs,
+    roofline_rank = {"bound": "hbm", "kernel": "rank_count_v3_kernel (one launch: thresholds, counting, CMC/AP epilogue)"
+                     if world == 1 else "rank_count_v3_kernel", "achieved": rank_gbs,
                      "peak": pk["hbm"], "unit": "GB/s", "frac": (rank_gbs / pk["hbm"]) if rank_gbs else None,
-                     "traffic": None,  # ncu only: profiles/r02_c2_full.md
+                     "traffic": None,  # ncu only: profiles/r02b_c2_full.md
                      "avg_launch_ms": ms_rc / max(n_rc, 1) if n_rc else None}
 
     line = {

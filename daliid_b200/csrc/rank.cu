@@ -1095,6 +1095,9 @@ static int launch_v3(dali_ctx *ctx, dim3 grid, const dali_rank_plan *plan, const
     if (!(env_tight && atoi(env_tight) == 0) && lnb == 11)
       rank_count_v3_kernel<11, THREADS, 7, FUSED, true><<<grid, THREADS, 0, ctx->stream>>>(
           dist, ld, g0, Gs, plan->d_off, plan->d_nv, plan->d_gid, keys, counts, nsplit, fo);
+    else if (!(env_tight && atoi(env_tight) == 0) && lnb == 12)
+      rank_count_v3_kernel<12, THREADS, 7, FUSED, true><<<grid, THREADS, 0, ctx->stream>>>(
+          dist, ld, g0, Gs, plan->d_off, plan->d_nv, plan->d_gid, keys, counts, nsplit, fo);
     else if (lnb == 12) DALI_V3_LAUNCH(12, 7); else DALI_V3_LAUNCH(11, 7);
   } else if (per_thread < (1 << 10)) {
     if (lnb == 12) DALI_V3_LAUNCH(12, 10); else DALI_V3_LAUNCH(11, 10);
