@@ -193,7 +193,8 @@ def test_roc_over_all_pairs_equals_sklearn(tiny, tmp_path, monkeypatch):
 
 # ---- whole ranked lists (get_subset*) -------------------------------------------
 
-@pytest.mark.parametrize("Q,G", [(1, 100003), (7, 4099), (300, 257), (1, 1)])
+@pytest.mark.parametrize("Q,G", [(1, 100003), (7, 4099), (300, 257), (1, 1), (3, 4096), (2, 4097), (70000, 5),
+                                 (129, 12936)])
 @pytest.mark.parametrize("descending", [False, True])
 def test_argsort_rows_equals_torch_stable(Q, G, descending):
     from daliid_b200 import metrics
@@ -208,6 +209,16 @@ def test_argsort_rows_equals_torch_stable(Q, G, descending):
     assert torch.equal(out.cpu().long(), ref)
     host = metrics.argsort_rows(d.numpy(), descending)
     np.testing.assert_array_equal(host, ref.numpy())
+
+
+def test_argsort_rows_strided_input_and_distances_in_place():
+    """A row-padded matrix (what compute_distance_matrix returns) and a slice of it."""
+    from daliid_b200 import metrics
+    g = torch.Generator().manual_seed(11)
+    base = torch.randn(64, 1000, generator=g).cuda()
+    view = base[:, 3:903]  # leading dimension 1000, 900 columns, unaligned start
+    out = metrics.argsort_rows(view, False)
+    assert torch.equal(out.cpu().long(), torch.argsort(view.cpu(), dim=1, stable=True))
 
 
 def test_rank_by_similarity_matches_reference_arithmetic():
