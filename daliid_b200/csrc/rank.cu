@@ -545,7 +545,12 @@ struct SlicedCounters {
   }
 };
 
-template <int LOG2NB, int THREADS, int PL, bool FUSED, bool TIGHT = false>
+// CAP = thresholds one CTA takes: 64 -> the bit-sliced register counters described above; 256 (queries
+// with many positives: DeepChange's ~120, up to 254) -> v3's front end (FMA bins, 16-byte table fill,
+// float exact path, cp.async ring) in front of v2's 8-bit private counters, packed four to a word in
+// DYNAMIC shared memory [bucket group][thread] and bumped with one conflict-free red.shared.add (a
+// thread must then see at most 255 elements: the launcher checks).
+template <int LOG2NB, int THREADS, int PL, bool FUSED, bool TIGHT = false, int CAP = 64>
 __global__ void __launch_bounds__(THREADS, TIGHT ? DALI_V3_MINB * 256 / THREADS : 1)
 rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int64_t Gs,
                      const int64_t *__restrict__ off, const int32_t *__restrict__ nvalid,
@@ -554,6 +559,9 @@ rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
   constexpr int NB = 1 << LOG2NB;  // bins 0 .. NB; thresholds fall into 2 .. NB-2
   constexpr int NE = NB + 8;       // table entries (a multiple of 8)
   constexpr int kJunkCap = 64;
+  constexpr int kV3Chunk = CAP;  // (shadows the namespace constant: this CTA's capacity)
+  constexpr bool BYTES = CAP > 64;
+  static_assert(THREADS >= CAP && THREADS % (CAP < THREADS ? CAP : THREADS) == 0, "one thread per threshold at least");
   __shared__ uint64_t Tu[kV3Chunk + kJunkCap];  // unsorted thresholds, then the junk composites
   __shared__ uint64_t T[kV3Chunk + 1];          // sorted, T[n] = sentinel above every composite
   __shared__ float Tf[kV3Chunk + 1];            // sorted thresholds as distances, Tf[n] = +inf
@@ -563,6 +571,7 @@ rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
   __shared__ uint16_t tb[kV3Chunk + 2];
   __shared__ double s_term[FUSED ? kV3Chunk : 1];
   __shared__ __align__(16) uint16_t lut[NE];
+  __shared__ uint32_t bh2[BYTES ? CAP + 4 : 1];  // byte-counter variant: elements per bucket
   // the row is streamed through a per-thread ring in shared memory with cp.async: the loads of the
   // first DEPTH iterations are in flight while the prologue runs, and no registers are held for them
   constexpr int DEPTH = DALI_V3_DEPTH;
@@ -634,12 +643,12 @@ rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
   const int nj = min(m - n, kJunkCap);  // staged; more than that are read from global memory later
 
   // 1. thresholds, sorted by counting (composites are distinct: gallery ids differ)
-  if (tid < n + nj) {
-    const uint32_t g = static_cast<uint32_t>(__ldg(gid + o + tid));
-    const uint32_t k = FUSED ? dist_key(__ldg(row + g)) : __ldg(keys + o + tid);
-    Tu[tid] = composite(k, g);
+  for (int t = tid; t < n + nj; t += THREADS) {
+    const uint32_t g = static_cast<uint32_t>(__ldg(gid + o + t));
+    const uint32_t k = FUSED ? dist_key(__ldg(row + g)) : __ldg(keys + o + t);
+    Tu[t] = composite(k, g);
   }
-  if (tid <= kV3Chunk) hist[tid] = 0u;
+  for (int t = tid; t <= kV3Chunk; t += THREADS) hist[t] = 0u;
   __syncthreads();
   {
     constexpr int TPT = THREADS / kV3Chunk;  // threads per threshold (4 or 2), adjacent lanes
@@ -835,11 +844,89 @@ rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
         hist[32 * warp + lane] = total;
       }
     };
-    if (n <= 32) run(std::integral_constant<int, 1>{}); else run(std::integral_constant<int, 2>{});
+    // many thresholds: 8-bit private counters in shared memory, bucket b = #{thresholds <= element}
+    auto run_bytes = [&]() {
+      extern __shared__ __align__(16) uint32_t cnt_dyn[];
+      const int groups = (n + 4) >> 2;  // buckets 0 .. n
+      for (int i = tid; i < groups * THREADS; i += THREADS) cnt_dyn[i] = 0u;
+      __syncthreads();
+      const uint32_t cnt_s = static_cast<uint32_t>(__cvta_generic_to_shared(cnt_dyn)) + static_cast<uint32_t>(tid << 2);
+      auto bump = [&](uint32_t b) {
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(cnt_s + (((b >> 2) * THREADS) << 2)),
+                     "r"(1u << ((b & 3u) << 3)) : "memory");
+      };
+      uint32_t ga = gbase + static_cast<uint32_t>(cv0) + 4u * tid;
+      int slot = 0;
+#pragma unroll 1
+      for (int it = 0; it < niter; ++it) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+        float4 x0, x1;
+        const uint32_t src = ring_s + static_cast<uint32_t>(slot * 2 * THREADS * 16);
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x0.x), "=f"(x0.y), "=f"(x0.z), "=f"(x0.w) : "r"(src) : "memory");
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x1.x), "=f"(x1.y), "=f"(x1.z), "=f"(x1.w) : "r"(src + THREADS * 16) : "memory");
+        issue(slot, it + DEPTH);
+        const float d[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        uint32_t e[8];
+#pragma unroll
+        for (int sidx = 0; sidx < 8; ++sidx) e[sidx] = entry_of(d[sidx]);
+        // (with ~120 thresholds in 4096 bins some lane needs the exact path in nearly every group; a
+        // warp-wide "while any lane has a flagged slot" loop that re-reads the element from the ring
+        // was measured slower than these eight per-slot branches: 2.01 vs 1.88 ms at DeepChange)
+        if ((e[0] | e[1] | e[2] | e[3] | e[4] | e[5] | e[6] | e[7]) & 0x8000u) {
+#pragma unroll
+          for (int sidx = 0; sidx < 8; ++sidx)
+            if (e[sidx] & 0x8000u) e[sidx] = exact(e[sidx], d[sidx], ga + (sidx < 4 ? 0u : 4u * THREADS) + (sidx & 3));
+        }
+#pragma unroll
+        for (int sidx = 0; sidx < 8; ++sidx) bump(e[sidx]);
+        ga += 8u * THREADS;
+        slot = slot + 1 == DEPTH ? 0 : slot + 1;
+      }
+      auto put = [&](float dv, uint32_t g) {
+        uint32_t e = entry_of(dv);
+        if (e & 0x8000u) e = exact(e, dv, g);
+        bump(e);
+      };
+      if (tid < head) put(__ldg(row + c0 + tid), gbase + static_cast<uint32_t>(c0 + tid));
+      const int64_t ct0 = cv0 + 4 * static_cast<int64_t>(nvec);
+      if (tid < tail) put(__ldg(row + ct0 + tid), gbase + static_cast<uint32_t>(ct0 + tid));
+      __syncthreads();
+      // per bucket group: the four byte fields of all threads' words, summed as two pairs of 16-bit
+      // fields (256 x 255 < 65536), one warp per group
+      const int lane = tid & 31, warp = tid >> 5;
+      for (int g4 = warp; g4 < groups; g4 += THREADS / 32) {
+        uint32_t s02 = 0, s13 = 0;
+        for (int e2 = lane; e2 < THREADS; e2 += 32) {
+          const uint32_t w = cnt_dyn[g4 * THREADS + e2];
+          s02 += w & 0x00FF00FFu;
+          s13 += (w >> 8) & 0x00FF00FFu;
+        }
+        s02 = __reduce_add_sync(0xffffffffu, s02);
+        s13 = __reduce_add_sync(0xffffffffu, s13);
+        if (lane == 0) {
+          const int b = 4 * g4;
+          bh2[b] = s02 & 0xFFFFu;
+          if (b + 1 <= kV3Chunk) bh2[b + 1] = s13 & 0xFFFFu;
+          if (b + 2 <= kV3Chunk) bh2[b + 2] = s02 >> 16;
+          if (b + 3 <= kV3Chunk) bh2[b + 3] = s13 >> 16;
+        }
+      }
+      __syncthreads();
+      if (tid < n) {  // count_below(T[i]) = elements in buckets 0 .. i
+        uint32_t sum = 0;
+        for (int b = 0; b <= tid; ++b) sum += bh2[b];
+        hist[tid] = sum;
+      }
+    };
+    if constexpr (BYTES) {
+      run_bytes();
+    } else {
+      if (n <= 32) run(std::integral_constant<int, 1>{}); else run(std::integral_constant<int, 2>{});
+    }
   } else {
     // generic: bucket histogram with exact compares, then a prefix sum
     __shared__ uint32_t bh[kV3Chunk + 1];
-    if (tid <= kV3Chunk) bh[tid] = 0u;
+    for (int t = tid; t <= kV3Chunk; t += THREADS) bh[t] = 0u;
     __syncthreads();
     for (int64_t c = c0 + tid; c < c1; c += THREADS) {
       const uint64_t cc = composite(dist_key(__ldg(row + c)), gbase + static_cast<uint32_t>(c));
@@ -1110,6 +1197,29 @@ static int launch_v3(dali_ctx *ctx, dim3 grid, const dali_rank_plan *plan, const
   return DALI_OK;
 }
 
+// v3 front end + byte counters: queries with 65 .. 254 valid positives (one chunk), rows of which a
+// thread sees at most 255 elements
+static bool v3b_enabled() {
+  static const char *env = getenv("DALI_RANK_V3B");
+  return v3_enabled() && !(env && atoi(env) == 0);
+}
+static bool v3b_fits(int64_t Gs, int nsplit) {
+  const int64_t per = (((Gs + nsplit - 1) / nsplit) + 3) & ~int64_t(3);
+  return ((per / 4 + 2 * 256 - 1) / (2 * 256)) * 8 + 2 <= 255;
+}
+template <bool FUSED>
+static int launch_v3b(dali_ctx *ctx, dim3 grid, const dali_rank_plan *plan, const float *dist, int64_t ld,
+                      int64_t g0, int64_t Gs, const uint32_t *keys, int32_t *counts, int nsplit, FusedOut fo) {
+  const size_t smem = static_cast<size_t>((std::min(plan->max_nv, 254) + 4) >> 2) * 256 * sizeof(uint32_t);
+  // static (38 KB) + dynamic shared memory exceed 48 KB even for few buckets: always opt in, for the most
+  if (int rc = ensure_dyn_smem(ctx, reinterpret_cast<const void *>(&rank_count_v3_kernel<12, 256, 7, FUSED, false, 256>),
+                               size_t(64) * 256 * sizeof(uint32_t)))
+    return rc;
+  rank_count_v3_kernel<12, 256, 7, FUSED, false, 256><<<grid, 256, smem, ctx->stream>>>(
+      dist, ld, g0, Gs, plan->d_off, plan->d_nv, plan->d_gid, keys, counts, nsplit, fo);
+  return DALI_OK;
+}
+
 int launch_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist, int64_t ld,
                       int64_t g0, int64_t Gs, const uint32_t *keys, int32_t *counts) {
   if (plan->M == 0 || plan->Q == 0) return DALI_OK;
@@ -1141,13 +1251,17 @@ int launch_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *di
   ns = std::max(ns, min_split);
   // many thresholds per query: byte counters, so a thread may see at most 255 elements
   static const char *env_b = getenv("DALI_RANK_BYTE");
-  const bool bytec = !use_v1 && !use_v3 && std::min(plan->max_nv, tchunk) > 64 && !(env_b && atoi(env_b) == 0);
+  const bool use_v3b = !use_v1 && !use_v3 && !env_c && !env_t && v3b_enabled() && plan->max_nv > kV3Chunk && plan->max_nv <= 254;
+  if (use_v3b) ns = std::max<int64_t>(ns, (Gs + 250ll * 256 - 1) / (250ll * 256));
+  const bool bytec = !use_v1 && !use_v3 && !use_v3b && std::min(plan->max_nv, tchunk) > 64 && !(env_b && atoi(env_b) == 0);
   if (bytec) ns = std::max<int64_t>(ns, (Gs + 250ll * 128 - 1) / (250ll * 128));
   if (ns > 65535) return set_err(ctx, DALI_ERR_UNSUPPORTED, "slab too wide for one launch");
   const int nsplit = static_cast<int>(ns);
   dim3 grid(static_cast<unsigned>(plan->Q), nchunk, nsplit);
   KTimer t(ctx, DALI_K_RANK_COUNT);
-  if (use_v3) {
+  if (use_v3b && v3b_fits(Gs, nsplit)) {
+    if (int rc = launch_v3b<false>(ctx, grid, plan, dist, ld, g0, Gs, keys, counts, nsplit, FusedOut{})) return rc;
+  } else if (use_v3) {
     const int rc = v3_threads() == 128
         ? launch_v3<128, false>(ctx, grid, plan, dist, ld, g0, Gs, keys, counts, nsplit, FusedOut{})
         : launch_v3<256, false>(ctx, grid, plan, dist, ld, g0, Gs, keys, counts, nsplit, FusedOut{});
@@ -1212,6 +1326,8 @@ int launch_rank_fused(dali_ctx *ctx, const dali_rank_plan *plan, const float *di
         ? launch_v3<128, true>(ctx, grid, plan, dist, ld, 0, G, nullptr, nullptr, 1, fo)
         : launch_v3<256, true>(ctx, grid, plan, dist, ld, 0, G, nullptr, nullptr, 1, fo);
     if (rc) return rc;
+  } else if (bytec && v3b_enabled() && v3b_fits(G, 1)) {
+    if (int rc = launch_v3b<true>(ctx, grid, plan, dist, ld, 0, G, nullptr, nullptr, 1, fo)) return rc;
   } else if (bytec) {
     const size_t smem = v2_smem_bytes(12, plan->max_nv, 256, true);
     if (int rc = ensure_dyn_smem(ctx, reinterpret_cast<const void *>(&rank_count_v2_kernel<12, 256, true, true>), smem))
