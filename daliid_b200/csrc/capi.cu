@@ -810,10 +810,14 @@ static int fused_keys_counts(dali_ctx *ctx, dali_rank_plan *plan, const float *q
   return DALI_OK;
 }
 
+static bool fused_switched_on(const dali_ctx *ctx) {
+  static const char *env = getenv("DALI_FUSED_COUNT");  // 1 / 0 override the context's switch
+  return env ? atoi(env) != 0 : ctx->fused_count != 0;
+}
+
 static bool fused_eligible(dali_ctx *ctx, const dali_rank_plan *plan, const float *q, const float *g, int64_t Q,
                            int64_t G, int64_t D, int precision, const float *distmat_opt) {
-  static const char *env = getenv("DALI_FUSED_COUNT");  // 1 / 0 override the context's switch
-  if (env ? atoi(env) == 0 : !ctx->fused_count) return false;
+  if (!fused_switched_on(ctx)) return false;
   if (distmat_opt || !fused_count_supports(precision) || Q == 0 || G == 0 || plan->M == 0) return false;
   if (plan->max_m > fused_max_matches(round_up(D, 32))) return false;
   // a big host gallery is better served by the chunked copy / contraction pipeline (the copy
@@ -1570,7 +1574,9 @@ int dali_eval_features_f32(dali_ctx *ctx, const float *q, int64_t Q, const float
   } hold;
   dali_rank_plan *&fplan = hold.p;  // built early for the fused path; reused by the matrix path
   if (accum_mode == DALI_ACCUM_CY_F32 || accum_mode == DALI_ACCUM_PY_F64) {
-    bool try_fused = !distmat_opt && fused_count_supports(precision) && Q && G;
+    // (the switch is tested first: the fused path needs the plan -- a 150 KB label comparison even
+    //  when cached -- BEFORE anything is launched, the matrix path builds it under the contraction)
+    bool try_fused = fused_switched_on(ctx) && !distmat_opt && fused_count_supports(precision) && Q && G;
     if (try_fused) {
       rc = dali_rank_plan_create(ctx, q_pid, g_pid, q_cam, g_cam, Q, G, &fplan);
       if (rc) return rc;
