@@ -818,6 +818,16 @@ distmat_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               }
               __syncwarp();
             }
+#ifdef DALI_UMMA_NO_STORE  // probe build (tests/probes/build_variants.sh): the tile is computed, not stored
+            if (v[0] != 0x7fc12345u) continue;
+#endif
+            // What the stores cost (round 2, tests/probes/contraction_probe.py): without them the
+            // launch is 21-24 us shorter at D = 768 (0.168 -> 0.147 ms) and at D = 2048 (0.418 ->
+            // 0.394 ms) alike -- the staging writes and the TMA store's reads add 10 % / 4 % to the
+            // shared-memory traffic of a tile, which the operand reads of the MMAs already saturate.
+            // Not the L2 (an evict-first policy on the stores changed nothing), not bursts (pacing the
+            // eight blocks of a tile over its MMA time: -1 %), and registers -> global memory without
+            // staging (32 rows x 128 B per warp instruction) was slower: 0.190 / 0.452 ms.
             if (p.tma_out) {
               if (EPI != kAccum || p.store_out) {
                 const uint32_t buf = stg_base + static_cast<uint32_t>(((nstore++) & 1) * 4096);
