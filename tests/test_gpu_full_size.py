@@ -279,3 +279,28 @@ def test_c5_slab_fused_topk_equals_materialised_topk():
     ev, ei = metrics.topk_identify(d, k=k)
     assert torch.equal(v[sel], ev) and torch.equal(i[sel] - 3_000_000, ei)
     assert bool((v[:, 1:] >= v[:, :-1]).all())        # ascending within every row
+
+
+def test_c4_three_model_ensemble_full_size(market):
+    """BASELINE config 3 (evaluate.py:260-279): three Market-shaped models, the mean formed in the
+    contractions' epilogues against the three separate matrices + the fusion pass, full size; the
+    reference's own numpy expression on a row subset; CMC / mAP / AP / first rank of the ensemble
+    bit-equal between the two routes."""
+    from daliid_b200 import metrics, synth
+    _, _, qp, gp, qc, gc = market
+    sets = [synth.make_config("market_vit", seed=sd, device="cuda")[:2] for sd in (12, 13, 14)]
+    qs, gs = [s_[0] for s_ in sets], [s_[1] for s_ in sets]
+    sep = [metrics.compute_distance_matrix(q, g, "cosine") for q, g in zip(qs, gs)]
+    ref = metrics.fuse_distmats(sep)
+    ds, mean = metrics.ensemble_distance_matrices(qs, gs, "cosine")
+    assert torch.equal(mean, ref)
+    for a, b in zip(ds, sep):
+        assert torch.equal(a, b)
+    rows = slice(1000, 1200)
+    cpu = [d[rows].cpu().numpy() for d in sep]
+    assert np.array_equal(mean[rows].cpu().numpy(), (cpu[0] + cpu[1] + cpu[2]) / 3)
+    only = metrics.ensemble_distance_matrices(qs, gs, "cosine", individual=False)[1]
+    assert torch.equal(only, ref)
+    a = metrics.evaluate_rank_detailed(mean, qp, gp, qc, gc)
+    b = metrics.evaluate_rank_detailed(ref, qp, gp, qc, gc)
+    assert np.array_equal(a[0], b[0]) and a[1] == b[1] and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])

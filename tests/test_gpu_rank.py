@@ -311,3 +311,75 @@ def test_entry_points_restore_the_callers_device():
     metrics.compute_distance_matrix(x, x, "cosine")
     assert torch.cuda.current_device() == 0
     assert torch.empty(1, device="cuda").device.index == 0
+
+
+# ---- counting kernel v3 (FMA bins + bit-sliced counters; 8-bit counters for 65..254 positives) --------
+
+def _labels(Q, G, per_id, ncam, rng):
+    """per_id gallery items per identity, cameras random: positives per query up to per_id."""
+    n_ids = max(1, G // per_id)
+    gp = np.arange(G) % n_ids
+    gc = rng.integers(0, ncam, G)
+    qp = rng.integers(0, n_ids, Q)
+    qc = rng.integers(0, ncam, Q)
+    return qp.astype(np.int32), gp.astype(np.int32), qc.astype(np.int32), gc.astype(np.int32)
+
+
+@pytest.mark.parametrize("per_id", [1, 2, 31, 32, 33, 63, 64, 65, 66, 130, 254])
+@pytest.mark.parametrize("kind", ["cosine_like", "clustered", "wide_range", "negative", "constant", "quantised"])
+def test_v3_threshold_count_boundaries_and_value_distributions(per_id, kind):
+    """1 / 32 / 33 / 64 / 65 / 254 thresholds per query (one and two mask words, the 8-bit counters) under
+    value distributions that stress the bin map: thresholds much closer together than their size
+    (the scale cap), twelve decades of dynamic range, negative values, one repeated value (every
+    element shares the thresholds' bin), heavily quantised values (ties decided by gallery id)."""
+    rng = np.random.default_rng(per_id * 7 + len(kind))
+    Q, G = 9, 1531 if per_id < 100 else 2047
+    qp, gp, qc, gc = _labels(Q, G, per_id, 4, rng)
+    if kind == "cosine_like":
+        d = rng.random((Q, G), dtype=np.float32) * 1.4 + 0.05
+    elif kind == "clustered":
+        d = (1.0 + rng.random((Q, G)) * 3e-6).astype(np.float32)
+    elif kind == "wide_range":
+        d = (10.0 ** rng.uniform(-18, 18, (Q, G))).astype(np.float32)
+    elif kind == "negative":
+        d = (rng.standard_normal((Q, G)) * 50 - 100).astype(np.float32)
+    elif kind == "constant":
+        d = np.full((Q, G), 0.625, dtype=np.float32)
+        d[:, ::7] = 0.5
+    else:
+        d = (np.round(rng.random((Q, G)) * 8) / 8).astype(np.float32)
+    for where in ("device", "device_strided"):
+        _check(d, qp, gp, qc, gc, where=where)
+
+
+def test_v3_non_finite_rows_take_the_generic_path():
+    rng = np.random.default_rng(5)
+    Q, G = 8, 700
+    qp, gp, qc, gc = _labels(Q, G, 20, 3, rng)
+    d = rng.random((Q, G), dtype=np.float32)
+    d[0, :] = np.nan                      # every threshold NaN
+    d[1, gp == qp[1]] = np.inf            # thresholds +inf, other elements finite
+    d[2, gp == qp[2]] = -np.inf
+    d[3, ::3] = np.nan                    # NaN elements among finite thresholds (and some NaN thresholds)
+    d[4, 5] = np.inf; d[4, 6] = -np.inf; d[4, 7] = -0.0; d[4, 8] = 0.0
+    d[5, :] = 0.0; d[5, ::2] = -0.0       # +-0 everywhere
+    d[6, :] = np.float32(1e-45)           # denormals
+    d[6, ::5] = np.float32(3e-45)
+    _check(d, qp, gp, qc, gc, where="device")
+
+
+def test_v3_row_lengths_around_the_vector_loop():
+    """Head / tail columns of misaligned rows and rows shorter than one iteration of the ring."""
+    rng = np.random.default_rng(9)
+    for G in (1, 2, 3, 4, 5, 63, 64, 65, 511, 512, 513, 2047, 2048, 2049, 4100):
+        Q = 5
+        qp, gp, qc, gc = _labels(Q, G, min(G, 6), 2, rng)
+        d = rng.random((Q, G), dtype=np.float32)
+        if not (gp[None, :] == qp[:, None]).any():
+            continue
+        try:
+            _check(d, qp, gp, qc, gc, where="device_strided")
+        except AssertionError as e:
+            if "do not appear in gallery" in str(e):  # every match same camera: upstream raises too
+                continue
+            raise
