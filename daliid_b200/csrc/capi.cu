@@ -922,6 +922,7 @@ void dali_ctx_destroy(dali_ctx *ctx) {
   for (auto e : ctx->chunk_events) cudaEventDestroy(e);
   for (auto st : ctx->copy_streams)
     if (st) cudaStreamDestroy(st);
+  if (ctx->plan_stream) cudaStreamDestroy(ctx->plan_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -1413,7 +1414,14 @@ int dali_rank_plan_create(dali_ctx *ctx, const int32_t *q_pid, const int32_t *g_
     }
     ctx->pool_ready = true;
   }
-  if ((e = cudaMallocAsync(&p->d_block, total, ctx->stream)) != cudaSuccess) return fail(e, "allocation");
+  // The upload and the expansion run on their own stream: a caller that enqueued its contraction
+  // first (eval_features) gets them done beside it instead of behind it; ctx->stream waits on the
+  // plan's `ready` event below.
+  if (!ctx->plan_stream &&
+      (e = cudaStreamCreateWithFlags(&ctx->plan_stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return fail(e, "stream");
+  cudaStream_t ps = ctx->plan_stream;
+  if ((e = cudaMallocAsync(&p->d_block, total, ps)) != cudaSuccess) return fail(e, "allocation");
   char *db = static_cast<char *>(p->d_block);
   p->d_off = reinterpret_cast<int64_t *>(db);
   p->d_lo = reinterpret_cast<int64_t *>(db + b_off);
@@ -1424,14 +1432,17 @@ int dali_rank_plan_create(dali_ctx *ctx, const int32_t *q_pid, const int32_t *g_
   p->d_njunk = reinterpret_cast<int32_t *>(db + stage_bytes + b_q32);
   p->d_gid = reinterpret_cast<int32_t *>(db + stage_bytes + 2 * b_q32);
   p->d_slot = reinterpret_cast<int32_t *>(db + stage_bytes + 2 * b_q32 + b_gid);
-  if ((e = cudaMemcpyAsync(p->d_block, hs, stage_bytes, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+  if ((e = cudaMemcpyAsync(p->d_block, hs, stage_bytes, cudaMemcpyHostToDevice, ps)) != cudaSuccess)
     return fail(e, "upload");
-  if ((e = cudaEventRecord(ctx->plan_stage_done, ctx->stream)) != cudaSuccess) return fail(e, "event record");
-  rc = launch_plan_expand(ctx, p);
+  if ((e = cudaEventRecord(ctx->plan_stage_done, ps)) != cudaSuccess) return fail(e, "event record");
+  rc = launch_plan_expand(ctx, p, ps);
   if (rc) {
     dali_rank_plan_destroy(p);
     return rc;
   }
+  if ((e = cudaEventCreateWithFlags(&p->ready, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
+  if ((e = cudaEventRecord(p->ready, ps)) != cudaSuccess) return fail(e, "event record");
+  if ((e = cudaStreamWaitEvent(ctx->stream, p->ready, 0)) != cudaSuccess) return fail(e, "event wait");
   if (use_cache) {  // keep it for the next call with the same labels
     p->labels.resize(2 * (Q + G));
     if (Q) {
@@ -1442,8 +1453,6 @@ int dali_rank_plan_create(dali_ctx *ctx, const int32_t *q_pid, const int32_t *g_
       std::memcpy(p->labels.data() + Q, g_pid, sizeof(int32_t) * G);
       std::memcpy(p->labels.data() + 2 * Q + G, g_cam, sizeof(int32_t) * G);
     }
-    if (cudaEventCreateWithFlags(&p->ready, cudaEventDisableTiming) == cudaSuccess)
-      cudaEventRecord(p->ready, ctx->stream);
     dali_rank_plan *old = ctx->cached_plan;
     ctx->cached_plan = p;
     p->refs++;

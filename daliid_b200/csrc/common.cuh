@@ -160,6 +160,7 @@ struct dali_ctx {
   void *plan_stage = nullptr;  // pinned staging of the rank plan (async upload)
   size_t plan_stage_cap = 0;
   cudaEvent_t plan_stage_done = nullptr;  // the last upload out of plan_stage
+  cudaStream_t plan_stream = nullptr;     // upload + expansion of a new plan run beside the contraction
   bool pool_ready = false;
   // H2D of host operands on side streams, overlapped with compute
   static constexpr int kCopyStreams = 4;
@@ -306,7 +307,7 @@ int launch_fused_sort_thresholds(dali_ctx *ctx, const dali_rank_plan *plan, cons
                                  float *sorted_thr, int32_t *sorted_slot, int32_t *flag);
 int launch_fused_prefix(dali_ctx *ctx, const dali_rank_plan *plan, const int32_t *hist,
                         const int32_t *sorted_slot, int32_t *counts, int pass);
-int launch_plan_expand(dali_ctx *ctx, const dali_rank_plan *plan);
+int launch_plan_expand(dali_ctx *ctx, const dali_rank_plan *plan, cudaStream_t stream = nullptr);
 int launch_rank_gather(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist, int64_t ld,
                        int64_t g0, int64_t Gs, uint32_t *keys);
 int launch_rank_count(dali_ctx *ctx, const dali_rank_plan *plan, const float *dist, int64_t ld,

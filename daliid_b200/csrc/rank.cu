@@ -1117,9 +1117,9 @@ int launch_fused_prefix(dali_ctx *ctx, const dali_rank_plan *plan, const int32_t
   return DALI_OK;
 }
 
-int launch_plan_expand(dali_ctx *ctx, const dali_rank_plan *plan) {
+int launch_plan_expand(dali_ctx *ctx, const dali_rank_plan *plan, cudaStream_t stream) {
   if (plan->Q == 0) return DALI_OK;
-  plan_expand_kernel<<<static_cast<unsigned>((plan->Q + 3) / 4), 128, 0, ctx->stream>>>(
+  plan_expand_kernel<<<static_cast<unsigned>((plan->Q + 3) / 4), 128, 0, stream ? stream : ctx->stream>>>(
       plan->Q, plan->d_off, plan->d_lo, plan->d_qcam, plan->d_order, plan->d_gcam, plan->d_gid,
       plan->d_nv, plan->d_njunk, plan->d_slot);
   DALI_CUDA_OK(ctx, cudaGetLastError());
