@@ -65,3 +65,33 @@ def test_share_queries_without_a_process_group_is_the_identity():
     assert sharded.share_queries(q, 0) is q
     qn = np.zeros((4, 8), dtype=np.float32)
     assert sharded.share_queries(qn, 0) is qn
+
+
+def test_ensemble_argument_checks_need_no_gpu():
+    """ensemble_distance_matrices validates its model list before touching the device."""
+    import pytest
+    from daliid_b200 import metrics
+    a = np.zeros((4, 8), dtype=np.float32)
+    b = np.zeros((6, 8), dtype=np.float32)
+    with pytest.raises(ValueError):
+        metrics.ensemble_distance_matrices([], [])
+    with pytest.raises(ValueError):
+        metrics.ensemble_distance_matrices([a, a], [b])
+    with pytest.raises(ValueError):  # the models must share the query and gallery sets
+        metrics.ensemble_distance_matrices([a, np.zeros((5, 8), dtype=np.float32)], [b, b])
+    with pytest.raises(ValueError):  # feature dimensions of one model must agree
+        metrics.ensemble_distance_matrices([a], [np.zeros((6, 9), dtype=np.float32)])
+    with pytest.raises(ValueError):
+        metrics.ensemble_distance_matrices([a] * 9, [b] * 9)
+
+
+def test_label_canonicalisation_keeps_int32_and_densifies_strings():
+    from daliid_b200 import metrics
+    q = np.array([3, 1], dtype=np.int32)
+    g = np.array([1, 3, 7], dtype=np.int32)
+    cq, cg = metrics.canonicalize_labels(q, g)
+    assert cq.dtype == np.int32 and np.array_equal(cq, q) and np.array_equal(cg, g)
+    cq, cg = metrics.canonicalize_labels(np.array(["b", "a"]), np.array(["a", "b", "zz"]))
+    assert cq.dtype == np.int32 and (cq[0] == cg[1]) and (cq[1] == cg[0]) and cg[2] not in (cq[0], cq[1])
+    cq, cg = metrics.canonicalize_labels(np.array([2 ** 40, 5]), np.array([5, 2 ** 40, 9]))
+    assert (cq[0] == cg[1]) and (cq[1] == cg[0]) and len({int(x) for x in cg}) == 3
