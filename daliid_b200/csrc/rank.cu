@@ -580,7 +580,7 @@ rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
   __shared__ uint32_t part[2 * kPartPlanes * 32];  // [threshold word][plane][partial sum]
 
   const int64_t q = blockIdx.x;
-  const int chunk = blockIdx.y;
+  const int chunk = FUSED ? 0 : blockIdx.y;  // FUSED: one CTA per query, the whole row, all thresholds
   const int tid = threadIdx.x;
   const float *row = dist + q * ld;
 
@@ -588,10 +588,10 @@ rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
   // aligned part, dealt out as float4 vectors: iteration `it` gives a thread the vectors
   // tid + 2 it THREADS and that + THREADS.  Vectors beyond the range read as NaN, which sorts above
   // every threshold and so counts for none.
-  const int64_t per = nsplit == 1 ? ((Gs + 3) & ~int64_t(3)) : ((((Gs + nsplit - 1) / nsplit) + 3) & ~int64_t(3));
-  const int64_t c0r = per * static_cast<int64_t>(blockIdx.z);
+  const int64_t per = (FUSED || nsplit == 1) ? ((Gs + 3) & ~int64_t(3)) : ((((Gs + nsplit - 1) / nsplit) + 3) & ~int64_t(3));
+  const int64_t c0r = FUSED ? 0 : per * static_cast<int64_t>(blockIdx.z);
   const int64_t c0 = c0r < Gs ? c0r : Gs;
-  const int64_t c1 = (c0 + per) < Gs ? (c0 + per) : Gs;
+  const int64_t c1 = (FUSED || (c0 + per) >= Gs) ? Gs : (c0 + per);
   const int mis = static_cast<int>((reinterpret_cast<uintptr_t>(row + c0) >> 2) & 3);
   int head = (4 - mis) & 3;
   if (head > c1 - c0) head = static_cast<int>(c1 - c0);
@@ -655,7 +655,8 @@ rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
     const int i = tid / TPT, part = tid % TPT;
     const uint64_t c = Tu[i < n ? i : 0];
     int pos = 0;
-    for (int u = part; u < n; u += TPT) pos += (Tu[u] < c) ? 1 : 0;
+    if (i < n)  // (whole warps beyond the thresholds skip the loop)
+      for (int u = part; u < n; u += TPT) pos += (Tu[u] < c) ? 1 : 0;
 #pragma unroll
     for (int x = 1; x < TPT; x <<= 1) pos += __shfl_xor_sync(0xffffffffu, pos, x);
     if (i < n && part == 0) {
