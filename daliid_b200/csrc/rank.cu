@@ -471,7 +471,7 @@ rank_count_v2_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
 constexpr int kV3Chunk = 64;
 constexpr int kV3MaxChunks = 1;  // threshold chunks per query the split launch takes before v2's byte counters
 #ifndef DALI_V3_DEPTH
-#define DALI_V3_DEPTH 2  // row vectors in flight per thread: ring slots of two float4
+#define DALI_V3_DEPTH 1  // ring slots (two float4 per thread each): 1 measured best (0.0641 / 0.0655 / 0.0696 ms for 1 / 2 / 3)
 #endif
 #ifndef DALI_V3_MINB
 #define DALI_V3_MINB 8  // resident 256-thread CTAs per SM the tight variant is compiled for (32 registers)
