@@ -473,6 +473,9 @@ constexpr int kV3MaxChunks = 1;  // threshold chunks per query the split launch 
 #ifndef DALI_V3_DEPTH
 #define DALI_V3_DEPTH 1  // ring slots (two float4 per thread each): 1 measured best (0.0641 / 0.0655 / 0.0696 ms for 1 / 2 / 3)
 #endif
+#ifndef DALI_V3B_LOG2NB
+#define DALI_V3B_LOG2NB 12  // table bins of the many-threshold (CAP = 256) variant
+#endif
 #ifndef DALI_V3_MINB
 #define DALI_V3_MINB 8  // resident 256-thread CTAs per SM the tight variant is compiled for (32 registers)
 #endif
@@ -577,7 +580,7 @@ rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
   constexpr int DEPTH = DALI_V3_DEPTH;
   __shared__ float4 ring[DEPTH][2][THREADS];
   constexpr int kPartPlanes = PL + 3;
-  __shared__ uint32_t part[2 * kPartPlanes * 32];  // [threshold word][plane][partial sum]
+  __shared__ uint32_t part[BYTES ? 1 : 2 * kPartPlanes * 32];  // [threshold word][plane][partial sum]
 
   const int64_t q = blockIdx.x;
   const int chunk = FUSED ? 0 : blockIdx.y;  // FUSED: one CTA per query, the whole row, all thresholds
@@ -1213,10 +1216,10 @@ static int launch_v3b(dali_ctx *ctx, dim3 grid, const dali_rank_plan *plan, cons
                       int64_t g0, int64_t Gs, const uint32_t *keys, int32_t *counts, int nsplit, FusedOut fo) {
   const size_t smem = static_cast<size_t>((std::min(plan->max_nv, 254) + 4) >> 2) * 256 * sizeof(uint32_t);
   // static (38 KB) + dynamic shared memory exceed 48 KB even for few buckets: always opt in, for the most
-  if (int rc = ensure_dyn_smem(ctx, reinterpret_cast<const void *>(&rank_count_v3_kernel<12, 256, 7, FUSED, false, 256>),
+  if (int rc = ensure_dyn_smem(ctx, reinterpret_cast<const void *>(&rank_count_v3_kernel<DALI_V3B_LOG2NB, 256, 7, FUSED, false, 256>),
                                size_t(64) * 256 * sizeof(uint32_t)))
     return rc;
-  rank_count_v3_kernel<12, 256, 7, FUSED, false, 256><<<grid, 256, smem, ctx->stream>>>(
+  rank_count_v3_kernel<DALI_V3B_LOG2NB, 256, 7, FUSED, false, 256><<<grid, 256, smem, ctx->stream>>>(
       dist, ld, g0, Gs, plan->d_off, plan->d_nv, plan->d_gid, keys, counts, nsplit, fo);
   return DALI_OK;
 }
