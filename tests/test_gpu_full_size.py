@@ -304,3 +304,31 @@ def test_c4_three_model_ensemble_full_size(market):
     a = metrics.evaluate_rank_detailed(mean, qp, gp, qc, gc)
     b = metrics.evaluate_rank_detailed(ref, qp, gp, qc, gc)
     assert np.array_equal(a[0], b[0]) and a[1] == b[1] and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+
+
+def test_jpm_feature_size_full_size():
+    """The largest feature size of the reference (SURVEY: the JPM heads concatenate to D = 3840) at
+    the Market matrix size, default precision -- above D = 2048 the contraction runs its
+    corrections-first schedule.  Same checks as the D = 2048 test: a row subset against the reference's
+    CPU fp32 expression (1e-5, planted exact and near duplicates included), CMC / mAP / first rank of
+    the subset bit-exact against the compiled oracle on the same matrix, the FP32 pipe within 0.01 pp."""
+    from daliid_b200 import metrics, synth
+    qf, gf, qp, gp, qc, gc = synth.make_config("market_resnet50", device="cuda", D=3840)
+    gf = gf.clone()
+    gf[:64] = qf[:64]
+    gf[64:128] = qf[64:128] + 0.01 * torch.randn(64, qf.shape[1], device="cuda")
+    sel = torch.cat([torch.arange(0, 128, device="cuda"), torch.arange(128, qf.shape[0], 29, device="cuda")])[:230]
+    seln = sel.cpu().numpy()
+    ref = do.cosine_distmat(qf[sel].cpu(), gf.cpu()).numpy()
+    cmc, mAP, d, det = metrics.evaluate_features(qf, gf, qp, gp, qc, gc, return_distmat=True, return_details=True)
+    sub = d[sel].cpu().numpy()
+    err = np.abs(sub.astype(np.float64) - ref) / np.maximum(1.0, np.abs(ref))
+    assert err.max() <= 1e-5, err.max()
+    dup = np.abs(sub[np.arange(128), np.arange(128)].astype(np.float64) - ref[np.arange(128), np.arange(128)])
+    assert dup.max() <= 1e-5, dup.max()
+    e = c_oracle.evaluate_rank_c(sub, qp[seln], gp, qc[seln], gc, return_details=True)
+    s_cmc, s_map, s_ap, s_first, _ = metrics.evaluate_rank_detailed(d[sel].contiguous(), qp[seln], gp, qc[seln], gc)
+    assert np.array_equal(s_cmc, e[0]) and s_map == e[1] and np.array_equal(s_first, e[3])
+    assert np.array_equal(det["first_rank"][seln], e[3])
+    x_cmc, x_map = metrics.evaluate_features(qf, gf, qp, gp, qc, gc, precision="fp32")
+    assert abs(x_map - mAP) * 100 <= 0.01 and np.abs(x_cmc - cmc).max() <= 0.001
