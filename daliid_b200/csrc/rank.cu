@@ -562,17 +562,17 @@ rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
   constexpr int NB = 1 << LOG2NB;  // bins 0 .. NB; thresholds fall into 2 .. NB-2
   constexpr int NE = NB + 8;       // table entries (a multiple of 8)
   constexpr int kJunkCap = 64;
-  constexpr int kV3Chunk = CAP;  // (shadows the namespace constant: this CTA's capacity)
+  constexpr int kCap = CAP;  // thresholds this CTA takes
   constexpr bool BYTES = CAP > 64;
   static_assert(THREADS >= CAP && THREADS % (CAP < THREADS ? CAP : THREADS) == 0, "one thread per threshold at least");
-  __shared__ uint64_t Tu[kV3Chunk + kJunkCap];  // unsorted thresholds, then the junk composites
-  __shared__ uint64_t T[kV3Chunk + 1];          // sorted, T[n] = sentinel above every composite
-  __shared__ float Tf[kV3Chunk + 1];            // sorted thresholds as distances, Tf[n] = +inf
-  __shared__ uint32_t Tg[kV3Chunk + 1];         // their gallery ids
-  __shared__ uint32_t hist[kV3Chunk + 1];
-  __shared__ uint16_t orig[kV3Chunk];
-  __shared__ uint16_t tb[kV3Chunk + 2];
-  __shared__ double s_term[FUSED ? kV3Chunk : 1];
+  __shared__ uint64_t Tu[kCap + kJunkCap];  // unsorted thresholds, then the junk composites
+  __shared__ uint64_t T[kCap + 1];          // sorted, T[n] = sentinel above every composite
+  __shared__ float Tf[kCap + 1];            // sorted thresholds as distances, Tf[n] = +inf
+  __shared__ uint32_t Tg[kCap + 1];         // their gallery ids
+  __shared__ uint32_t hist[kCap + 1];
+  __shared__ uint16_t orig[kCap];
+  __shared__ uint16_t tb[kCap + 2];
+  __shared__ double s_term[FUSED ? kCap : 1];
   __shared__ __align__(16) uint16_t lut[NE];
   __shared__ uint32_t bh2[BYTES ? CAP + 4 : 1];  // byte-counter variant: elements per bucket
   // the row is streamed through a per-thread ring in shared memory with cp.async: the loads of the
@@ -638,9 +638,9 @@ rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
     }
     return;
   }
-  if (chunk * kV3Chunk >= nv) return;  // uniform exit
-  const int n = min(kV3Chunk, nv - chunk * kV3Chunk);
-  const int64_t o = off_q + static_cast<int64_t>(chunk) * kV3Chunk;
+  if (chunk * kCap >= nv) return;  // uniform exit
+  const int n = min(kCap, nv - chunk * kCap);
+  const int64_t o = off_q + static_cast<int64_t>(chunk) * kCap;
   // FUSED: the junk matches (same identity, same camera) follow the valid ones in the match list
   const int m = FUSED ? static_cast<int>(off_q1 - off_q) : n;
   const int nj = min(m - n, kJunkCap);  // staged; more than that are read from global memory later
@@ -651,10 +651,10 @@ rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
     const uint32_t k = FUSED ? dist_key(__ldg(row + g)) : __ldg(keys + o + t);
     Tu[t] = composite(k, g);
   }
-  for (int t = tid; t <= kV3Chunk; t += THREADS) hist[t] = 0u;
+  for (int t = tid; t <= kCap; t += THREADS) hist[t] = 0u;
   __syncthreads();
   {
-    constexpr int TPT = THREADS / kV3Chunk;  // threads per threshold (4 or 2), adjacent lanes
+    constexpr int TPT = THREADS / kCap;  // threads per threshold (4 or 2), adjacent lanes
     const int i = tid / TPT, part = tid % TPT;
     const uint64_t c = Tu[i < n ? i : 0];
     int pos = 0;
@@ -910,9 +910,9 @@ rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
         if (lane == 0) {
           const int b = 4 * g4;
           bh2[b] = s02 & 0xFFFFu;
-          if (b + 1 <= kV3Chunk) bh2[b + 1] = s13 & 0xFFFFu;
-          if (b + 2 <= kV3Chunk) bh2[b + 2] = s02 >> 16;
-          if (b + 3 <= kV3Chunk) bh2[b + 3] = s13 >> 16;
+          if (b + 1 <= kCap) bh2[b + 1] = s13 & 0xFFFFu;
+          if (b + 2 <= kCap) bh2[b + 2] = s02 >> 16;
+          if (b + 3 <= kCap) bh2[b + 3] = s13 >> 16;
         }
       }
       __syncthreads();
@@ -929,8 +929,8 @@ rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
     }
   } else {
     // generic: bucket histogram with exact compares, then a prefix sum
-    __shared__ uint32_t bh[kV3Chunk + 1];
-    for (int t = tid; t <= kV3Chunk; t += THREADS) bh[t] = 0u;
+    __shared__ uint32_t bh[kCap + 1];
+    for (int t = tid; t <= kCap; t += THREADS) bh[t] = 0u;
     __syncthreads();
     for (int64_t c = c0 + tid; c < c1; c += THREADS) {
       const uint64_t cc = composite(dist_key(__ldg(row + c)), gbase + static_cast<uint32_t>(c));
