@@ -7,7 +7,8 @@ from daliid_b200 import _lib, metrics, synth
 ctx = _lib.get_ctx(0)
 tag = os.environ.get("TAG", os.path.basename(os.environ.get("DALIID_B200_LIB", "default")))
 for name in (sys.argv[1:] or ["market_resnet50", "market_vit"]):
-    qf, gf, qp, gp, qc, gc = synth.make_config(name, device="cuda")
+    over = {"n_ids": int(os.environ["PROBE_NIDS"])} if os.environ.get("PROBE_NIDS") else {}
+    qf, gf, qp, gp, qc, gc = synth.make_config(name, device="cuda", **over)
     d = metrics.compute_distance_matrix(qf, gf, metric="cosine")
     for _ in range(3):
         cmc, mAP = metrics.evaluate_rank(d, qp, gp, qc, gc, max_rank=50)[:2]
