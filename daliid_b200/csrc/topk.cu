@@ -621,6 +621,166 @@ topk_select_kernel(const float *__restrict__ dist, int64_t G, int64_t ld, int k,
   }
 }
 
+// ---- rows of up to 16384 columns, second form: the row stays in registers ------------------------
+// 512 threads, thread t holds the 16-byte pieces t, t + 512, ... (eight at most: 32 order keys in
+// registers, all eight loads in flight at once, no staging in shared memory, two CTAs per SM).
+//   1. every group of `gs` adjacent threads takes the minimum of its keys: M = 512 / gs >= 2 k group
+//      minima.  The k smallest of them are k different elements of the row, so the k-th smallest
+//      minimum T bounds the row's k-th smallest key from above -- and closely: about k (1 + k / M)
+//      keys lie at or below it (Market row, k = 20: ~25 candidates, against ~130 from the sample
+//      histogram of topk_select_kernel);
+//   2. T = the minimum whose (stable) rank among the M minima is k - 1, found by counting;
+//   3. every thread offers its keys at or below T to the candidate list; the list is ranked by
+//      counting and its k best leave.
+// Exact for the same reason as above (every key <= T is a candidate, the composite order decides);
+// a row with more candidates than the list holds (massive ties) is flagged for topk_kernel.
+constexpr int kMinThreads = 512;
+constexpr int kMinPieces = 8;     // 16-byte pieces per thread
+constexpr int kMinCap = 512;      // candidate list
+constexpr int kMinMaxGroups = 256;
+
+// 16 bytes at p + OFF (a compile-time byte offset: one address register for all of a thread's pieces)
+// if `on`, `fill` otherwise; a predicated-off load touches nothing
+template <int OFF>
+__device__ __forceinline__ float4 ld_piece_if(const float4 *p, bool on, float fill) {
+  float4 x;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t"
+      "mov.f32 %0, %7;\n\tmov.f32 %1, %7;\n\tmov.f32 %2, %7;\n\tmov.f32 %3, %7;\n\t"
+      "@p ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4 + %6];\n\t}"
+      : "=&f"(x.x), "=&f"(x.y), "=&f"(x.z), "=&f"(x.w)
+      : "l"(p), "r"(on ? 1 : 0), "n"(OFF), "f"(fill));
+  return x;
+}
+
+__global__ void __launch_bounds__(kMinThreads, 2)
+topk_minima_kernel(const float *__restrict__ dist, int64_t G, int64_t ld, int k, int log2gs, int largest,
+                   int32_t id_base, float *__restrict__ d_out, int32_t *__restrict__ i_out,
+                   int32_t *__restrict__ row_flags) {
+  __shared__ float gm[kMinMaxGroups];
+  __shared__ uint64_t cand[kMinCap];
+  __shared__ float s_thr;
+  __shared__ int s_cnt, s_nan;
+  const int64_t q = blockIdx.x;
+  const float *row = dist + q * ld;
+  const int tid = threadIdx.x;
+  const int Gi = static_cast<int>(G);
+  const uint32_t flip = largest ? 0xFFFFFFFFu : 0u;
+  // 0. the row: [a0, a0 + 4 nv) is its 16-byte aligned part, thread t holds the pieces t, t + 512, ...
+  // (all loads unconditional or predicated -- no branch between them, so the eight are in flight
+  // together); the <= 3 columns before and after it go to the threads 0 .. 2 and 32 .. 34 as one
+  // extra key each.  Slots without a column get the largest key and are never offered.
+  const int mis = static_cast<int>((reinterpret_cast<uintptr_t>(row) >> 2) & 3);
+  const int a0 = min((4 - mis) & 3, Gi);
+  const int nv = (Gi - a0) >> 2;
+  const int ct0 = a0 + 4 * nv;
+  if (tid == 0) {
+    s_cnt = 0;
+    s_nan = 0;
+    s_thr = INFINITY;
+  }
+  const float4 *vrow = reinterpret_cast<const float4 *>(row + a0);
+  float4 x[kMinPieces];
+  {
+    const float4 *p0 = vrow + tid;
+    const float fill = largest ? -INFINITY : INFINITY;  // times sgn below: +inf, never under a threshold
+    x[0] = ld_piece_if<0 * kMinThreads * 16>(p0, tid + 0 * kMinThreads < nv, fill);
+    x[1] = ld_piece_if<1 * kMinThreads * 16>(p0, tid + 1 * kMinThreads < nv, fill);
+    x[2] = ld_piece_if<2 * kMinThreads * 16>(p0, tid + 2 * kMinThreads < nv, fill);
+    x[3] = ld_piece_if<3 * kMinThreads * 16>(p0, tid + 3 * kMinThreads < nv, fill);
+    x[4] = ld_piece_if<4 * kMinThreads * 16>(p0, tid + 4 * kMinThreads < nv, fill);
+    x[5] = ld_piece_if<5 * kMinThreads * 16>(p0, tid + 5 * kMinThreads < nv, fill);
+    x[6] = ld_piece_if<6 * kMinThreads * 16>(p0, tid + 6 * kMinThreads < nv, fill);
+    x[7] = ld_piece_if<7 * kMinThreads * 16>(p0, tid + 7 * kMinThreads < nv, fill);
+    static_assert(kMinPieces == 8, "eight pieces per thread");
+  }
+  // (the values are not touched before all eight requests have been issued)
+#pragma unroll
+  for (int j = 0; j < kMinPieces; ++j)
+    asm volatile("" : "+f"(x[j].x), "+f"(x[j].y), "+f"(x[j].z), "+f"(x[j].w));
+  // everything up to the candidate list works on the distances themselves (times -1 for `largest`):
+  // for numbers the float order is the key order (-0 == +0 in both); NaN compares false everywhere,
+  // so a NaN is never a candidate -- right for the smallest k unless fewer than k numbers exist (the
+  // row is then flagged below), wrong for the largest k, where NaN ranks first: such rows are flagged
+  const float sgn = largest ? -1.f : 1.f;
+  int ec = -1;  // column of the extra element
+  if (tid < a0) ec = tid;
+  if (tid >= 32 && tid - 32 < Gi - ct0) ec = ct0 + tid - 32;
+  const float ex = ec >= 0 ? __ldg(row + ec) * sgn : INFINITY;
+  float y[kMinPieces][4];
+#pragma unroll
+  for (int j = 0; j < kMinPieces; ++j) {
+    y[j][0] = x[j].x * sgn; y[j][1] = x[j].y * sgn; y[j][2] = x[j].z * sgn; y[j][3] = x[j].w * sgn;
+  }
+  if (largest) {  // uniform
+    bool nan = ex != ex;
+#pragma unroll
+    for (int j = 0; j < kMinPieces; ++j)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) nan |= y[j][u] != y[j][u];
+    if (nan) s_nan = 1;
+  }
+  // 1. group minima (fminf skips NaN; slots without a column hold +inf)
+  float mn = ex;
+#pragma unroll
+  for (int j = 0; j < kMinPieces; ++j)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) mn = fminf(mn, y[j][u]);
+  for (int o = 1; o < (1 << log2gs); o <<= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  const int M = kMinThreads >> log2gs;
+  if ((tid & ((1 << log2gs) - 1)) == 0) gm[tid >> log2gs] = mn;
+  __syncthreads();
+  // 2. the minimum of rank want - 1 (ties by group index).  Whatever value comes out, the result is
+  // exact as long as at least `want` elements lie at or below it.
+  const int want = k < Gi ? k : Gi;
+  if (tid < M) {
+    const float mine = gm[tid];
+    int rank = 0;
+    for (int j = 0; j < M; ++j) {
+      const float o = gm[j];
+      rank += (o < mine || (o == mine && j < tid)) ? 1 : 0;
+    }
+    if (rank == want - 1) s_thr = mine;
+  }
+  __syncthreads();
+  const float thr = s_thr;
+  // 3. candidates: every element of the row at or below the threshold
+  auto offer = [&](float v, int c) {
+    const int pos = atomicAdd(&s_cnt, 1);
+    if (pos < kMinCap) cand[pos] = composite(dist_key(v * sgn) ^ flip, static_cast<uint32_t>(id_base + c));
+  };
+#pragma unroll
+  for (int j = 0; j < kMinPieces; ++j) {
+    const int v = tid + j * kMinThreads;
+    // (one test per piece first: a piece with a candidate is rare)
+    if (v < nv && fminf(fminf(y[j][0], y[j][1]), fminf(y[j][2], y[j][3])) <= thr) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (y[j][u] <= thr) offer(y[j][u], a0 + 4 * v + u);
+    }
+  }
+  if (ec >= 0 && ex <= thr) offer(ex, ec);
+  __syncthreads();
+  const int cnt = s_cnt;
+  if (cnt < want || cnt > kMinCap || s_nan) {  // block-uniform: the one-CTA-per-row kernel redoes this row
+    if (tid == 0) row_flags[q] = 1;
+    return;
+  }
+  for (int i = tid; i < cnt; i += kMinThreads) {
+    const uint64_t c = cand[i];
+    int rank = 0;
+    for (int j = 0; j < cnt; ++j) rank += cand[j] < c ? 1 : 0;
+    if (rank < k) {
+      d_out[q * k + rank] = key_to_dist(static_cast<uint32_t>(c >> 32) ^ flip);
+      i_out[q * k + rank] = static_cast<int32_t>(static_cast<uint32_t>(c));
+    }
+  }
+  for (int i = cnt + tid; i < k; i += kMinThreads) {  // rows shorter than k
+    d_out[q * k + i] = largest ? -INFINITY : INFINITY;
+    i_out[q * k + i] = -1;
+  }
+}
+
 }  // namespace
 
 static int launch_topk_classic(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t ld, int k,
@@ -646,6 +806,18 @@ int launch_topk(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t 
     if (rc) return rc;
     int32_t *row_flags = static_cast<int32_t *>(flags_v) + Q;
     DALI_CUDA_OK(ctx, cudaMemsetAsync(row_flags, 0, sizeof(int32_t) * Q, ctx->stream));
+    static const char *env_min = getenv("DALI_TOPK_MINIMA");
+    if (!(env_min && atoi(env_min) == 0) && (G + 6) / 4 <= int64_t(kMinThreads) * kMinPieces) {
+      // the row in registers, threshold from group minima: 512 / gs >= 2 k groups
+      const int log2gs = k <= 32 ? 3 : k <= 64 ? 2 : 1;
+      {
+        KTimer t(ctx, DALI_K_TOPK);
+        topk_minima_kernel<<<static_cast<unsigned>(Q), kMinThreads, 0, ctx->stream>>>(
+            dist, G, ld, k, log2gs, largest, id_base, d_out, i_out, row_flags);
+        DALI_CUDA_OK(ctx, cudaGetLastError());
+      }
+      return launch_topk_classic(ctx, dist, Q, G, ld, k, largest, nullptr, id_base, d_out, i_out, row_flags);
+    }
     const int cap = k <= 64 ? kSelCap / 2 : kSelCap;
     const size_t smem = sizeof(float) * ((G + 6) & ~int64_t(3)) + sizeof(uint64_t) * cap + sizeof(uint32_t) * kSelBins;
     if ((rc = ensure_dyn_smem(ctx, reinterpret_cast<const void *>(&topk_select_kernel), smem))) return rc;

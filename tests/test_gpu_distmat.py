@@ -309,6 +309,44 @@ def test_topk_matches_stable_argsort(k):
 
 
 @pytest.mark.parametrize("largest", [False, True])
+@pytest.mark.parametrize("G", [256, 257, 1003, 4099, 15913, 16378])
+def test_topk_rows_in_registers(G, largest):
+    """``topk_minima_kernel`` (rows of 256 .. 16378 columns held in registers, threshold from group
+    minima): every alignment of the row start (odd leading dimension), rows with NaN / +-inf / -0,
+    quantised values with many ties at the threshold, constant rows (more candidates than the list
+    holds: the repair kernel), rows with fewer than k numbers -- against the stable argsort order
+    (smallest) and torch.topk's order (largest: NaN first, ties by ascending index)."""
+    from daliid_b200 import metrics
+    rng = np.random.default_rng(G + int(largest))
+    Q = 11
+    d = rng.standard_normal((Q, G)).astype(np.float32)
+    d[1] = np.round(d[1] * 8) / 8                      # heavy ties
+    d[2] = 0.25                                        # constant row
+    d[3, ::3] = np.nan
+    d[4] = np.nan
+    d[4, 5:9] = [3.0, -0.0, 0.0, -np.inf]              # fewer numbers than k
+    d[5, :7] = [np.inf, -np.inf, -0.0, 0.0, np.nan, 1e-38, -1e-38]
+    d[6] = np.sort(d[6])                               # best first
+    d[7] = np.sort(d[7])[::-1]                         # best last
+    d[8, G // 2:] = d[8, : G - G // 2]                 # duplicated halves
+    ld = G + 3
+    buf = torch.full((Q * ld + 4,), 7.0, dtype=torch.float32, device="cuda")
+    for shift in range(4):                             # rows start at every 4-byte phase of 16 bytes
+        view = buf[shift: shift + Q * ld].view(Q, ld)[:, :G]
+        view.copy_(torch.from_numpy(d))
+        for k in (1, 20, 64, 128):
+            v, i = metrics.topk_identify(view, k=k, largest=largest)
+            if largest:  # torch.topk: NaN above +inf, then descending, ties by ascending index
+                nan = np.isnan(d)
+                val = np.where(nan, 0.0, d) + 0.0
+                order = np.stack([np.lexsort((np.arange(G), -val[r], ~nan[r])) for r in range(Q)])[:, :k]
+            else:
+                order = ro.stable_argsort(d)[:, :k]
+            assert np.array_equal(i.cpu().numpy(), order.astype(np.int32)), (G, largest, shift, k)
+            assert np.array_equal(v.cpu().numpy(), np.take_along_axis(d, order, 1), equal_nan=True)
+
+
+@pytest.mark.parametrize("largest", [False, True])
 def test_topk_streaming_long_rows(largest):
     """Rows of >= 4096 columns take the streaming filter + compaction path; rows whose candidate
     list overflows (here: values quantised to 9 levels, one row sorted so that every later column
