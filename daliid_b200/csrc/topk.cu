@@ -634,7 +634,6 @@ topk_select_kernel(const float *__restrict__ dist, int64_t G, int64_t ld, int k,
 //      counting and its k best leave.
 // Exact for the same reason as above (every key <= T is a candidate, the composite order decides);
 // a row with more candidates than the list holds (massive ties) is flagged for topk_kernel.
-constexpr int kMinThreads = 512;
 constexpr int kMinPieces = 8;     // 16-byte pieces per thread
 constexpr int kMinCap = 512;      // candidate list
 constexpr int kMinMaxGroups = 256;
@@ -653,7 +652,9 @@ __device__ __forceinline__ float4 ld_piece_if(const float4 *p, bool on, float fi
   return x;
 }
 
-__global__ void __launch_bounds__(kMinThreads, 2)
+// THREADS = 512 (two CTAs per SM, rows of up to 16378 columns) or 1024 (one CTA per SM, up to 32762)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 topk_minima_kernel(const float *__restrict__ dist, int64_t G, int64_t ld, int k, int log2gs, int largest,
                    int32_t id_base, float *__restrict__ d_out, int32_t *__restrict__ i_out,
                    int32_t *__restrict__ row_flags) {
@@ -684,14 +685,14 @@ topk_minima_kernel(const float *__restrict__ dist, int64_t G, int64_t ld, int k,
   {
     const float4 *p0 = vrow + tid;
     const float fill = largest ? -INFINITY : INFINITY;  // times sgn below: +inf, never under a threshold
-    x[0] = ld_piece_if<0 * kMinThreads * 16>(p0, tid + 0 * kMinThreads < nv, fill);
-    x[1] = ld_piece_if<1 * kMinThreads * 16>(p0, tid + 1 * kMinThreads < nv, fill);
-    x[2] = ld_piece_if<2 * kMinThreads * 16>(p0, tid + 2 * kMinThreads < nv, fill);
-    x[3] = ld_piece_if<3 * kMinThreads * 16>(p0, tid + 3 * kMinThreads < nv, fill);
-    x[4] = ld_piece_if<4 * kMinThreads * 16>(p0, tid + 4 * kMinThreads < nv, fill);
-    x[5] = ld_piece_if<5 * kMinThreads * 16>(p0, tid + 5 * kMinThreads < nv, fill);
-    x[6] = ld_piece_if<6 * kMinThreads * 16>(p0, tid + 6 * kMinThreads < nv, fill);
-    x[7] = ld_piece_if<7 * kMinThreads * 16>(p0, tid + 7 * kMinThreads < nv, fill);
+    x[0] = ld_piece_if<0 * THREADS * 16>(p0, tid + 0 * THREADS < nv, fill);
+    x[1] = ld_piece_if<1 * THREADS * 16>(p0, tid + 1 * THREADS < nv, fill);
+    x[2] = ld_piece_if<2 * THREADS * 16>(p0, tid + 2 * THREADS < nv, fill);
+    x[3] = ld_piece_if<3 * THREADS * 16>(p0, tid + 3 * THREADS < nv, fill);
+    x[4] = ld_piece_if<4 * THREADS * 16>(p0, tid + 4 * THREADS < nv, fill);
+    x[5] = ld_piece_if<5 * THREADS * 16>(p0, tid + 5 * THREADS < nv, fill);
+    x[6] = ld_piece_if<6 * THREADS * 16>(p0, tid + 6 * THREADS < nv, fill);
+    x[7] = ld_piece_if<7 * THREADS * 16>(p0, tid + 7 * THREADS < nv, fill);
     static_assert(kMinPieces == 8, "eight pieces per thread");
   }
   // (the values are not touched before all eight requests have been issued)
@@ -727,7 +728,7 @@ topk_minima_kernel(const float *__restrict__ dist, int64_t G, int64_t ld, int k,
 #pragma unroll
     for (int u = 0; u < 4; ++u) mn = fminf(mn, y[j][u]);
   for (int o = 1; o < (1 << log2gs); o <<= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-  const int M = kMinThreads >> log2gs;
+  const int M = THREADS >> log2gs;
   if ((tid & ((1 << log2gs) - 1)) == 0) gm[tid >> log2gs] = mn;
   __syncthreads();
   // 2. the minimum of rank want - 1 (ties by group index).  Whatever value comes out, the result is
@@ -751,7 +752,7 @@ topk_minima_kernel(const float *__restrict__ dist, int64_t G, int64_t ld, int k,
   };
 #pragma unroll
   for (int j = 0; j < kMinPieces; ++j) {
-    const int v = tid + j * kMinThreads;
+    const int v = tid + j * THREADS;
     // (one test per piece first: a piece with a candidate is rare)
     if (v < nv && fminf(fminf(y[j][0], y[j][1]), fminf(y[j][2], y[j][3])) <= thr) {
 #pragma unroll
@@ -766,7 +767,7 @@ topk_minima_kernel(const float *__restrict__ dist, int64_t G, int64_t ld, int k,
     if (tid == 0) row_flags[q] = 1;
     return;
   }
-  for (int i = tid; i < cnt; i += kMinThreads) {
+  for (int i = tid; i < cnt; i += THREADS) {
     const uint64_t c = cand[i];
     int rank = 0;
     for (int j = 0; j < cnt; ++j) rank += cand[j] < c ? 1 : 0;
@@ -775,7 +776,7 @@ topk_minima_kernel(const float *__restrict__ dist, int64_t G, int64_t ld, int k,
       i_out[q * k + rank] = static_cast<int32_t>(static_cast<uint32_t>(c));
     }
   }
-  for (int i = cnt + tid; i < k; i += kMinThreads) {  // rows shorter than k
+  for (int i = cnt + tid; i < k; i += THREADS) {  // rows shorter than k
     d_out[q * k + i] = largest ? -INFINITY : INFINITY;
     i_out[q * k + i] = -1;
   }
@@ -798,6 +799,28 @@ int launch_topk(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t 
                 int32_t *i_out) {
   if (Q == 0) return DALI_OK;
   if (k < 1 || k > 128) return set_err(ctx, DALI_ERR_INVALID, "top-k needs 1 <= k <= 128");
+  // rows that fit the registers of one CTA: one pass, one launch (+ the repair launch for flagged rows);
+  // threshold from group minima: THREADS / gs >= 2 k groups
+  static const char *env_min = getenv("DALI_TOPK_MINIMA");
+  if (!col_ids && G >= 256 && (G + 6) / 4 <= 1024ll * kMinPieces && !(env_min && atoi(env_min) == 0)) {
+    void *flags_v;
+    int rc = ws_ensure(ctx, WS_CAND_CNT, sizeof(int32_t) * 2 * Q, &flags_v);
+    if (rc) return rc;
+    int32_t *row_flags = static_cast<int32_t *>(flags_v) + Q;
+    DALI_CUDA_OK(ctx, cudaMemsetAsync(row_flags, 0, sizeof(int32_t) * Q, ctx->stream));
+    const int log2gs = k <= 32 ? 3 : k <= 64 ? 2 : 1;
+    {
+      KTimer t(ctx, DALI_K_TOPK);
+      if ((G + 6) / 4 <= 512ll * kMinPieces)
+        topk_minima_kernel<512><<<static_cast<unsigned>(Q), 512, 0, ctx->stream>>>(
+            dist, G, ld, k, log2gs, largest, id_base, d_out, i_out, row_flags);
+      else
+        topk_minima_kernel<1024><<<static_cast<unsigned>(Q), 1024, 0, ctx->stream>>>(
+            dist, G, ld, k, log2gs + 1, largest, id_base, d_out, i_out, row_flags);
+      DALI_CUDA_OK(ctx, cudaGetLastError());
+    }
+    return launch_topk_classic(ctx, dist, Q, G, ld, k, largest, nullptr, id_base, d_out, i_out, row_flags);
+  }
   // rows that fit shared memory: one pass, one launch (+ the repair launch for flagged rows)
   static const char *env_sel = getenv("DALI_TOPK_SELECT");
   if (!col_ids && G >= 256 && G <= kSelMaxG && !(env_sel && atoi(env_sel) == 0)) {
@@ -806,18 +829,6 @@ int launch_topk(dali_ctx *ctx, const float *dist, int64_t Q, int64_t G, int64_t 
     if (rc) return rc;
     int32_t *row_flags = static_cast<int32_t *>(flags_v) + Q;
     DALI_CUDA_OK(ctx, cudaMemsetAsync(row_flags, 0, sizeof(int32_t) * Q, ctx->stream));
-    static const char *env_min = getenv("DALI_TOPK_MINIMA");
-    if (!(env_min && atoi(env_min) == 0) && (G + 6) / 4 <= int64_t(kMinThreads) * kMinPieces) {
-      // the row in registers, threshold from group minima: 512 / gs >= 2 k groups
-      const int log2gs = k <= 32 ? 3 : k <= 64 ? 2 : 1;
-      {
-        KTimer t(ctx, DALI_K_TOPK);
-        topk_minima_kernel<<<static_cast<unsigned>(Q), kMinThreads, 0, ctx->stream>>>(
-            dist, G, ld, k, log2gs, largest, id_base, d_out, i_out, row_flags);
-        DALI_CUDA_OK(ctx, cudaGetLastError());
-      }
-      return launch_topk_classic(ctx, dist, Q, G, ld, k, largest, nullptr, id_base, d_out, i_out, row_flags);
-    }
     const int cap = k <= 64 ? kSelCap / 2 : kSelCap;
     const size_t smem = sizeof(float) * ((G + 6) & ~int64_t(3)) + sizeof(uint64_t) * cap + sizeof(uint32_t) * kSelBins;
     if ((rc = ensure_dyn_smem(ctx, reinterpret_cast<const void *>(&topk_select_kernel), smem))) return rc;

@@ -347,14 +347,15 @@ def test_topk_rows_in_registers(G, largest):
 
 
 @pytest.mark.parametrize("largest", [False, True])
-def test_topk_streaming_long_rows(largest):
+@pytest.mark.parametrize("G", [30011, 40013])
+def test_topk_streaming_long_rows(largest, G):
     """Rows of >= 4096 columns take the streaming filter + compaction path; rows whose candidate
     list overflows (here: values quantised to 9 levels, one row sorted so that every later column
     is better, a row of NaN / inf) are redone on the device by the one-CTA-per-row kernel.  Equal
     to the stable argsort prefix in all cases, odd leading dimension included."""
     from daliid_b200 import metrics
     rng = np.random.default_rng(21)
-    Q, G = 41, 30011
+    Q = 41  # (30011 columns: the row-in-registers kernel with 1024 threads; 40013: the streaming path)
     d = rng.random((Q, G)).astype(np.float32)
     d[1] = np.round(d[1] * 8) / 8                       # massive ties
     d[2] = np.sort(d[2])[::-1] if not largest else np.sort(d[2])   # every later column is better
@@ -376,8 +377,8 @@ def test_topk_streaming_long_rows(largest):
         assert np.array_equal(i.cpu().numpy(), order.astype(np.int32)), (largest, k)
         assert np.array_equal(v.cpu().numpy(), np.take_along_axis(d, order, 1), equal_nan=True)
     # host matrix with an odd width (unaligned rows)
-    v, i = metrics.topk_identify(d[:, :30001].copy(), k=20, largest=largest)
-    e, ei = metrics.topk_identify(dt[:, :30001].contiguous(), k=20, largest=largest)
+    v, i = metrics.topk_identify(d[:, :G - 10].copy(), k=20, largest=largest)
+    e, ei = metrics.topk_identify(dt[:, :G - 10].contiguous(), k=20, largest=largest)
     assert np.array_equal(i, ei.cpu().numpy()) and np.array_equal(v, e.cpu().numpy(), equal_nan=True)
 
 
