@@ -358,7 +358,8 @@ __global__ void csc_fill_kernel(int64_t N, const int32_t *__restrict__ v_idx, co
 
 // persistent CTAs, each with a temp[N] accumulator; columns of V[i] are visited in ascending
 // order with a barrier between them, so every temp[r] receives its terms in the reference's order
-__global__ void __launch_bounds__(256)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
 jaccard_kernel(int64_t Q, int64_t G, const float *__restrict__ od, const int32_t *__restrict__ v_idx,
                const float *__restrict__ v_val, const int32_t *__restrict__ v_cnt, int cap,
                const int64_t *__restrict__ col_off, const int32_t *__restrict__ csc_row,
@@ -367,21 +368,21 @@ jaccard_kernel(int64_t Q, int64_t G, const float *__restrict__ od, const int32_t
   const int64_t N = Q + G;
   float *temp = temp_all + static_cast<int64_t>(blockIdx.x) * N;
   for (int64_t i = blockIdx.x; i < Q; i += gridDim.x) {
-    for (int64_t r = threadIdx.x; r < N; r += 256) temp[r] = 0.f;
+    for (int64_t r = threadIdx.x; r < N; r += THREADS) temp[r] = 0.f;
     __syncthreads();
     const int n = v_cnt[i];
     for (int e = 0; e < n; ++e) {
       const int32_t c = v_idx[i * cap + e];
       const float vi = v_val[i * cap + e];
       const int64_t b = col_off[c], en = col_off[c + 1];
-      for (int64_t p = b + threadIdx.x; p < en; p += 256) {
+      for (int64_t p = b + threadIdx.x; p < en; p += THREADS) {
         const int32_t r = csc_row[p];
         temp[r] = __fadd_rn(temp[r], fminf(vi, csc_val[p]));
       }
       __syncthreads();
     }
     const float *odi = od + i * N + Q;
-    for (int64_t j = threadIdx.x; j < G; j += 256) {
+    for (int64_t j = threadIdx.x; j < G; j += THREADS) {
       const float t = temp[Q + j];
       const float jac = __fsub_rn(1.0f, __fdiv_rn(t, __fsub_rn(2.0f, t)));
       out[i * ld_out + j] = __fadd_rn(__fmul_rn(jac, w_jac), __fmul_rn(odi[j], w_od));
@@ -487,11 +488,21 @@ int launch_rerank(dali_ctx *ctx, const float *qg, int64_t ld_qg, const float *qq
     csc_fill_kernel<<<static_cast<unsigned>(N), 128, 0, st>>>(N, v_idx, v_val, cnt_final, cap2, col_off, col_cnt,
                                                               csc_row, csc_val);
     // 6. Jaccard + final
-    const int ctas = static_cast<int>(std::min<int64_t>(Q, 2 * ctx->num_sms));
+    // (every column of a query costs a chain of dependent global loads and a barrier: what hides
+    // them is the number of resident CTAs -- 2 / 4 / 8 CTAs of 256 threads per SM and 16 of 128 measured at the Market shape)
+    static const char *env_j = getenv("DALI_RR_CTAS_PER_SM");
+    static const char *env_jt = getenv("DALI_RR_JACCARD_THREADS");
+    const int jthreads = env_jt && atoi(env_jt) == 128 ? 128 : 256;
+    const int per_sm = env_j ? std::max(1, std::min(2048 / jthreads, atoi(env_j))) : 2048 / jthreads;
+    const int ctas = static_cast<int>(std::min<int64_t>(Q, static_cast<int64_t>(per_sm) * ctx->num_sms));
     if ((rc = ws_ensure(ctx, WS_RR_TEMP, sizeof(float) * N * ctas, &p))) return rc;
     const float w_jac = static_cast<float>(1.0 - lambda), w_od = static_cast<float>(lambda);
-    jaccard_kernel<<<ctas, 256, 0, st>>>(Q, G, od, v_idx, v_val, cnt_final, cap2, col_off, csc_row, csc_val,
-                                         static_cast<float *>(p), w_jac, w_od, out, ld_out);
+    if (jthreads == 256)
+      jaccard_kernel<256><<<ctas, 256, 0, st>>>(Q, G, od, v_idx, v_val, cnt_final, cap2, col_off, csc_row, csc_val,
+                                                static_cast<float *>(p), w_jac, w_od, out, ld_out);
+    else
+      jaccard_kernel<128><<<ctas, 128, 0, st>>>(Q, G, od, v_idx, v_val, cnt_final, cap2, col_off, csc_row, csc_val,
+                                                static_cast<float *>(p), w_jac, w_od, out, ld_out);
     DALI_CUDA_OK(ctx, cudaGetLastError());
   }
   return DALI_OK;
