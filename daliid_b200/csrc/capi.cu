@@ -577,6 +577,24 @@ static int prep_rows(dali_ctx *ctx, const Prepared &o, const float *xd, int64_t 
                      p16 ? p16 + 2 * (o.rows_pad * o.Dp + off) : nullptr, perm);
 }
 
+// Both operands of an evaluation live on the device: their two preparation launches are issued as one
+// (normalize.cu holds the first back until the second arrives; anything else launches at once)
+struct PrepPair {
+  dali_ctx *ctx;
+  bool on;
+  PrepPair(dali_ctx *c, bool enable) : ctx(c), on(enable) {
+    if (on) prep_defer_begin(ctx);
+  }
+  int finish() {
+    if (!on) return DALI_OK;
+    on = false;
+    return prep_defer_end(ctx);
+  }
+  ~PrepPair() {
+    if (on) prep_defer_end(ctx);
+  }
+};
+
 static int prepare_operand(dali_ctx *ctx, int ws_in, int ws_planes, int ws_p16, int ws_sq, const float *x,
                            int64_t n, int64_t D, int metric, int precision, int normalize,
                            Prepared *out, const int32_t *perm = nullptr) {
@@ -1128,6 +1146,7 @@ static int gallery_pipelined(dali_ctx *ctx, const Prepared &a, const float *g_ho
 static int distmat_to(dali_ctx *ctx, const float *q, int64_t Q, const float *g, int64_t G, int64_t D,
                       int metric, int precision, int normalize, float *out_dev, int64_t ld) {
   Prepared a, b;
+  PrepPair pair(ctx, is_device_ptr(q) && is_device_ptr(g));
   int rc = prepare_operand(ctx, WS_QIN, WS_QN, WS_QN16, WS_QNORM, q, Q, D, metric, precision, normalize, &a);
   if (rc) return rc;
   if (!is_device_ptr(g) && static_cast<int64_t>(sizeof(float)) * G * D >= (24ll << 20))
@@ -1136,6 +1155,7 @@ static int distmat_to(dali_ctx *ctx, const float *q, int64_t Q, const float *g, 
   //  three shorter launches of the persistent kernel lose more than the 0.06 ms they hide)
   rc = prepare_operand(ctx, WS_GIN, WS_GN, WS_GN16, WS_GNORM, g, G, D, metric, precision, normalize, &b);
   if (rc) return rc;
+  if ((rc = pair.finish())) return rc;
   return contract(ctx, a, b, Q, 0, G, metric, precision, out_dev, ld);
 }
 
@@ -1205,10 +1225,12 @@ int dali_distmat_fuse_mean_f32(dali_ctx *ctx, const float *q, int64_t Q, const f
                    "distmat_fuse_mean: tensor-core precisions and device matrices with 16-byte aligned rows only");
   if (Q == 0 || G == 0) return DALI_OK;
   Prepared a, b;
+  PrepPair pair(ctx, is_device_ptr(q) && is_device_ptr(g));
   rc = prepare_operand(ctx, WS_QIN, WS_QN, WS_QN16, WS_QNORM, q, Q, D, metric, precision, normalize, &a);
   if (rc) return rc;
   rc = prepare_operand(ctx, WS_GIN, WS_GN, WS_GN16, WS_GNORM, g, G, D, metric, precision, normalize, &b);
   if (rc) return rc;
+  if ((rc = pair.finish())) return rc;
   // 1: acc = d; 2: acc += d; 3: acc = (acc + d) / n.  One model: the mean is the matrix itself, divided by 1.
   const int mode = step == 0 ? 1 : (step == n_models - 1 ? 3 : 2);
   return contract(ctx, a, b, Q, 0, G, metric, precision, out_opt, ld_out, acc, ld_acc, mode,

@@ -168,6 +168,12 @@ struct dali_ctx {
   std::vector<cudaEvent_t> chunk_events;
   size_t next_event = 0;
   int h2d_streams = 1;  // DMA streams one H2D copy is split over (DALI_H2D_STREAMS)
+  // operand preparation: between prep_defer_begin / prep_defer_end the first launch of the default
+  // (fp16 planes) kind is held back and issued together with the second one as ONE launch
+  bool prep_defer = false, prep_pending = false;
+  int prep_kind = 0;
+  unsigned prep_blocks = 0;
+  alignas(8) unsigned char prep_params[192];
   // online choice between one and two DMA streams for pipelined host galleries: the first calls
   // of a context are timed (events around the copy/compute pipeline) with either setting
   int h2d_tune_calls = 0;        // pipelined calls seen so far
@@ -274,6 +280,8 @@ int launch_prep(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx
                 float *plane1, int64_t ldo, int64_t d_pad, int64_t rows_pad, int do_normalize,
                 int round_mode, float *norms, float *sq, void *hi16 = nullptr,
                 void *lo16 = nullptr, const int32_t *perm = nullptr);
+void prep_defer_begin(dali_ctx *ctx);
+int prep_defer_end(dali_ctx *ctx);  // launches a held-back preparation, if any
 float f16x3_hi_grid(int64_t d_pad);
 int launch_selftest_div(dali_ctx *ctx, int n, unsigned long long *bad_dev);  // fuse.cu
 // distmat_simt.cu

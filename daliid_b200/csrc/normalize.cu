@@ -7,6 +7,7 @@
 //   evaluate_ensembled_models.py:278-279,297-298, evaluateCleanATModels.py:106-107,115-119,252-254
 // No eps, as in the reference: a zero row divides 0/0 and becomes NaN.
 #include <cstdlib>
+#include <cstring>
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -213,9 +214,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_rows_vec_kernel(PrepParams 
 // by ONE factor 4096 / ||x|| (the planes are internal: a last-ulp difference to x / ||x|| changes a
 // distance by < 1e-8), conversions are packed, and NVEC is a compile-time constant.
 template <int NVEC>
-__global__ void __launch_bounds__(kPrepThreads) prep_f16_kernel(PrepParams p) {
-  __shared__ float s_red[kPrepThreads / 32];
-  const int64_t r = blockIdx.x;
+__device__ __forceinline__ void prep_f16_body(const PrepParams &p, const int64_t r, float *s_red) {
   uint2 *h16 = reinterpret_cast<uint2 *>(p.hi16 + r * p.ldo);
   uint2 *l16 = reinterpret_cast<uint2 *>(p.lo16 + r * p.ldo);
   const int nv_pad = static_cast<int>(p.d_pad >> 2);
@@ -274,13 +273,27 @@ __global__ void __launch_bounds__(kPrepThreads) prep_f16_kernel(PrepParams p) {
   }
 }
 
+template <int NVEC>
+__global__ void __launch_bounds__(kPrepThreads) prep_f16_kernel(PrepParams p) {
+  __shared__ float s_red[kPrepThreads / 32];
+  prep_f16_body<NVEC>(p, blockIdx.x, s_red);
+}
+// two operands (queries and gallery of one evaluation) in ONE launch: the first `blocks_a` CTAs take
+// `pa`, the others `pb` -- saves a launch gap and the ramp of the short query launch
+template <int NVEC>
+__global__ void __launch_bounds__(kPrepThreads) prep_f16_pair_kernel(PrepParams pa, PrepParams pb, unsigned blocks_a) {
+  __shared__ float s_red[kPrepThreads / 32];
+  if (blockIdx.x < blocks_a) prep_f16_body<NVEC>(pa, blockIdx.x, s_red);
+  else prep_f16_body<NVEC>(pb, blockIdx.x - blocks_a, s_red);
+}
+
 // Rows of at most 1024 elements (D = 512 / 768: most BASELINE shapes): one WARP per row, eight rows
 // per CTA, reductions by shuffle only.  A 256-thread CTA per 3 KB row with two block barriers ran at
 // 1.4 TB/s (0.085 ms for queries + gallery at the Market/ViT shape).
 template <int NV>
-__global__ void __launch_bounds__(kPrepThreads) prep_f16_warp_kernel(PrepParams p) {
+__device__ __forceinline__ void prep_f16_warp_body(const PrepParams &p, const unsigned blk) {
   const int lane = threadIdx.x & 31;
-  const int64_t r = static_cast<int64_t>(blockIdx.x) * (kPrepThreads / 32) + (threadIdx.x >> 5);
+  const int64_t r = static_cast<int64_t>(blk) * (kPrepThreads / 32) + (threadIdx.x >> 5);
   if (r >= p.rows_pad) return;
   uint2 *h16 = reinterpret_cast<uint2 *>(p.hi16 + r * p.ldo);
   uint2 *l16 = reinterpret_cast<uint2 *>(p.lo16 + r * p.ldo);
@@ -343,7 +356,58 @@ __global__ void __launch_bounds__(kPrepThreads) prep_f16_warp_kernel(PrepParams 
   }
 }
 
+template <int NV>
+__global__ void __launch_bounds__(kPrepThreads) prep_f16_warp_kernel(PrepParams p) {
+  prep_f16_warp_body<NV>(p, blockIdx.x);
+}
+template <int NV>
+__global__ void __launch_bounds__(kPrepThreads) prep_f16_warp_pair_kernel(PrepParams pa, PrepParams pb, unsigned blocks_a) {
+  if (blockIdx.x < blocks_a) prep_f16_warp_body<NV>(pa, blockIdx.x);
+  else prep_f16_warp_body<NV>(pb, blockIdx.x - blocks_a);
+}
+
+static_assert(sizeof(PrepParams) <= sizeof(dali_ctx::prep_params), "dali_ctx::prep_params holds a PrepParams");
+
+// kind = 10 + float4 per lane (warp per row: 2 / 4 / 6 / 8) or 20 + float4 per thread (CTA per row: 1 .. 4)
+int launch_f16_kind(dali_ctx *ctx, int kind, const PrepParams &p, unsigned blocks, const PrepParams *pb, unsigned blocks_b) {
+  KTimer t(ctx, DALI_K_NORMALIZE);
+  const unsigned total = blocks + (pb ? blocks_b : 0u);
+#define DALI_PREP_CASE(K, SINGLE, PAIR)                                                       \
+  case K:                                                                                     \
+    if (pb) PAIR<<<total, kPrepThreads, 0, ctx->stream>>>(p, *pb, blocks);                    \
+    else SINGLE<<<total, kPrepThreads, 0, ctx->stream>>>(p);                                  \
+    break
+  switch (kind) {
+    DALI_PREP_CASE(12, prep_f16_warp_kernel<2>, prep_f16_warp_pair_kernel<2>);
+    DALI_PREP_CASE(14, prep_f16_warp_kernel<4>, prep_f16_warp_pair_kernel<4>);
+    DALI_PREP_CASE(16, prep_f16_warp_kernel<6>, prep_f16_warp_pair_kernel<6>);
+    DALI_PREP_CASE(18, prep_f16_warp_kernel<8>, prep_f16_warp_pair_kernel<8>);
+    DALI_PREP_CASE(21, prep_f16_kernel<1>, prep_f16_pair_kernel<1>);
+    DALI_PREP_CASE(22, prep_f16_kernel<2>, prep_f16_pair_kernel<2>);
+    DALI_PREP_CASE(23, prep_f16_kernel<3>, prep_f16_pair_kernel<3>);
+    DALI_PREP_CASE(24, prep_f16_kernel<4>, prep_f16_pair_kernel<4>);
+    default: return set_err(ctx, DALI_ERR_INVALID, "operand preparation: unknown kernel kind");
+  }
+#undef DALI_PREP_CASE
+  DALI_CUDA_OK(ctx, cudaGetLastError());
+  return DALI_OK;
+}
+
+int flush_pending_prep(dali_ctx *ctx) {
+  if (!ctx->prep_pending) return DALI_OK;
+  ctx->prep_pending = false;
+  PrepParams q;
+  std::memcpy(&q, ctx->prep_params, sizeof(PrepParams));
+  return launch_f16_kind(ctx, ctx->prep_kind, q, ctx->prep_blocks, nullptr, 0);
+}
+
 }  // namespace
+
+void prep_defer_begin(dali_ctx *ctx) { ctx->prep_defer = true; }
+int prep_defer_end(dali_ctx *ctx) {
+  ctx->prep_defer = false;
+  return flush_pending_prep(ctx);
+}
 
 // Grid of the fixed-point hi plane (0 = plain fp16 rounding); DALI_F16X3_GRID overrides (probes).
 float f16x3_hi_grid(int64_t) {
@@ -363,7 +427,6 @@ int launch_prep(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx
   PrepParams p{x, n, d, ldx, plane0, plane1, ldo, d_pad, rows_pad, do_normalize, round_mode,
                hgrid > 0.f ? 1.0f / hgrid : 0.f, hgrid, norms, sq,
                static_cast<__nv_bfloat16 *>(hi16), static_cast<__nv_bfloat16 *>(lo16), perm};
-  KTimer t(ctx, DALI_K_NORMALIZE);
   const bool vec = d % 4 == 0 && d_pad <= 4 * kPrepThreads * kVecCache && ldx % 4 == 0 && ldo % 4 == 0 &&
                    (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(plane0) & 15) == 0 &&
@@ -376,16 +439,28 @@ int launch_prep(dali_ctx *ctx, const float *x, int64_t n, int64_t d, int64_t ldx
     const int nvw = static_cast<int>((d_pad / 4 + 31) / 32);  // float4 per lane with one warp per row
     const unsigned gridw = static_cast<unsigned>((rows_pad + kPrepThreads / 32 - 1) / (kPrepThreads / 32));
     static const char *env_warp = getenv("DALI_PREP_WARP");  // 0: one CTA per row also for short rows
-    if (nvw <= 8 && !(env_warp && atoi(env_warp) == 0)) {
-      if (nvw <= 2) prep_f16_warp_kernel<2><<<gridw, kPrepThreads, 0, ctx->stream>>>(p);
-      else if (nvw <= 4) prep_f16_warp_kernel<4><<<gridw, kPrepThreads, 0, ctx->stream>>>(p);
-      else if (nvw <= 6) prep_f16_warp_kernel<6><<<gridw, kPrepThreads, 0, ctx->stream>>>(p);
-      else prep_f16_warp_kernel<8><<<gridw, kPrepThreads, 0, ctx->stream>>>(p);
-    } else if (nvec <= 1) prep_f16_kernel<1><<<grid, kPrepThreads, 0, ctx->stream>>>(p);
-    else if (nvec == 2) prep_f16_kernel<2><<<grid, kPrepThreads, 0, ctx->stream>>>(p);
-    else if (nvec == 3) prep_f16_kernel<3><<<grid, kPrepThreads, 0, ctx->stream>>>(p);
-    else prep_f16_kernel<4><<<grid, kPrepThreads, 0, ctx->stream>>>(p);
-  } else if (vec)
+    const bool warp_rows = nvw <= 8 && !(env_warp && atoi(env_warp) == 0);
+    const int kind = warp_rows ? 10 + (nvw <= 2 ? 2 : nvw <= 4 ? 4 : nvw <= 6 ? 6 : 8) : 20 + std::min(std::max(nvec, 1), 4);
+    const unsigned blocks = warp_rows ? gridw : grid;
+    if (ctx->prep_pending && ctx->prep_kind == kind) {  // the held-back operand and this one: one launch
+      ctx->prep_pending = false;
+      PrepParams first;
+      std::memcpy(&first, ctx->prep_params, sizeof(PrepParams));
+      return launch_f16_kind(ctx, kind, first, ctx->prep_blocks, &p, blocks);
+    }
+    if (int rc = flush_pending_prep(ctx)) return rc;
+    if (ctx->prep_defer) {
+      std::memcpy(ctx->prep_params, &p, sizeof(PrepParams));
+      ctx->prep_kind = kind;
+      ctx->prep_blocks = blocks;
+      ctx->prep_pending = true;
+      return DALI_OK;
+    }
+    return launch_f16_kind(ctx, kind, p, blocks, nullptr, 0);
+  }
+  if (int rc = flush_pending_prep(ctx)) return rc;  // (keeps the stream order of the preparations)
+  KTimer t(ctx, DALI_K_NORMALIZE);
+  if (vec)
     prep_rows_vec_kernel<<<grid, kPrepThreads, 0, ctx->stream>>>(p);
   else
     prep_rows_kernel<<<static_cast<unsigned>(rows_pad), kPrepThreads, 0, ctx->stream>>>(p);
