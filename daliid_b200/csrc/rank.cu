@@ -476,6 +476,9 @@ constexpr int kV3MaxChunks = 1;  // threshold chunks per query the split launch 
 #ifndef DALI_V3B_LOG2NB
 #define DALI_V3B_LOG2NB 12  // table bins of the many-threshold (CAP = 256) variant
 #endif
+#ifndef DALI_V3_SPREAD_TOTALS
+#define DALI_V3_SPREAD_TOTALS 1  // totals: plane transposes spread over the CTA's warps (0: one warp per word)
+#endif
 #ifndef DALI_V3_MINB
 #define DALI_V3_MINB 8  // resident 256-thread CTAs per SM the tight variant is compiled for (32 registers)
 #endif
@@ -840,6 +843,16 @@ rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
         }
       }
       __syncthreads();
+#if DALI_V3_SPREAD_TOTALS
+      // the NW * PLR plane transposes are dealt out to all warps (one warp doing them in a row is a
+      // chain of 5 PLR dependent shuffles while the others wait at the next barrier); hist[] is zero
+#pragma unroll 1
+      for (int job = warp; job < NW * PLR; job += THREADS / 32) {
+        const int w = job / PLR, k2 = job - w * PLR;
+        const uint32_t v = static_cast<uint32_t>(__popc(warp_bit_transpose(part[(w * kPartPlanes + k2) * 32 + lane], lane))) << k2;
+        if (v) atomicAdd(&hist[32 * w + lane], v);
+      }
+#else
       if (warp < NW) {
         uint32_t total = 0;
 #pragma unroll
@@ -847,6 +860,7 @@ rank_count_v3_kernel(const float *__restrict__ dist, int64_t ld, int64_t g0, int
           total += static_cast<uint32_t>(__popc(warp_bit_transpose(part[(warp * kPartPlanes + k2) * 32 + lane], lane))) << k2;
         hist[32 * warp + lane] = total;
       }
+#endif
     };
     // many thresholds: 8-bit private counters in shared memory, bucket b = #{thresholds <= element}
     auto run_bytes = [&]() {
